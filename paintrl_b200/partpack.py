@@ -1,0 +1,143 @@
+"""Constant per-part tables ("part pack") consumed by the batched paint step.
+
+The reference derives these once per environment at load time
+(PaintRLEnv/bullet_paint_wrapper.py:622-648 texel tables, 599-620 kd-tree inputs, 816-832 /
+922-963 silhouette table, 740-809 start points).  A pack is the
+frozen output of that preprocessing for one (part, texture size); it is stored as an `.npz`
+under `paintrl_b200/data/partpacks/` and handed to the C ABI as a `PaintrlPartPack`.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+
+from . import _capi
+
+PACK_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'partpacks')
+
+# robot_gym_env.py:106-117 Part_Dict
+PART_DICT = {
+    0: ['door_test.urdf', 9148],
+    1: ['square.urdf', 14350],
+    2: ['door_lf.urdf', 0],
+    3: ['door_lr.urdf', 0],
+    4: ['door_rf.urdf', 0],
+    5: ['door_rr.urdf', 17000],
+    6: ['roof.urdf', 0],
+    7: ['bonnet.urdf', 0],
+    8: ['door_rr_big.urdf', 0],
+    9: ['test.urdf', 9148],
+}
+
+START_POINT_MODES = ('fixed', 'anchor', 'edge', 'all')
+
+
+class PartPack(object):
+    """Host-side (NumPy) view of one part's constant tables."""
+
+    _ARRAYS = ('ranges', 'planes_n', 'planes_off', 'front_ij', 'front_pos', 'vertices',
+               'vtri_start', 'vtri_idx', 'tri_a', 'tri_v0', 'tri_v1', 'tri_d00', 'tri_d01',
+               'tri_d11', 'tri_inv_denom', 'tri_n', 'grid_lo', 'grid_hi')
+
+    def __init__(self, meta, arrays):
+        self.meta = dict(meta)
+        self.arrays = arrays
+        for name in self._ARRAYS:
+            dtype = np.int32 if arrays[name].dtype.kind in 'iu' else np.float64
+            setattr(self, name, np.ascontiguousarray(arrays[name], dtype=dtype))
+        self.length_width_ratio = float(arrays['length_width_ratio'])
+        self.width = int(self.meta['width'])
+        self.height = int(self.meta['height'])
+        self.axes = tuple(int(a) for a in self.meta['axes'])
+        self.max_points = float(self.meta['max_points'])
+        self.starts = {m: np.ascontiguousarray(arrays['start_' + m], dtype=np.float64)
+                       for m in START_POINT_MODES if 'start_' + m in arrays}
+
+    # ------------------------------------------------------------------------------ io
+    @classmethod
+    def load(cls, path):
+        with np.load(path, allow_pickle=False) as z:
+            arrays = {k: z[k] for k in z.files}
+        meta = json.loads(str(arrays.pop('meta')))
+        return cls(meta, arrays)
+
+    @classmethod
+    def for_part(cls, part_no, width=240, height=240):
+        """Pack of `Part_Dict[part_no]` (robot_gym_env.py:106-117) at a texture size."""
+        if part_no not in PART_DICT:
+            raise KeyError(part_no)
+        name = os.path.splitext(PART_DICT[part_no][0])[0]
+        path = os.path.join(PACK_DIR, '%s_%dx%d.npz' % (name, width, height))
+        if not os.path.isfile(path):
+            raise FileNotFoundError(
+                'no part pack for Part_NO=%d (%s) at %dx%d: %s' % (part_no, name, width, height, path))
+        return cls.load(path)
+
+    @property
+    def n_texels(self):
+        return self.front_pos.shape[0]
+
+    def start_points(self, mode):
+        """`Part.get_start_points(mode)` (bullet_paint_wrapper.py:749-783): [S,2,3] (pos, normal)."""
+        if mode not in self.starts:
+            raise ValueError('START_POINT_MODE %r not in %s' % (mode, sorted(self.starts)))
+        return self.starts[mode]
+
+    def status_init(self, color_mode):
+        """First-channel value of a fresh front texel (bullet_paint_wrapper.py:586)."""
+        key = 'status_init_rgb' if color_mode == 'RGB' else 'status_init_hsi'
+        values = np.unique(self.arrays[key])
+        if values.size != 1:
+            raise ValueError('non-uniform initial front colour: %s' % values)
+        return int(values[0])
+
+    def init_texture(self, color_mode):
+        key = 'init_texture_rgb' if color_mode == 'RGB' else 'init_texture_hsi'
+        return np.array(self.arrays[key], dtype=np.uint8)
+
+    # ------------------------------------------------------------------------------ C view
+    def to_c(self, start_mode, color_mode):
+        """Build the `PaintrlPartPack` struct; returns (struct, keepalive)."""
+        starts = self.start_points(start_mode)
+        start_pos = np.ascontiguousarray(starts[:, 0, :])
+        start_normal = np.ascontiguousarray(starts[:, 1, :])
+        keep = [start_pos, start_normal]
+
+        def dptr(a):
+            keep.append(a)
+            return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+        def iptr(a):
+            keep.append(a)
+            return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+
+        p = _capi.PaintrlPartPack()
+        p.abi_version = _capi.PAINTRL_ABI_VERSION
+        p.width, p.height = self.width, self.height
+        p.axis0, p.axis1 = self.axes
+        p.n_texels = self.n_texels
+        p.texel_pos = dptr(self.front_pos)
+        p.texel_ij = iptr(self.front_ij)
+        p.n_planes = self.planes_n.shape[0]
+        p.plane_n = dptr(self.planes_n)
+        p.plane_off = dptr(self.planes_off)
+        p.n_vertices = self.vertices.shape[0]
+        p.vertices = dptr(self.vertices)
+        p.vtri_start = iptr(self.vtri_start)
+        p.vtri_idx = iptr(self.vtri_idx)
+        p.n_tris = self.tri_a.shape[0]
+        p.tri_a, p.tri_v0, p.tri_v1 = dptr(self.tri_a), dptr(self.tri_v0), dptr(self.tri_v1)
+        p.tri_d00, p.tri_d01, p.tri_d11 = dptr(self.tri_d00), dptr(self.tri_d01), dptr(self.tri_d11)
+        p.tri_inv_denom = dptr(self.tri_inv_denom)
+        p.tri_n = dptr(self.tri_n)
+        p.range0_min, p.range0_max = float(self.ranges[0, 0]), float(self.ranges[0, 1])
+        p.range1_min, p.range1_max = float(self.ranges[1, 0]), float(self.ranges[1, 1])
+        p.length_width_ratio = self.length_width_ratio
+        p.grid_granularity = self.grid_lo.shape[0]
+        p.grid_lo, p.grid_hi = dptr(self.grid_lo), dptr(self.grid_hi)
+        p.n_starts = start_pos.shape[0]
+        p.start_pos = dptr(start_pos)
+        p.start_normal = dptr(start_normal)
+        p.status_init = self.status_init(color_mode)
+        return p, keep
