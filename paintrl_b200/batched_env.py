@@ -1,0 +1,223 @@
+"""`BatchedPaintEnv` -- thousands of independent PaintRL environments resident on one GPU.
+
+Host-side mirror of the reference's per-environment interface
+(PaintRLEnv/robot_gym_env.py:207-422, PaintRLEnv/bullet_paint_wrapper.py:1327-1400) over the C ABI
+of include/paintrl.h.  PyTorch is used for device memory and streams only; every result comes
+from the CUDA library (there is no CPU fallback -- construction fails without it).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _capi
+from .config import EnvConfig
+from .partpack import PartPack
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class BatchedPaintEnv(object):
+    """`num_envs` PaintGymEnv instances sharing one part and one configuration.
+
+    Args mirror PaintGymEnv (robot_gym_env.py:207-208, 126-157): `extra_config` carries the same
+    keys; the class attributes ACTION_MODE/ACTION_SHAPE/DISCRETE_GRANULARITY/OBS_MODE/OBS_GRAD are
+    keyword arguments here because one process can hold several configurations.
+    """
+
+    def __init__(self, num_envs, extra_config=None, action_mode='discrete', action_shape=1,
+                 discrete_granularity=4, obs_mode='section', obs_grad=4, device=None,
+                 auto_reset=False, seed=0, pack=None, texture_size=(240, 240), max_possible_point=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('paintrl_b200 needs a CUDA device: there is no CPU fallback')
+        self.cfg = extra_config if isinstance(extra_config, EnvConfig) else EnvConfig(
+            extra_config, action_mode=action_mode, action_shape=action_shape,
+            discrete_granularity=discrete_granularity, obs_mode=obs_mode, obs_grad=obs_grad,
+            auto_reset=auto_reset, seed=seed, max_possible_point=max_possible_point)
+        self.pack = pack if pack is not None else PartPack.for_part(self.cfg.part_no, *texture_size)
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        if self.device.type != 'cuda':
+            raise RuntimeError('paintrl_b200 runs on CUDA devices only')
+        self.num_envs = int(num_envs)
+        self._lib = _capi.lib()
+        cpack, keep_pack = self.pack.to_c(self.cfg.start_point_mode, self.cfg.color_mode)
+        ccfg, keep_cfg = self.cfg.to_c(self.pack.max_points)
+        handle = ctypes.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        with torch.cuda.device(index):
+            _capi.check(self._lib.paintrl_create(ctypes.byref(cpack), ctypes.byref(ccfg), self.num_envs,
+                                                 index, ctypes.byref(handle)))
+        del keep_pack, keep_cfg     # paintrl_create copied everything it needs
+        self._h = handle
+        self.obs_dim = int(self._lib.paintrl_obs_dim(self._h))
+        self.action_dim = int(self._lib.paintrl_action_dim(self._h))
+        self.n_texels = int(self._lib.paintrl_num_texels(self._h))
+        self.n_starts = self.pack.start_points(self.cfg.start_point_mode).shape[0]
+        B, f64 = self.num_envs, torch.float64
+        dev = self.device
+        self.obs = torch.zeros(B, self.obs_dim, dtype=f64, device=dev)
+        self.next_obs = torch.zeros(B, self.obs_dim, dtype=f64, device=dev)
+        self.reward = torch.zeros(B, dtype=f64, device=dev)
+        self.penalty = torch.zeros(B, dtype=f64, device=dev)
+        self.actual = torch.zeros(B, dtype=f64, device=dev)
+        self.done = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self.new_texels = torch.zeros(B, dtype=torch.int32, device=dev)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.paintrl_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _ids(self, env_ids):
+        if env_ids is None:
+            return None, self.num_envs
+        ids = torch.as_tensor(env_ids, dtype=torch.int32, device=self.device).contiguous()
+        return ids, int(ids.numel())
+
+    # ------------------------------------------------------------------ reference call mirror
+    def reset(self, start_index=None, env_ids=None):
+        """PaintGymEnv.reset (robot_gym_env.py:370-387).  `start_index` plays the role of the
+        reference's `randint(0, len(start_points) - 1)` draw (0 in rollout mode); None uses the
+        library's seeded stream.  Returns the first observations [n, obs_dim]."""
+        ids, n = self._ids(env_ids)
+        si = None
+        if start_index is not None:
+            si = torch.as_tensor(start_index, dtype=torch.int32, device=self.device)
+            si = si.expand(n).contiguous() if si.dim() == 0 else si.contiguous()
+            if si.numel() != n:
+                raise ValueError('start_index must have one entry per reset environment')
+        out = self.obs if ids is None else torch.zeros(n, self.obs_dim, dtype=torch.float64, device=self.device)
+        _capi.check(self._lib.paintrl_reset(self._h, _ptr(ids), n, _ptr(si), _ptr(out), self._stream()))
+        if ids is None:
+            self.next_obs.copy_(out)
+        return out
+
+    def set_pose(self, pos, normal, env_ids=None):
+        """Robot.reset(pose) (robot.py:366-372) as spiral.py:28-38 uses it."""
+        ids, n = self._ids(env_ids)
+        pos = torch.as_tensor(pos, dtype=torch.float64, device=self.device).expand(n, 3).contiguous()
+        normal = torch.as_tensor(normal, dtype=torch.float64, device=self.device).expand(n, 3).contiguous()
+        out = torch.zeros(n, self.obs_dim, dtype=torch.float64, device=self.device)
+        _capi.check(self._lib.paintrl_set_pose(self._h, _ptr(ids), n, _ptr(pos), _ptr(normal), _ptr(out),
+                                               self._stream()))
+        return out
+
+    def step(self, actions, reset_start_index=None):
+        """PaintGymEnv.step for all environments (robot_gym_env.py:349-368), device tensors in and
+        out, asynchronous on the current stream.  Returns (obs, actual_reward, done, info) where
+        info = {'reward', 'penalty'} like robot_gym_env.py:368 plus 'next_obs' / 'new_texels'."""
+        if self.cfg.action_mode == 'discrete':
+            a = torch.as_tensor(actions, device=self.device).to(torch.int64).contiguous()
+            if a.numel() != self.num_envs:
+                raise ValueError('expected %d discrete actions' % self.num_envs)
+        else:
+            a = torch.as_tensor(actions, device=self.device).to(torch.float64).contiguous()
+            if a.numel() != self.num_envs * self.action_dim:
+                raise ValueError('expected actions of shape [%d, %d]' % (self.num_envs, self.action_dim))
+        rs = None
+        if reset_start_index is not None:
+            rs = torch.as_tensor(reset_start_index, dtype=torch.int32, device=self.device).contiguous()
+        _capi.check(self._lib.paintrl_step(
+            self._h, _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.penalty), _ptr(self.actual),
+            _ptr(self.done), _ptr(self.new_texels), _ptr(self.next_obs) if self.cfg.auto_reset else None,
+            _ptr(rs), self._stream()))
+        info = {'reward': self.reward, 'penalty': self.penalty, 'new_texels': self.new_texels,
+                'next_obs': self.next_obs if self.cfg.auto_reset else self.obs}
+        return self.obs, self.actual, self.done, info
+
+    def step_host(self, actions, out=None):
+        """The same step through HOST buffers (paintrl_step_host): actions are copied host->device
+        and obs / reward / penalty / actual / done device->host inside the call."""
+        B = self.num_envs
+        if self.cfg.action_mode == 'discrete':
+            a = np.ascontiguousarray(actions, dtype=np.int64).reshape(B)
+        else:
+            a = np.ascontiguousarray(actions, dtype=np.float64).reshape(B, self.action_dim)
+        if out is None:
+            out = self.host_buffers()
+        nxt = out.get('next_obs')
+        _capi.check(self._lib.paintrl_step_host(
+            self._h, ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(out['obs'].ctypes.data),
+            ctypes.c_void_p(out['reward'].ctypes.data), ctypes.c_void_p(out['penalty'].ctypes.data),
+            ctypes.c_void_p(out['actual'].ctypes.data), ctypes.c_void_p(out['done'].ctypes.data),
+            ctypes.c_void_p(nxt.ctypes.data) if nxt is not None else None, self._stream()))
+        return out
+
+    def host_buffers(self, pinned=True):
+        """Host result buffers for `step_host` (pinned by default so the copies are asynchronous)."""
+        B = self.num_envs
+
+        def buf(shape, dtype):
+            t = torch.zeros(shape, dtype=dtype, pin_memory=pinned)
+            return t.numpy()
+        return {'obs': buf((B, self.obs_dim), torch.float64), 'reward': buf((B,), torch.float64),
+                'penalty': buf((B,), torch.float64), 'actual': buf((B,), torch.float64),
+                'done': buf((B,), torch.uint8), 'next_obs': buf((B, self.obs_dim), torch.float64)}
+
+    # ------------------------------------------------------------------ state
+    def get_state(self, env_ids=None, status=True):
+        ids, n = self._ids(env_ids)
+        dev = self.device
+        st = torch.zeros(n, self.n_texels, dtype=torch.int16, device=dev) if status else None
+        pose = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+        quat = torch.zeros(n, 4, dtype=torch.float64, device=dev)
+        scal = torch.zeros(n, 8, dtype=torch.float64, device=dev)
+        _capi.check(self._lib.paintrl_get_state(self._h, _ptr(ids), n, _ptr(st), _ptr(pose), _ptr(quat),
+                                                _ptr(scal), self._stream()))
+        keys = ('total_reward', 'total_return', 'step_counter', 'term_counter', 'last_on_part',
+                'terminate', 'last_angle', 'angle_diff')
+        out = {'status': st, 'pose': pose, 'quat': quat, 'scalars': scal}
+        out.update({k: scal[:, i] for i, k in enumerate(keys)})
+        return out
+
+    def set_state(self, env_ids=None, status=None, pose=None, quat=None, scalars=None):
+        ids, n = self._ids(env_ids)
+
+        def prep(t, dtype, shape):
+            if t is None:
+                return None
+            t = torch.as_tensor(t, device=self.device).to(dtype).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError('expected shape %s, got %s' % (shape, tuple(t.shape)))
+            return t
+        st = prep(status, torch.int16, (n, self.n_texels))
+        po = prep(pose, torch.float64, (n, 3))
+        qu = prep(quat, torch.float64, (n, 4))
+        sc = prep(scalars, torch.float64, (n, 8))
+        _capi.check(self._lib.paintrl_set_state(self._h, _ptr(ids), n, _ptr(st), _ptr(po), _ptr(qu), _ptr(sc),
+                                                self._stream()))
+
+    def job_status(self):
+        """get_job_status per env (bullet_paint_wrapper.py:727-732)."""
+        out = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        _capi.check(self._lib.paintrl_job_status(self._h, _ptr(out), self._stream()))
+        return out
+
+    def job_limit(self):
+        """get_job_limit (bullet_paint_wrapper.py:734-735)."""
+        return self.n_texels
+
+    def stats(self):
+        s = _capi.PaintrlStats()
+        torch.cuda.synchronize(self.device)
+        _capi.check(self._lib.paintrl_stats(self._h, ctypes.byref(s)))
+        return {'env_steps': int(s.env_steps), 'episodes_ended': int(s.episodes_ended),
+                'footprint_texels': int(s.footprint_texels), 'kernel_launches': int(s.kernel_launches)}

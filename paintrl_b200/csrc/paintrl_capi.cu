@@ -1,0 +1,568 @@
+// paintrl_capi.cu -- host side of the C ABI in include/paintrl.h: builds the device tables from a
+// PaintrlPartPack, owns per-environment state, launches the kernels of paintrl_kernels.cuh.
+// Built with: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (paintrl_b200/build.py)
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/paintrl.h"
+#include "paintrl_kernels.cuh"
+
+using namespace paintrl;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t err__ = (expr);                                                          \
+        if (err__ != cudaSuccess)                                                            \
+            return fail(PAINTRL_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+struct DeviceArena {
+    std::vector<void *> ptrs;
+    ~DeviceArena() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t upload(const std::vector<T> &host, const T **out) {
+        void *p = nullptr;
+        size_t bytes = std::max<size_t>(host.size() * sizeof(T), 16);
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(p);
+        if (!host.empty()) {
+            e = cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return e;
+        }
+        *out = reinterpret_cast<const T *>(p);
+        return cudaSuccess;
+    }
+    cudaError_t alloc(void **out, size_t bytes) {
+        cudaError_t e = cudaMalloc(out, std::max<size_t>(bytes, 16));
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+};
+
+}  // namespace
+
+struct PaintrlEngine {
+    int device = 0;
+    int num_envs = 0;
+    int color = 0;
+    int rank_bytes = 2;
+    DevPack pk{};
+    DevConfig cfg{};
+    DeviceArena arena;
+    EnvState *states = nullptr;
+    void *planes = nullptr;          // [num_envs][n_pad] uint8 (RGB) or int16 (HSI)
+    unsigned long long *stats = nullptr;
+    // staging for the host-buffer entry points
+    void *stage_actions = nullptr;
+    double *stage_obs = nullptr, *stage_next_obs = nullptr, *stage_scalars = nullptr;   // scalars: reward|penalty|actual
+    uint8_t *stage_done = nullptr;
+    unsigned long long launches = 0;
+};
+
+namespace {
+
+double axis_of(const double *p, int a) { return p[a]; }
+
+// Host-side construction of the acceleration tables (see DESIGN.md "Data layout in HBM").
+int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlConfig *cfg) {
+    DevPack &pk = e->pk;
+    const int n = pack->n_texels;
+    const int a0 = pack->axis0, a1 = pack->axis1;
+    pk.n_texels = n;
+    pk.n_pad = ((n + 127) / 128) * 128;
+    pk.axis0 = a0;
+    pk.axis1 = a1;
+    pk.status_init = pack->status_init;
+
+    // ---- collision planes
+    pk.n_planes = pack->n_planes;
+    std::vector<double4> planes(pack->n_planes);
+    for (int i = 0; i < pack->n_planes; ++i)
+        planes[i] = make_double4(pack->plane_n[3 * i], pack->plane_n[3 * i + 1], pack->plane_n[3 * i + 2], pack->plane_off[i]);
+    CUDA_TRY(e->arena.upload(planes, &pk.planes));
+
+    // ---- vertex grid (vertices parked at IRRELEVANT_POSE (10,10,10) can never be nearest; skip them)
+    std::vector<int> front;
+    for (int v = 0; v < pack->n_vertices; ++v) {
+        const double *p = pack->vertices + 3 * v;
+        if (p[0] == 10.0 && p[1] == 10.0 && p[2] == 10.0) continue;
+        front.push_back(v);
+    }
+    if (front.empty()) return fail(PAINTRL_E_INVALID, "part pack has no front-side vertices");
+    double vmin0 = INFINITY, vmax0 = -INFINITY, vmin1 = INFINITY, vmax1 = -INFINITY;
+    for (int v : front) {
+        const double *p = pack->vertices + 3 * v;
+        vmin0 = std::min(vmin0, p[a0]); vmax0 = std::max(vmax0, p[a0]);
+        vmin1 = std::min(vmin1, p[a1]); vmax1 = std::max(vmax1, p[a1]);
+    }
+    double area = std::max((vmax0 - vmin0) * (vmax1 - vmin1), 1e-12);
+    pk.vg_cs = std::max(2.0 * std::sqrt(area / (double)front.size()), 1e-6);
+    pk.vg_inv = 1.0 / pk.vg_cs;
+    pk.vg_o0 = vmin0;
+    pk.vg_o1 = vmin1;
+    pk.vg_nx = std::min(4096, (int)std::floor((vmax0 - vmin0) * pk.vg_inv) + 1);
+    pk.vg_ny = std::min(4096, (int)std::floor((vmax1 - vmin1) * pk.vg_inv) + 1);
+    {
+        const int cells = pk.vg_nx * pk.vg_ny;
+        std::vector<int> cell_of(front.size());
+        std::vector<int> start(cells + 1, 0);
+        for (size_t i = 0; i < front.size(); ++i) {
+            const double *p = pack->vertices + 3 * front[i];
+            int cx = std::min(std::max((int)std::floor((p[a0] - pk.vg_o0) * pk.vg_inv), 0), pk.vg_nx - 1);
+            int cy = std::min(std::max((int)std::floor((p[a1] - pk.vg_o1) * pk.vg_inv), 0), pk.vg_ny - 1);
+            cell_of[i] = cy * pk.vg_nx + cx;
+            start[cell_of[i] + 1]++;
+        }
+        for (int c = 0; c < cells; ++c) start[c + 1] += start[c];
+        std::vector<int> order(front.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cell_of[x] < cell_of[y]; });
+        std::vector<double> vx(front.size()), vy(front.size()), vz(front.size());
+        std::vector<int> vid(front.size());
+        for (size_t j = 0; j < order.size(); ++j) {
+            int v = front[order[j]];
+            vx[j] = pack->vertices[3 * v];
+            vy[j] = pack->vertices[3 * v + 1];
+            vz[j] = pack->vertices[3 * v + 2];
+            vid[j] = v;
+        }
+        CUDA_TRY(e->arena.upload(start, &pk.vg_start));
+        CUDA_TRY(e->arena.upload(vx, &pk.vx));
+        CUDA_TRY(e->arena.upload(vy, &pk.vy));
+        CUDA_TRY(e->arena.upload(vz, &pk.vz));
+        CUDA_TRY(e->arena.upload(vid, &pk.vid));
+    }
+    {
+        std::vector<int> vs(pack->vtri_start, pack->vtri_start + pack->n_vertices + 1);
+        std::vector<int> vi(pack->vtri_idx, pack->vtri_idx + vs.back());
+        for (int t : vi)
+            if (t < 0 || t >= pack->n_tris) return fail(PAINTRL_E_INVALID, "vtri_idx out of range");
+        CUDA_TRY(e->arena.upload(vs, &pk.vtri_start));
+        CUDA_TRY(e->arena.upload(vi, &pk.vtri_idx));
+        std::vector<double> tri((size_t)pack->n_tris * 16);
+        for (int t = 0; t < pack->n_tris; ++t) {
+            double *o = &tri[(size_t)t * 16];
+            for (int k = 0; k < 3; ++k) {
+                o[k] = pack->tri_a[3 * t + k];
+                o[3 + k] = pack->tri_v0[3 * t + k];
+                o[6 + k] = pack->tri_v1[3 * t + k];
+                o[13 + k] = pack->tri_n[3 * t + k];
+            }
+            o[9] = pack->tri_d00[t]; o[10] = pack->tri_d01[t]; o[11] = pack->tri_d11[t]; o[12] = pack->tri_inv_denom[t];
+        }
+        CUDA_TRY(e->arena.upload(tri, &pk.tri));
+    }
+
+    // ---- texel bins: cell = PAINT_RADIUS, rows along axis1; texels sorted by cell (stable)
+    double tmin0 = INFINITY, tmax0 = -INFINITY, tmin1 = INFINITY, tmax1 = -INFINITY;
+    for (int i = 0; i < n; ++i) {
+        const double *p = pack->texel_pos + 3 * i;
+        tmin0 = std::min(tmin0, p[a0]); tmax0 = std::max(tmax0, p[a0]);
+        tmin1 = std::min(tmin1, p[a1]); tmax1 = std::max(tmax1, p[a1]);
+    }
+    pk.tb_inv = 1.0 / kPaintRadius;
+    pk.tb_o0 = tmin0;
+    pk.tb_o1 = tmin1;
+    pk.tb_nx = (int)std::floor((tmax0 - tmin0) * pk.tb_inv) + 1;
+    pk.tb_ny = (int)std::floor((tmax1 - tmin1) * pk.tb_inv) + 1;
+    if ((long long)pk.tb_nx * pk.tb_ny > (1 << 24)) return fail(PAINTRL_E_INVALID, "texel bin grid too large");
+    std::vector<int> order(n);
+    {
+        const int cells = pk.tb_nx * pk.tb_ny;
+        std::vector<int> cell_of(n), start(cells + 1, 0);
+        for (int i = 0; i < n; ++i) {
+            const double *p = pack->texel_pos + 3 * i;
+            int cx = std::min(std::max((int)std::floor((p[a0] - pk.tb_o0) * pk.tb_inv), 0), pk.tb_nx - 1);
+            int cy = std::min(std::max((int)std::floor((p[a1] - pk.tb_o1) * pk.tb_inv), 0), pk.tb_ny - 1);
+            cell_of[i] = cy * pk.tb_nx + cx;
+            start[cell_of[i] + 1]++;
+        }
+        for (int c = 0; c < cells; ++c) start[c + 1] += start[c];
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cell_of[x] < cell_of[y]; });
+        CUDA_TRY(e->arena.upload(start, &pk.tb_start));
+    }
+    {
+        std::vector<double> tx(pk.n_pad, 1e30), ty(pk.n_pad, 1e30), tz(pk.n_pad, 1e30);
+        for (int j = 0; j < n; ++j) {
+            const double *p = pack->texel_pos + 3 * order[j];
+            tx[j] = p[0]; ty[j] = p[1]; tz[j] = p[2];
+        }
+        CUDA_TRY(e->arena.upload(tx, &pk.tx));
+        CUDA_TRY(e->arena.upload(ty, &pk.ty));
+        CUDA_TRY(e->arena.upload(tz, &pk.tz));
+        CUDA_TRY(e->arena.upload(order, &pk.sorted_to_pack));
+    }
+
+    // ---- coordinate ranks for the 4-sector observation
+    {
+        std::vector<double> u0(n), u1(n);
+        for (int i = 0; i < n; ++i) {
+            u0[i] = pack->texel_pos[3 * i + a0];
+            u1[i] = pack->texel_pos[3 * i + a1];
+        }
+        std::sort(u0.begin(), u0.end());
+        u0.erase(std::unique(u0.begin(), u0.end()), u0.end());
+        std::sort(u1.begin(), u1.end());
+        u1.erase(std::unique(u1.begin(), u1.end()), u1.end());
+        pk.n_uniq0 = (int)u0.size();
+        pk.n_uniq1 = (int)u1.size();
+        e->rank_bytes = (u0.size() < 65535 && u1.size() < 65535) ? 2 : 4;
+        pk.rank_bytes = e->rank_bytes;
+        auto rank_of = [](const std::vector<double> &u, double v) {
+            return (unsigned)(std::lower_bound(u.begin(), u.end(), v) - u.begin());
+        };
+        if (e->rank_bytes == 2) {
+            std::vector<uint16_t> r0(pk.n_pad, 0xFFFF), r1(pk.n_pad, 0xFFFF);
+            for (int j = 0; j < n; ++j) {
+                const double *p = pack->texel_pos + 3 * order[j];
+                r0[j] = (uint16_t)rank_of(u0, p[a0]);
+                r1[j] = (uint16_t)rank_of(u1, p[a1]);
+            }
+            const uint16_t *d0, *d1;
+            CUDA_TRY(e->arena.upload(r0, &d0));
+            CUDA_TRY(e->arena.upload(r1, &d1));
+            pk.rank0 = d0; pk.rank1 = d1;
+        } else {
+            std::vector<uint32_t> r0(pk.n_pad, 0xFFFFFFFFu), r1(pk.n_pad, 0xFFFFFFFFu);
+            for (int j = 0; j < n; ++j) {
+                const double *p = pack->texel_pos + 3 * order[j];
+                r0[j] = rank_of(u0, p[a0]);
+                r1[j] = rank_of(u1, p[a1]);
+            }
+            const uint32_t *d0, *d1;
+            CUDA_TRY(e->arena.upload(r0, &d0));
+            CUDA_TRY(e->arena.upload(r1, &d1));
+            pk.rank0 = d0; pk.rank1 = d1;
+        }
+        CUDA_TRY(e->arena.upload(u0, &pk.uniq0));
+        CUDA_TRY(e->arena.upload(u1, &pk.uniq1));
+    }
+
+    // ---- silhouette table, ranges
+    pk.grid_granularity = pack->grid_granularity;
+    {
+        std::vector<double> lo(pack->grid_lo, pack->grid_lo + pack->grid_granularity);
+        std::vector<double> hi(pack->grid_hi, pack->grid_hi + pack->grid_granularity);
+        CUDA_TRY(e->arena.upload(lo, &pk.grid_lo));
+        CUDA_TRY(e->arena.upload(hi, &pk.grid_hi));
+    }
+    pk.range0_min = pack->range0_min; pk.range0_max = pack->range0_max;
+    pk.range1_min = pack->range1_min; pk.range1_max = pack->range1_max;
+    pk.lwr = pack->length_width_ratio;
+
+    // ---- grid-observation cells (bullet_paint_wrapper.py:1072-1112)
+    if (cfg->obs_mode == PAINTRL_OBS_GRID) {
+        const int g = cfg->obs_grad, vgran = pack->grid_granularity;
+        const int v_interval = (int)((double)vgran / (double)g);
+        if (v_interval <= 0) return fail(PAINTRL_E_INVALID, "OBS_GRAD larger than GRID_GRANULARITY");
+        const double axis_2_step = (pack->range1_max - pack->range1_min) / vgran;
+        std::vector<uint16_t> gcell(pk.n_pad, 0xFFFF);
+        std::vector<int> gtotal((size_t)g * g, 0);
+        for (int j = 0; j < n; ++j) {
+            const double *p = pack->texel_pos + 3 * order[j];
+            double yq = (p[a1] - pack->range1_min) / axis_2_step;
+            if (!(yq > -1.0)) return fail(PAINTRL_E_INVALID, "texel below the silhouette table (reference KeyError)");
+            int y_grid = std::min(vgran - 1, (int)yq);
+            double range = pack->grid_hi[y_grid] - pack->grid_lo[y_grid];
+            int x_grid = 0;
+            if (range != 0) {
+                double x_step = range / g;
+                double xq = (p[a0] - pack->grid_lo[y_grid]) / x_step;
+                if (!(xq > -1.0)) return fail(PAINTRL_E_INVALID, "texel left of its silhouette row (reference KeyError)");
+                x_grid = std::min(g - 1, (int)xq);
+            }
+            int v_target = y_grid / v_interval;
+            if (v_target >= g)
+                return fail(PAINTRL_E_INVALID, "OBS_GRAD does not tile GRID_GRANULARITY (reference KeyError)");
+            gcell[j] = (uint16_t)(v_target * g + x_grid);
+            gtotal[v_target * g + x_grid]++;
+        }
+        CUDA_TRY(e->arena.upload(gcell, &pk.gcell));
+        CUDA_TRY(e->arena.upload(gtotal, &pk.gtotal));
+    }
+
+    // ---- start points
+    pk.n_starts = pack->n_starts;
+    {
+        std::vector<double> sp(pack->start_pos, pack->start_pos + 3 * (size_t)pack->n_starts);
+        std::vector<double> sn(pack->start_normal, pack->start_normal + 3 * (size_t)pack->n_starts);
+        CUDA_TRY(e->arena.upload(sp, &pk.start_pos));
+        CUDA_TRY(e->arena.upload(sn, &pk.start_normal));
+    }
+    return PAINTRL_OK;
+}
+
+int obs_dim_of(const PaintrlConfig *cfg) {
+    switch (cfg->obs_mode) {
+        case PAINTRL_OBS_SECTION: return cfg->obs_grad + 2;
+        case PAINTRL_OBS_GRID: return cfg->obs_grad * cfg->obs_grad;
+        case PAINTRL_OBS_SIMPLE: return 2;
+        default: return cfg->obs_grad + 1;
+    }
+}
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+template <typename F>
+int dispatch(PaintrlEngine *e, F &&f) {
+    // (colour mode, rank width) -> kernel instantiation
+    if (e->color == 0) return e->rank_bytes == 2 ? f(std::integral_constant<int, 0>{}, uint16_t{}) : f(std::integral_constant<int, 0>{}, uint32_t{});
+    return e->rank_bytes == 2 ? f(std::integral_constant<int, 1>{}, uint16_t{}) : f(std::integral_constant<int, 1>{}, uint32_t{});
+}
+
+int launch_check(PaintrlEngine *e, const char *what) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(PAINTRL_E_CUDA, std::string(what) + ": " + cudaGetErrorString(err));
+    e->launches++;
+    return PAINTRL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t paintrl_abi_version(void) { return PAINTRL_ABI_VERSION; }
+const char *paintrl_last_error(void) { return g_error.c_str(); }
+
+int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_t num_envs, int32_t device,
+                   PaintrlHandle *out) {
+    if (!pack || !cfg || !out) return fail(PAINTRL_E_INVALID, "null argument");
+    if (pack->abi_version != PAINTRL_ABI_VERSION || cfg->abi_version != PAINTRL_ABI_VERSION)
+        return fail(PAINTRL_E_INVALID, "ABI version mismatch");
+    if (num_envs <= 0) return fail(PAINTRL_E_INVALID, "num_envs must be positive");
+    if (pack->n_texels <= 0 || pack->n_planes <= 0 || pack->n_vertices <= 0 || pack->n_tris <= 0 || pack->n_starts <= 0)
+        return fail(PAINTRL_E_INVALID, "empty part pack table");
+    if (pack->axis0 < 0 || pack->axis0 > 2 || pack->axis1 < 0 || pack->axis1 > 2 || pack->axis0 == pack->axis1)
+        return fail(PAINTRL_E_INVALID, "bad principal axes");
+    if (cfg->action_mode == PAINTRL_ACTION_DISCRETE && (cfg->discrete_granularity <= 0 || !cfg->discrete_table))
+        return fail(PAINTRL_E_INVALID, "discrete actions need discrete_granularity > 0 and a discrete_table");
+    if (cfg->action_mode == PAINTRL_ACTION_CONTINUOUS && cfg->action_shape != 1 && cfg->action_shape != 2)
+        return fail(PAINTRL_E_INVALID, "ACTION_SHAPE must be 1 or 2");
+    if (cfg->obs_mode < 0 || cfg->obs_mode > 3 || cfg->obs_grad <= 0) return fail(PAINTRL_E_INVALID, "bad observation mode");
+    const int od = obs_dim_of(cfg);
+    if (od > kMaxObs) return fail(PAINTRL_E_INVALID, "observation larger than 128 entries is not supported");
+    if (cfg->color_mode == PAINTRL_COLOR_HSI && (pack->status_init > 32767 || pack->status_init < -32768))
+        return fail(PAINTRL_E_INVALID, "status_init out of int16 range");
+    if (cfg->color_mode == PAINTRL_COLOR_RGB && (pack->status_init > 255 || pack->status_init < 0))
+        return fail(PAINTRL_E_INVALID, "status_init out of uint8 range");
+
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return fail(PAINTRL_E_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(err));
+    if (device < 0 || device >= count) return fail(PAINTRL_E_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+
+    PaintrlEngine *e = new PaintrlEngine();
+    e->device = device;
+    e->num_envs = num_envs;
+    e->color = cfg->color_mode == PAINTRL_COLOR_RGB ? 0 : 1;
+    int rc = build_tables(e, pack, cfg);
+    if (rc != PAINTRL_OK) { delete e; return rc; }
+
+    DevConfig &c = e->cfg;
+    c.action_mode = cfg->action_mode;
+    c.action_shape = cfg->action_mode == PAINTRL_ACTION_CONTINUOUS ? cfg->action_shape : 1;
+    c.discrete_granularity = cfg->discrete_granularity;
+    c.discrete_table = nullptr;
+    if (cfg->action_mode == PAINTRL_ACTION_DISCRETE) {
+        std::vector<double> t(cfg->discrete_table, cfg->discrete_table + 3 * (size_t)cfg->discrete_granularity);
+        if (e->arena.upload(t, &c.discrete_table) != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, "upload discrete table"); }
+    }
+    c.obs_mode = cfg->obs_mode; c.obs_grad = cfg->obs_grad; c.obs_dim = od;
+    c.color_mode = cfg->color_mode; c.termination_mode = cfg->termination_mode;
+    c.switch_threshold = cfg->switch_threshold;
+    c.expected_episode_length = cfg->expected_episode_length;
+    c.episode_max_length = cfg->episode_max_length;
+    c.turning_penalty = cfg->turning_penalty; c.overlap_penalty = cfg->overlap_penalty;
+    c.max_possible_point = cfg->max_possible_point;
+    c.auto_reset = cfg->auto_reset;
+    c.seed = cfg->seed;
+
+    const size_t elem = e->color == 0 ? 1 : 2;
+    const size_t plane_bytes = (size_t)num_envs * e->pk.n_pad * elem;
+    const size_t adim = c.action_mode == 0 ? sizeof(long long) : sizeof(double) * c.action_shape;
+    bool ok = e->arena.alloc((void **)&e->states, sizeof(EnvState) * (size_t)num_envs) == cudaSuccess &&
+              e->arena.alloc(&e->planes, plane_bytes) == cudaSuccess &&
+              e->arena.alloc((void **)&e->stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              e->arena.alloc(&e->stage_actions, adim * num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&e->stage_obs, sizeof(double) * od * (size_t)num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&e->stage_next_obs, sizeof(double) * od * (size_t)num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&e->stage_scalars, sizeof(double) * 3 * (size_t)num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&e->stage_done, (size_t)num_envs) == cudaSuccess;
+    if (!ok) { delete e; return fail(PAINTRL_E_CUDA, "device allocation failed (state / status planes)"); }
+    cudaMemset(e->states, 0, sizeof(EnvState) * (size_t)num_envs);
+    cudaMemset(e->planes, 0, plane_bytes);
+    cudaMemset(e->stats, 0, 4 * sizeof(unsigned long long));
+    err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, cudaGetErrorString(err)); }
+    *out = e;
+    return PAINTRL_OK;
+}
+
+void paintrl_destroy(PaintrlHandle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    delete h;
+}
+
+int32_t paintrl_num_envs(PaintrlHandle h) { return h ? h->num_envs : 0; }
+int32_t paintrl_obs_dim(PaintrlHandle h) { return h ? h->cfg.obs_dim : 0; }
+int32_t paintrl_action_dim(PaintrlHandle h) { return h ? h->cfg.action_shape : 0; }
+int32_t paintrl_num_texels(PaintrlHandle h) { return h ? h->pk.n_texels : 0; }
+int32_t paintrl_status_bytes(PaintrlHandle h) { return h ? (h->color == 0 ? 1 : 2) : 0; }
+
+static int reset_like(PaintrlHandle h, const int32_t *env_ids, int32_t n, const int32_t *start_idx, const double *pos,
+                      const double *normal, double *obs, void *stream, int mode) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (n <= 0 || n > h->num_envs) return fail(PAINTRL_E_INVALID, "bad env count");
+    if (!env_ids && n != h->num_envs) return fail(PAINTRL_E_INVALID, "env_ids == NULL requires n == num_envs");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    return dispatch(h, [&](auto color, auto rank) {
+        constexpr int C = decltype(color)::value;
+        typedef decltype(rank) R;
+        typedef typename StatusT<C>::type S;
+        reset_kernel<C, R><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(
+            h->pk, h->cfg, h->states, reinterpret_cast<S *>(h->planes), env_ids, n, start_idx, pos, normal, obs, mode);
+        return launch_check(h, "reset_kernel");
+    });
+}
+
+int paintrl_reset(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, const int32_t *start_idx_dev, double *obs_dev,
+                  void *stream) {
+    return reset_like(h, env_ids_dev, n, start_idx_dev, nullptr, nullptr, obs_dev, stream, 0);
+}
+
+int paintrl_set_pose(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, const double *pos_dev,
+                     const double *normal_dev, double *obs_dev, void *stream) {
+    if (!pos_dev || !normal_dev) return fail(PAINTRL_E_INVALID, "null pose");
+    return reset_like(h, env_ids_dev, n, nullptr, pos_dev, normal_dev, obs_dev, stream, 1);
+}
+
+int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, double *reward_dev, double *penalty_dev,
+                 double *actual_dev, uint8_t *done_dev, int32_t *new_texels_dev, double *next_obs_dev,
+                 const int32_t *reset_start_idx_dev, void *stream) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (!actions_dev || !obs_dev || !reward_dev || !penalty_dev || !actual_dev || !done_dev)
+        return fail(PAINTRL_E_INVALID, "null I/O buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    StepIO io;
+    io.actions = actions_dev; io.obs = obs_dev; io.reward = reward_dev; io.penalty = penalty_dev;
+    io.actual = actual_dev; io.done = done_dev; io.new_texels = new_texels_dev;
+    io.next_obs = h->cfg.auto_reset ? next_obs_dev : nullptr;
+    io.reset_start_idx = reset_start_idx_dev;
+    io.stats = h->stats;
+    const int blocks = (h->num_envs + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    return dispatch(h, [&](auto color, auto rank) {
+        constexpr int C = decltype(color)::value;
+        typedef decltype(rank) R;
+        typedef typename StatusT<C>::type S;
+        step_kernel<C, R><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(
+            h->pk, h->cfg, h->states, reinterpret_cast<S *>(h->planes), h->num_envs, io);
+        return launch_check(h, "step_kernel");
+    });
+}
+
+int paintrl_step_host(PaintrlHandle h, const void *actions_host, double *obs_host, double *reward_host,
+                      double *penalty_host, double *actual_host, uint8_t *done_host, double *next_obs_host,
+                      void *stream) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (!actions_host || !obs_host || !reward_host || !penalty_host || !actual_host || !done_host)
+        return fail(PAINTRL_E_INVALID, "null I/O buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = as_stream(stream);
+    const size_t nenv = (size_t)h->num_envs;
+    const size_t abytes = (h->cfg.action_mode == 0 ? sizeof(long long) : sizeof(double) * h->cfg.action_shape) * nenv;
+    const size_t obytes = sizeof(double) * h->cfg.obs_dim * nenv;
+    CUDA_TRY(cudaMemcpyAsync(h->stage_actions, actions_host, abytes, cudaMemcpyHostToDevice, s));
+    double *sc = h->stage_scalars;
+    int rc = paintrl_step(h, h->stage_actions, h->stage_obs, sc, sc + nenv, sc + 2 * nenv, h->stage_done, nullptr,
+                          next_obs_host ? h->stage_next_obs : nullptr, nullptr, stream);
+    if (rc != PAINTRL_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(obs_host, h->stage_obs, obytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(reward_host, sc, sizeof(double) * nenv, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(penalty_host, sc + nenv, sizeof(double) * nenv, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(actual_host, sc + 2 * nenv, sizeof(double) * nenv, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(done_host, h->stage_done, nenv, cudaMemcpyDeviceToHost, s));
+    if (next_obs_host) {
+        const double *src = h->cfg.auto_reset ? h->stage_next_obs : h->stage_obs;
+        CUDA_TRY(cudaMemcpyAsync(next_obs_host, src, obytes, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PAINTRL_OK;
+}
+
+int paintrl_get_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, int16_t *status_dev, double *pose_dev,
+                      double *quat_dev, double *scalars_dev, void *stream) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (n <= 0 || n > h->num_envs || (!env_ids_dev && n != h->num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
+    CUDA_TRY(cudaSetDevice(h->device));
+    dim3 grid(std::max(1, std::min(64, (h->pk.n_texels + 255) / 256)), n);
+    if (h->color == 0)
+        get_state_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(h->pk, h->states, (const uint8_t *)h->planes, env_ids_dev, n,
+                                                                   status_dev, pose_dev, quat_dev, scalars_dev);
+    else
+        get_state_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(h->pk, h->states, (const int16_t *)h->planes, env_ids_dev, n,
+                                                                   status_dev, pose_dev, quat_dev, scalars_dev);
+    return launch_check(h, "get_state_kernel");
+}
+
+int paintrl_set_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, const int16_t *status_dev,
+                      const double *pose_dev, const double *quat_dev, const double *scalars_dev, void *stream) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (n <= 0 || n > h->num_envs || (!env_ids_dev && n != h->num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
+    CUDA_TRY(cudaSetDevice(h->device));
+    dim3 grid(std::max(1, std::min(64, (h->pk.n_texels + 255) / 256)), n);
+    if (h->color == 0)
+        set_state_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(h->pk, h->states, (uint8_t *)h->planes, env_ids_dev, n,
+                                                                   status_dev, pose_dev, quat_dev, scalars_dev);
+    else
+        set_state_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(h->pk, h->states, (int16_t *)h->planes, env_ids_dev, n,
+                                                                   status_dev, pose_dev, quat_dev, scalars_dev);
+    return launch_check(h, "set_state_kernel");
+}
+
+int paintrl_job_status(PaintrlHandle h, int32_t *painted_dev, void *stream) {
+    if (!h || !painted_dev) return fail(PAINTRL_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int blocks = (h->num_envs + 3) / 4;
+    if (h->color == 0)
+        job_status_kernel<0><<<blocks, 128, 0, as_stream(stream)>>>(h->pk, (const uint8_t *)h->planes, h->num_envs, painted_dev);
+    else
+        job_status_kernel<1><<<blocks, 128, 0, as_stream(stream)>>>(h->pk, (const int16_t *)h->planes, h->num_envs, painted_dev);
+    return launch_check(h, "job_status_kernel");
+}
+
+int paintrl_stats(PaintrlHandle h, PaintrlStats *out) {
+    if (!h || !out) return fail(PAINTRL_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long host[4];
+    CUDA_TRY(cudaMemcpy(host, h->stats, sizeof(host), cudaMemcpyDeviceToHost));
+    out->env_steps = host[0];
+    out->episodes_ended = host[1];
+    out->footprint_texels = host[2];
+    out->kernel_launches = h->launches;
+    return PAINTRL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+"""GPU parity, gate 2: batches of environments stepped by the CUDA engine and by the C
+restatement (oracle/paint_oracle.c, itself pinned to the golden traces) on the same seeded
+actions and start points, including same-step auto-reset."""
+import numpy as np
+import pytest
+import torch
+
+from paintrl_b200.config import EnvConfig
+from paintrl_b200.partpack import PartPack
+
+pytestmark = pytest.mark.gpu
+
+BASE = {'RENDER_HEIGHT': 720, 'RENDER_WIDTH': 960, 'Part_NO': 0, 'Expected_Episode_Length': 245,
+        'EPISODE_MAX_LENGTH': 245, 'TERMINATION_MODE': 'late', 'SWITCH_THRESHOLD': 0.9,
+        'START_POINT_MODE': 'anchor', 'TURNING_PENALTY': False, 'OVERLAP_PENALTY': False,
+        'COLOR_MODE': 'RGB'}
+
+CASES = {
+    # BASELINE config C2 semantics (door, RGB, anchor, discrete-4, section-4, late)
+    'c2_door': (dict(BASE), dict(), 192, 70),
+    # C3: sheet, HSI, penalties, hybrid
+    'c3_sheet_hsi': (dict(BASE, Part_NO=1, COLOR_MODE='HSI', TURNING_PENALTY=True, OVERLAP_PENALTY=True,
+                          TERMINATION_MODE='hybrid'), dict(), 96, 40),
+    # sheet HSI late: long overlapping walks (thickness saturation)
+    'sheet_hsi_late': (dict(BASE, Part_NO=1, COLOR_MODE='HSI', OVERLAP_PENALTY=True), dict(), 64, 120),
+    # C4 at 240x240: continuous-2, grid-4, all start points
+    'c4_door_grid': (dict(BASE, START_POINT_MODE='all'),
+                     dict(action_mode='continuous', action_shape=2, obs_mode='grid', obs_grad=4), 96, 50),
+    'door_discrete_obs': (dict(BASE, START_POINT_MODE='edge', TERMINATION_MODE='early',
+                               Expected_Episode_Length=600),
+                          dict(obs_mode='discrete', obs_grad=4, discrete_granularity=8), 64, 50),
+    'sheet_simple': (dict(BASE, Part_NO=1, START_POINT_MODE='all'), dict(obs_mode='simple'), 64, 60),
+}
+
+
+def _run_case(extra, kw, num_envs, steps, device, auto_reset=True):
+    from oracle.oracle import OracleBatch, action_directions
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    cfg = EnvConfig(extra, auto_reset=auto_reset, **kw)
+    pack = PartPack.for_part(cfg.part_no)
+    env = BatchedPaintEnv(num_envs, cfg, device=device, pack=pack)
+    ora = OracleBatch(pack, cfg, num_envs)
+    rng = np.random.default_rng(20261017)
+    n_starts = env.n_starts
+    start = rng.integers(0, n_starts, size=num_envs).astype(np.int32)
+    obs_g = env.reset(start).cpu().numpy()
+    obs_o = ora.reset(start)
+    continuous = cfg.action_mode == 'continuous'
+    tol = dict(rtol=1e-5, atol=1e-12)
+    assert np.array_equal(obs_g, obs_o)
+    episodes = 0
+    for t in range(steps):
+        if continuous:
+            acts = rng.uniform(-1, 1, size=(num_envs, cfg.action_dim))
+            # the oracle takes the unit directions NumPy computes (as the reference does); the
+            # engine computes them on the device from the raw actions
+        else:
+            acts = rng.integers(0, cfg.discrete_granularity, size=num_envs)
+        nxt = rng.integers(0, n_starts, size=num_envs).astype(np.int32)
+        o_g, a_g, d_g, info = env.step(acts, reset_start_index=nxt)
+        o_o, r_o, p_o, a_o, d_o = ora.step(acts)
+        o_g, a_g, d_g = o_g.cpu().numpy(), a_g.cpu().numpy(), d_g.cpu().numpy()
+        ctx = ('step', t)
+        assert np.array_equal(d_g, d_o), ctx
+        if continuous or cfg.color_mode != 'RGB':
+            assert np.allclose(o_g, o_o, **tol), ctx
+            assert np.allclose(info['reward'].cpu().numpy(), r_o, **tol), ctx
+            assert np.allclose(info['penalty'].cpu().numpy(), p_o, **tol), ctx
+            assert np.allclose(a_g, a_o, **tol), ctx
+        else:
+            assert np.array_equal(o_g, o_o), ctx
+            assert np.array_equal(info['reward'].cpu().numpy(), r_o), ctx
+            assert np.array_equal(info['penalty'].cpu().numpy(), p_o), ctx
+            assert np.array_equal(a_g, a_o), ctx
+        # status planes: bit-exact, before the oracle side applies the auto-reset
+        if t % 7 == 0 or t == steps - 1:
+            pre_reset = env.get_state()['status'].cpu().numpy()
+            for e in range(num_envs):
+                if not d_o[e] or not auto_reset:
+                    assert np.array_equal(pre_reset[e], ora.status(e)), ctx + (e,)
+        done_ids = np.flatnonzero(d_o)
+        if auto_reset and len(done_ids):
+            episodes += len(done_ids)
+            ro = ora.reset(nxt[done_ids], env_ids=list(done_ids))
+            ng = info['next_obs'].cpu().numpy()
+            assert np.allclose(ng[done_ids], ro, **tol) if continuous else np.array_equal(ng[done_ids], ro), ctx
+    env.close()
+    ora.close()
+    return episodes
+
+
+@pytest.mark.parametrize('case', sorted(CASES))
+def test_batch_matches_oracle(case, cuda_device):
+    extra, kw, num_envs, steps = CASES[case]
+    _run_case(extra, kw, num_envs, steps, cuda_device)
+
+
+def test_host_step_matches_device_step(cuda_device):
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    a = BatchedPaintEnv(32, dict(BASE), device=cuda_device)
+    b = BatchedPaintEnv(32, dict(BASE), device=cuda_device)
+    start = np.arange(32, dtype=np.int32) % 4
+    a.reset(start)
+    b.reset(start)
+    rng = np.random.default_rng(3)
+    out = b.host_buffers()
+    for _ in range(20):
+        acts = rng.integers(0, 4, size=32)
+        o, actual, done, info = a.step(acts)
+        b.step_host(acts, out)
+        assert np.array_equal(o.cpu().numpy(), out['obs'])
+        assert np.array_equal(actual.cpu().numpy(), out['actual'])
+        assert np.array_equal(done.cpu().numpy(), out['done'])
+        assert np.array_equal(info['reward'].cpu().numpy(), out['reward'])
+    a.close()
+    b.close()
