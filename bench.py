@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the batched paint-simulation step (BASELINE.json metric: batched env steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5] [--impl reference]
+
+One process per GPU (torchrun for N > 1), environments sharded by index, no collective on the
+step path.  A "step" is one `paintrl_step` over the whole per-GPU batch with random actions that
+are already resident in HBM; `value` = env-steps of all ranks / max-over-ranks device time.
+Prints ONE JSON line on rank 0 (see the driver contract in the task statement).
+
+Timing: W >= 3 warm-up steps; each timed step is bracketed by CUDA events on the launch stream
+and the L2 is flushed (a 512 MiB write) between timed steps, outside the event brackets, so every
+step starts with its status planes in HBM, not in the 126 MB L2; `ms_per_step` is the mean
+bracketed duration, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASE = {'RENDER_HEIGHT': 720, 'RENDER_WIDTH': 960, 'Part_NO': 0, 'Expected_Episode_Length': 245,
+        'EPISODE_MAX_LENGTH': 245, 'TERMINATION_MODE': 'late', 'SWITCH_THRESHOLD': 0.9,
+        'START_POINT_MODE': 'anchor', 'TURNING_PENALTY': False, 'OVERLAP_PENALTY': False,
+        'COLOR_MODE': 'RGB'}
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    'c2': dict(name='C2 door panel x4096 envs/GPU, RGB, START_POINT_MODE=anchor, random discrete-4 actions, '
+                    'OBS_MODE=section-4, late termination, auto-reset',
+               extra=dict(BASE), kw={}, envs_per_gpu=4096, scaling='weak'),
+    # configs[2]
+    'c3': dict(name='C3 quadratic sheet x16384 envs/GPU, HSI, turning+overlap penalties, hybrid termination',
+               extra=dict(BASE, Part_NO=1, COLOR_MODE='HSI', TURNING_PENALTY=True, OVERLAP_PENALTY=True,
+                          TERMINATION_MODE='hybrid'), kw={}, envs_per_gpu=16384, scaling='weak'),
+    # configs[4] env side: 65536 envs sharded over the GPUs (strong scaling)
+    'c5': dict(name='C5 door panel, 65536 envs sharded over N GPUs, C2 settings',
+               extra=dict(BASE), kw={}, envs_total=65536, scaling='strong'),
+}
+
+METRIC = 'batched env steps/sec'
+UNIT = 'env-steps/s'
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def algorithmic_bytes(status_bytes, n_front, obs_dim, act_dim, scan, u_mean, p_reset):
+    """B_alg per env-step."""
+    return (status_bytes * n_front * (1 if scan else 0) + 2 * status_bytes * u_mean + 8 * obs_dim + 8 * act_dim
+            + 40 + 2 * 160 + p_reset * status_bytes * n_front)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown'}
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.error = index, [], set(), None, None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop_evt.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.002)
+        except Exception as exc:      # pragma: no cover - depends on the box
+            self.error = repr(exc)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        out = {'sm_mhz': float(np.median(self.samples)) if self.samples else None, 'sm_max_mhz': self.max_mhz,
+               'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+        if self.error:
+            out['error'] = self.error
+        return out
+
+
+def physical_gpu_index(local_index):
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if vis:
+        try:
+            return int(vis.split(',')[local_index])
+        except (ValueError, IndexError):
+            return local_index
+    return local_index
+
+
+def cpu_baseline_sample(workload, seconds=12.0, threads=None):
+    """The oracle's C restatement (kind "port") on the host cores: a bounded sample of the same
+    workload (same part, config, start mode, random discrete actions, reset on done)."""
+    from oracle.oracle import OracleBatch
+    from paintrl_b200.config import EnvConfig
+    from paintrl_b200.partpack import PartPack
+    threads = threads or os.cpu_count() or 1
+    cfg = EnvConfig(workload['extra'], **workload['kw'])
+    pack = PartPack.for_part(cfg.part_no)
+    n_env = 16 * threads
+    ora = OracleBatch(pack, cfg, n_env, threads=threads)
+    rng = np.random.default_rng(1234)
+    n_starts = pack.start_points(cfg.start_point_mode).shape[0]
+    ora.reset(rng.integers(0, n_starts, size=n_env))
+    steps = 0
+    t0 = time.perf_counter()
+    while True:
+        if cfg.action_mode == 'discrete':
+            acts = rng.integers(0, cfg.discrete_granularity, size=n_env)
+        else:
+            acts = rng.uniform(-1, 1, size=(n_env, cfg.action_dim))
+        _, _, _, _, done = ora.step(acts)
+        ids = np.flatnonzero(done)
+        if len(ids):
+            ora.reset(rng.integers(0, n_starts, size=len(ids)), env_ids=list(ids))
+        steps += n_env
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+    ora.close()
+    return {'value': steps / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+            'sample': '%d envs x %d steps of the same workload (C restatement oracle/paint_oracle.c, OpenMP, '
+                      '%.1f s); the Python reference itself runs ~44 env-steps/s/core (BASELINE.md)'
+                      % (n_env, steps // n_env, dt)}
+
+
+def run_reference(args, workload, rank, world_size):
+    """--impl reference: the reference path's CPU implementation on the host cores (the oracle
+    port: the Python reference cannot travel to the GPU box), same config / metric / unit."""
+    if rank != 0:
+        return
+    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline_sample(workload, seconds=0.5)
+    samples = [cpu_baseline_sample(workload, seconds=per_step) for _ in range(max(1, min(args.steps, 5)))]
+    value = float(np.mean([s['value'] for s in samples]))
+    base = dict(samples[-1], value=value)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': None, 'higher_is_better': True,
+            'scaling': workload['scaling'], 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload['name']}, 'cpu_baseline': base,
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=500)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--envs', type=int, default=None, help='override environments per GPU')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-flush', action='store_true', help='keep the L2 warm between steps (not the headline)')
+    args = ap.parse_args()
+    workload = WORKLOADS[args.workload]
+
+    from paintrl_b200 import sharding
+    rank, local_rank, world_size = sharding.world()
+    if args.impl == 'reference':
+        run_reference(args, workload, rank, world_size)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    sharding.init_process_group()
+
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    from paintrl_b200.config import EnvConfig
+    if args.envs:
+        n_env = args.envs
+    elif 'envs_total' in workload:
+        lo, hi = sharding.shard_range(workload['envs_total'], rank, world_size)
+        n_env = hi - lo
+    else:
+        n_env = workload['envs_per_gpu']
+    cfg = EnvConfig(workload['extra'], auto_reset=True, seed=1234 + rank, **workload['kw'])
+    env = BatchedPaintEnv(n_env, cfg, device=device)
+
+    gen = torch.Generator(device=device)
+    gen.manual_seed(1234 + rank)
+    total = warmup + args.steps
+    if cfg.action_mode == 'discrete':
+        actions = torch.randint(0, cfg.discrete_granularity, (total, n_env), generator=gen, device=device,
+                                dtype=torch.int64)
+    else:
+        actions = torch.rand((total, n_env, cfg.action_dim), generator=gen, device=device, dtype=torch.float64) * 2 - 1
+    gs = torch.Generator(device=device)
+    gs.manual_seed(rank)
+    env.reset(torch.randint(0, env.n_starts, (n_env,), generator=gs, device=device, dtype=torch.int32))
+    flush = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=device)
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for i in range(warmup):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        env.step(actions[i])
+    barrier()
+    s0 = env.stats()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    sum_reward = torch.zeros((), dtype=torch.float64, device=device)
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(i & 0xff)
+        starts[i].record()
+        env.step(actions[warmup + i])
+        stops[i].record()
+    barrier()
+    wall_s = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    s1 = env.stats()
+    step_ms = np.array([a.elapsed_time(b) for a, b in zip(starts, stops)])
+    dev_ms = float(step_ms.sum())
+
+    # ---- end-to-end through the host-buffer API (pinned host actions in, results out, every step)
+    e2e_steps = max(10, min(args.steps, 200))
+    host_out = env.host_buffers(pinned=True)
+    host_actions = actions[warmup:warmup + e2e_steps].cpu().pin_memory().numpy()
+    for i in range(3):
+        env.step_host(host_actions[i], host_out)
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for i in range(e2e_steps):
+        env.step_host(host_actions[i], host_out)
+        checksum += float(host_out['actual'][0])
+    torch.cuda.synchronize(device)
+    e2e_s = time.perf_counter() - t0
+    act_bytes = int(host_actions[0].nbytes)
+    d2h_bytes = int(sum(host_out[k].nbytes for k in ('obs', 'reward', 'penalty', 'actual', 'done')))
+
+    # ---- reduce over ranks: max time, summed work
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=device)
+    w = torch.tensor([float(n_env)], dtype=torch.float64, device=device)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max = float(t[0]), float(t[1])
+    total_envs = int(w[0])
+    rollout = sharding.allreduce_stats({
+        'env_steps': s1['env_steps'] - s0['env_steps'], 'episodes': s1['episodes_ended'] - s0['episodes_ended'],
+        'new_texels': 0.0, 'max_step_ms': float(step_ms.max())}, device=device)
+
+    if rank == 0:
+        steps_done = s1['env_steps'] - s0['env_steps']
+        u_mean = (s1['footprint_texels'] - s0['footprint_texels']) / max(1, steps_done)
+        p_reset = (s1['episodes_ended'] - s0['episodes_ended']) / max(1, steps_done)
+        status_bytes = 1 if cfg.color_mode == 'RGB' else 2
+        b_alg = algorithmic_bytes(status_bytes, env.n_texels, env.obs_dim, cfg.action_dim,
+                                  cfg.obs_mode != 'simple', u_mean, p_reset)
+        kernel_ms = dev_ms / args.steps                      # rank 0's own mean launch duration
+        achieved = b_alg * n_env / (kernel_ms * 1e-3) / 1e9
+        peak, peak_src = measured_peaks()
+        value = total_envs * args.steps / (dev_ms_max * 1e-3)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world_size, 'steps': args.steps,
+            'warmup': warmup, 'ms_per_step': dev_ms_max / args.steps, 'higher_is_better': True,
+            'scaling': workload['scaling'], 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload['name'], 'envs_per_gpu': n_env, 'envs_total': total_envs,
+                       'n_front_texels': env.n_texels, 'status_bytes_per_texel': status_bytes,
+                       'obs_dim': env.obs_dim, 'l2': 'warm (no flush)' if flush is None else
+                       'flushed with a 512 MiB write between timed steps', 'timing': 'CUDA events per step, summed',
+                       'parallelism': 'env-sharded x%d, no step-path collective' % world_size},
+            'clocks': clocks,
+            'e2e': {'value': total_envs * e2e_steps / e2e_s_max, 'unit': UNIT, 'h2d_bytes_per_step': act_bytes,
+                    'd2h_bytes_per_step': d2h_bytes, 'steps': e2e_steps, 'api': 'BatchedPaintEnv.step_host -> paintrl_step_host'},
+            'gpu_launches': s1['kernel_launches'] - s0['kernel_launches'],
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': None, 'peak_source': peak_src, 'kernel': 'paintrl::step_kernel',
+                         'kernel_ms': kernel_ms, 'algorithmic_bytes_per_env_step': b_alg,
+                         'footprint_union_texels_mean': u_mean, 'p_reset': p_reset},
+            'rollout_stats': rollout, 'wall_s_timed_region': wall_s,
+        }
+        if world_size == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline_sample(workload)
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -198,6 +198,7 @@ typedef struct PaintrlStats {
     uint64_t episodes_ended;
     uint64_t footprint_texels;
     uint64_t kernel_launches;
+    uint64_t ray_full_scans;   /* rays that needed the full plane list (5 rays per env-step) */
 } PaintrlStats;
 int paintrl_stats(PaintrlHandle h, PaintrlStats *out);
 

@@ -74,11 +74,101 @@ struct PaintrlEngine {
     double *stage_obs = nullptr, *stage_next_obs = nullptr, *stage_scalars = nullptr;   // scalars: reward|penalty|actual
     uint8_t *stage_done = nullptr;
     unsigned long long launches = 0;
+    double ray_cell_planes_mean = 0.0;
 };
 
 namespace {
 
-double axis_of(const double *p, int a) { return p[a]; }
+// Host copy of the slab test (same formula as the device's; used only to sample the hull's front
+// surface while building the ray cells, so its rounding does not matter).
+bool host_ray(const PaintrlPartPack *pack, const double *frm, const double *d, double *t_hit) {
+    double t_in = -INFINITY, t_out = INFINITY;
+    for (int i = 0; i < pack->n_planes; ++i) {
+        const double *n = pack->plane_n + 3 * i;
+        double den = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
+        double num = pack->plane_off[i] - (n[0] * frm[0] + n[1] * frm[1] + n[2] * frm[2]);
+        if (den == 0.0) {
+            if (num < 0.0) return false;
+            continue;
+        }
+        double t = num / den;
+        if (den < 0.0) t_in = std::max(t_in, t);
+        else t_out = std::min(t_out, t);
+    }
+    if (!(t_in <= t_out) || !std::isfinite(t_in)) return false;
+    *t_hit = t_in;
+    return true;
+}
+
+// Ray-test cells (see ray_test in paintrl_device.cuh): a grid over (axis0, axis1); per cell the
+// depth range of the hull's front surface (sampled, padded) and the list of planes that are not
+// satisfied with margin at every point of the cell's box.  Only the list must be conservative;
+// the depth range merely decides how often the fast path is accepted.
+int build_ray_cells(PaintrlEngine *e, const PaintrlPartPack *pack) {
+    DevPack &pk = e->pk;
+    pk.rc_nx = pk.rc_ny = 0;
+    if (pack->n_planes >= 65535) return PAINTRL_OK;   // fast path disabled: plane ids are 16-bit
+    const int a0 = pack->axis0, a1 = pack->axis1, np = 3 - a0 - a1;
+    const double cs = kPaintRadius / 2, pad = 0.1;
+    const double o0 = pack->range0_min - pad, o1 = pack->range1_min - pad;
+    const int nx = (int)std::ceil((pack->range0_max + pad - o0) / cs), ny = (int)std::ceil((pack->range1_max + pad - o1) / cs);
+    if (nx <= 0 || ny <= 0 || (long long)nx * ny > (1 << 20)) return PAINTRL_OK;
+    const double kDepthPad = 0.005, kFootSlack = 1e-6, kMargin = 1e-9;
+    const int K = 4;
+    std::vector<int> start((size_t)nx * ny + 1, 0);
+    std::vector<uint16_t> idx;
+    std::vector<double> dlo((size_t)nx * ny, 0.0), dhi((size_t)nx * ny, 0.0);
+    double dir[3] = {0, 0, 0};
+    dir[np] = -1.0;   // the tool looks along -front_normal (bullet_paint_wrapper.py:500, 530)
+    for (int cy = 0; cy < ny; ++cy) {
+        for (int cx = 0; cx < nx; ++cx) {
+            const int cell = cy * nx + cx;
+            const double lo0 = o0 + cx * cs, hi0 = o0 + (cx + 1) * cs, lo1 = o1 + cy * cs, hi1 = o1 + (cy + 1) * cs;
+            double zmin = INFINITY, zmax = -INFINITY;
+            for (int i = 0; i < K; ++i) {
+                for (int j = 0; j < K; ++j) {
+                    double frm[3];
+                    frm[a0] = lo0 + (hi0 - lo0) * i / (K - 1);
+                    frm[a1] = lo1 + (hi1 - lo1) * j / (K - 1);
+                    frm[np] = 100.0;
+                    double t;
+                    if (host_ray(pack, frm, dir, &t)) {
+                        double depth = frm[np] - t;
+                        zmin = std::min(zmin, depth);
+                        zmax = std::max(zmax, depth);
+                    }
+                }
+            }
+            if (zmin <= zmax) {
+                zmin -= kDepthPad;
+                zmax += kDepthPad;
+                dlo[cell] = zmin;
+                dhi[cell] = zmax;
+                for (int p = 0; p < pack->n_planes; ++p) {
+                    const double *n = pack->plane_n + 3 * p;
+                    double worst = -INFINITY;
+                    for (int c = 0; c < 8; ++c) {
+                        double pt[3];
+                        pt[a0] = (c & 1) ? hi0 + kFootSlack : lo0 - kFootSlack;
+                        pt[a1] = (c & 2) ? hi1 + kFootSlack : lo1 - kFootSlack;
+                        pt[np] = (c & 4) ? zmax : zmin;
+                        worst = std::max(worst, n[0] * pt[0] + n[1] * pt[1] + n[2] * pt[2]);
+                    }
+                    if (worst > pack->plane_off[p] - kMargin) idx.push_back((uint16_t)p);
+                }
+            }
+            start[cell + 1] = (int)idx.size();
+        }
+    }
+    pk.rc_nx = nx; pk.rc_ny = ny;
+    pk.rc_o0 = o0; pk.rc_o1 = o1; pk.rc_inv = 1.0 / cs;
+    CUDA_TRY(e->arena.upload(start, &pk.rc_start));
+    CUDA_TRY(e->arena.upload(idx, &pk.rc_idx));
+    CUDA_TRY(e->arena.upload(dlo, &pk.rc_dlo));
+    CUDA_TRY(e->arena.upload(dhi, &pk.rc_dhi));
+    e->ray_cell_planes_mean = idx.empty() ? 0.0 : (double)idx.size() / std::max<size_t>(1, (size_t)nx * ny);
+    return PAINTRL_OK;
+}
 
 // Host-side construction of the acceleration tables (see DESIGN.md "Data layout in HBM").
 int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlConfig *cfg) {
@@ -97,6 +187,10 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
     for (int i = 0; i < pack->n_planes; ++i)
         planes[i] = make_double4(pack->plane_n[3 * i], pack->plane_n[3 * i + 1], pack->plane_n[3 * i + 2], pack->plane_off[i]);
     CUDA_TRY(e->arena.upload(planes, &pk.planes));
+    {
+        int rc = build_ray_cells(e, pack);
+        if (rc != PAINTRL_OK) return rc;
+    }
 
     // ---- vertex grid (vertices parked at IRRELEVANT_POSE (10,10,10) can never be nearest; skip them)
     std::vector<int> front;
@@ -195,8 +289,15 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
             start[cell_of[i] + 1]++;
         }
         for (int c = 0; c < cells; ++c) start[c + 1] += start[c];
+        // within a bin row texels are ordered by their axis0 coordinate: cells stay contiguous (the
+        // cell index is monotone in the coordinate) and every 16-texel chunk covers a narrow
+        // coordinate interval, which keeps the chunk rank boxes of the observation scan tight
         std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cell_of[x] < cell_of[y]; });
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+            int rx = cell_of[x] / pk.tb_nx, ry = cell_of[y] / pk.tb_nx;
+            if (rx != ry) return rx < ry;
+            return pack->texel_pos[3 * x + a0] < pack->texel_pos[3 * y + a0];
+        });
         CUDA_TRY(e->arena.upload(start, &pk.tb_start));
     }
     {
@@ -240,6 +341,22 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
             CUDA_TRY(e->arena.upload(r0, &d0));
             CUDA_TRY(e->arena.upload(r1, &d1));
             pk.rank0 = d0; pk.rank1 = d1;
+            std::vector<uint16_t> box((size_t)(pk.n_pad / 16) * 4);
+            for (int c = 0; c < pk.n_pad / 16; ++c) {
+                uint16_t b0 = 0xFFFF, b1 = 0, b2 = 0xFFFF, b3 = 0;
+                bool has_pad = false;
+                for (int k = 0; k < 16; ++k) {
+                    int j = c * 16 + k;
+                    if (j >= n) { has_pad = true; continue; }
+                    b0 = std::min(b0, r0[j]); b1 = std::max(b1, r0[j]);
+                    b2 = std::min(b2, r1[j]); b3 = std::max(b3, r1[j]);
+                }
+                if (has_pad) { b0 = 0xFFFF; b1 = 0; b2 = 0xFFFF; b3 = 0; }   // inverted box: never "pure"
+                box[4 * c] = b0; box[4 * c + 1] = b1; box[4 * c + 2] = b2; box[4 * c + 3] = b3;
+            }
+            const uint16_t *db;
+            CUDA_TRY(e->arena.upload(box, &db));
+            pk.chunk_box = db;
         } else {
             std::vector<uint32_t> r0(pk.n_pad, 0xFFFFFFFFu), r1(pk.n_pad, 0xFFFFFFFFu);
             for (int j = 0; j < n; ++j) {
@@ -251,6 +368,22 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
             CUDA_TRY(e->arena.upload(r0, &d0));
             CUDA_TRY(e->arena.upload(r1, &d1));
             pk.rank0 = d0; pk.rank1 = d1;
+            std::vector<uint32_t> box((size_t)(pk.n_pad / 16) * 4);
+            for (int c = 0; c < pk.n_pad / 16; ++c) {
+                uint32_t b0 = 0xFFFFFFFFu, b1 = 0, b2 = 0xFFFFFFFFu, b3 = 0;
+                bool has_pad = false;
+                for (int k = 0; k < 16; ++k) {
+                    int j = c * 16 + k;
+                    if (j >= n) { has_pad = true; continue; }
+                    b0 = std::min(b0, r0[j]); b1 = std::max(b1, r0[j]);
+                    b2 = std::min(b2, r1[j]); b3 = std::max(b3, r1[j]);
+                }
+                if (has_pad) { b0 = 0xFFFFFFFFu; b1 = 0; b2 = 0xFFFFFFFFu; b3 = 0; }
+                box[4 * c] = b0; box[4 * c + 1] = b1; box[4 * c + 2] = b2; box[4 * c + 3] = b3;
+            }
+            const uint32_t *db;
+            CUDA_TRY(e->arena.upload(box, &db));
+            pk.chunk_box = db;
         }
         CUDA_TRY(e->arena.upload(u0, &pk.uniq0));
         CUDA_TRY(e->arena.upload(u1, &pk.uniq1));
@@ -562,6 +695,7 @@ int paintrl_stats(PaintrlHandle h, PaintrlStats *out) {
     out->episodes_ended = host[1];
     out->footprint_texels = host[2];
     out->kernel_launches = h->launches;
+    out->ray_full_scans = host[3];
     return PAINTRL_OK;
 }
 

@@ -53,6 +53,12 @@ struct DevPack {
     // collision hull: (nx, ny, nz, off) per plane
     int n_planes;
     const double4 *planes;
+    // ray-test cells over (axis0, axis1): per cell the planes not trivially satisfied in its box
+    int rc_nx, rc_ny;
+    double rc_o0, rc_o1, rc_inv;
+    const int *rc_start;          // [rc_nx*rc_ny + 1]
+    const uint16_t *rc_idx;       // plane indices
+    const double *rc_dlo, *rc_dhi;  // depth (non-principal axis) range of each cell's box
     // nearest-vertex grid over (axis0, axis1): front vertices sorted by cell
     int vg_nx, vg_ny;
     double vg_o0, vg_o1, vg_cs, vg_inv;
@@ -70,6 +76,7 @@ struct DevPack {
     // section observation: rank of each sorted texel's axis0 / axis1 coordinate among the
     // sorted distinct values (0xFFFF / 0xFFFFFFFF marks padding)
     const void *rank0, *rank1;    // uint16_t or uint32_t [n_pad]
+    const void *chunk_box;        // [n_pad/16] rank bounding box (r0min, r0max, r1min, r1max) per 16-texel chunk
     int rank_bytes;
     int n_uniq0, n_uniq1;
     const double *uniq0, *uniq1;
@@ -162,18 +169,21 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
-// Exact slab test of the ray frm -> to against the hull half-spaces (shim S1), the plane loop
-// split across the warp; max/min are order-independent so the result is the serial one.
-__device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, const Vec3 &to, int lane, Vec3 &hit) {
-    double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
+// One pass of the slab test over a list of planes (all of them, or one cell's active list),
+// split across the warp; max/min are order-independent so the result equals the serial one.
+struct SlabResult { double t_in, t_out; bool outside; };
+
+template <bool INDEXED>
+__device__ __forceinline__ SlabResult slab_pass(const DevPack &pk, const Vec3 &frm, double d0, double d1, double d2,
+                                                int begin, int end, int lane) {
     double t_in = -INFINITY, t_out = INFINITY;
     bool outside = false;
-    for (int i = lane; i < pk.n_planes; i += 32) {
-        const double2 *p2 = reinterpret_cast<const double2 *>(pk.planes) + 2 * i;
+    for (int i = begin + lane; i < end; i += 32) {
+        int pi = INDEXED ? (int)__ldg(&pk.rc_idx[i]) : i;
+        const double2 *p2 = reinterpret_cast<const double2 *>(pk.planes) + 2 * pi;
         double2 lo = __ldg(p2), hi2 = __ldg(p2 + 1);
-        double4 pl = make_double4(lo.x, lo.y, hi2.x, hi2.y);
-        double den = (pl.x * d0 + pl.y * d1) + pl.z * d2;
-        double num = pl.w - ((pl.x * frm.x + pl.y * frm.y) + pl.z * frm.z);
+        double den = (lo.x * d0 + lo.y * d1) + hi2.x * d2;
+        double num = hi2.y - ((lo.x * frm.x + lo.y * frm.y) + hi2.x * frm.z);
         if (den == 0.0) {
             if (num < 0.0) outside = true;
         } else {
@@ -182,13 +192,56 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, con
             else t_out = fmin(t_out, t);
         }
     }
-    t_in = warp_max(t_in);
-    t_out = warp_min(t_out);
-    outside = __any_sync(kFull, outside);
-    if (outside || !(t_in <= t_out && 0.0 <= t_in && t_in <= 1.0)) return false;
-    hit.x = frm.x + d0 * t_in;
-    hit.y = frm.y + d1 * t_in;
-    hit.z = frm.z + d2 * t_in;
+    SlabResult r;
+    r.t_in = warp_max(t_in);
+    r.t_out = warp_min(t_out);
+    r.outside = __any_sync(kFull, outside);
+    return r;
+}
+
+// Exact slab test of the ray frm -> to against the hull half-spaces (shim S1).
+//
+// Fast path: the hull footprint is covered by a grid of cells over (axis0, axis1); each cell
+// lists the planes that are NOT satisfied with a safety margin everywhere in the cell's box
+// (footprint x the cell's depth range).  If the entry point h* found from one cell's list lies in
+// that same box, every unlisted plane j satisfies n_j.h* < off_j - margin, i.e. t_j < t* if it is
+// an entering plane and t_j > t* if it is an exiting one, so max/min over the list decide exactly
+// what max/min over all planes decide, and t* is the global t_in bit for bit.  Otherwise the
+// full plane list is scanned.  Either way the result is the serial slab test's.
+__device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, const Vec3 &to, int lane, Vec3 &hit,
+                                         int &full_scans) {
+    double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
+    SlabResult r;
+    bool accepted = false;
+    if (pk.rc_nx > 0) {
+        // the TCP hovers kHookDistance above the surface: first guess = the point that far along the ray
+        Vec3 g = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2 && !accepted; ++attempt) {
+            int cx = (int)floor((comp(g, pk.axis0) - pk.rc_o0) * pk.rc_inv);
+            int cy = (int)floor((comp(g, pk.axis1) - pk.rc_o1) * pk.rc_inv);
+            if (cx < 0 || cy < 0 || cx >= pk.rc_nx || cy >= pk.rc_ny) break;
+            int cell = cy * pk.rc_nx + cx;
+            int begin = __ldg(&pk.rc_start[cell]), end = __ldg(&pk.rc_start[cell + 1]);
+            if (end <= begin) break;
+            r = slab_pass<true>(pk, frm, d0, d1, d2, begin, end, lane);
+            if (!(r.t_in > -INFINITY) || !(r.t_in < INFINITY)) break;
+            Vec3 h = {frm.x + d0 * r.t_in, frm.y + d1 * r.t_in, frm.z + d2 * r.t_in};
+            int hx = (int)floor((comp(h, pk.axis0) - pk.rc_o0) * pk.rc_inv);
+            int hy = (int)floor((comp(h, pk.axis1) - pk.rc_o1) * pk.rc_inv);
+            double depth = comp(h, 3 - pk.axis0 - pk.axis1);
+            if (hx == cx && hy == cy && depth >= __ldg(&pk.rc_dlo[cell]) && depth <= __ldg(&pk.rc_dhi[cell])) accepted = true;
+            else g = h;
+        }
+    }
+    if (!accepted) {
+        r = slab_pass<false>(pk, frm, d0, d1, d2, 0, pk.n_planes, lane);
+        full_scans += 1;
+    }
+    if (r.outside || !(r.t_in <= r.t_out && 0.0 <= r.t_in && r.t_in <= 1.0)) return false;
+    hit.x = frm.x + d0 * r.t_in;
+    hit.y = frm.y + d1 * r.t_in;
+    hit.z = frm.z + d2 * r.t_in;
     return true;
 }
 

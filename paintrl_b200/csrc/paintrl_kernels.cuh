@@ -25,83 +25,174 @@ struct StepIO {
     int32_t *new_texels;
     double *next_obs;
     const int32_t *reset_start_idx;
-    unsigned long long *stats;   // [0] env steps, [1] episodes ended, [2] footprint texels
+    unsigned long long *stats;   // [0] env steps, [1] episodes ended, [2] footprint texels, [3] full-plane ray scans
 };
 
 __device__ __forceinline__ uint4 ldcg16(const void *p) { return __ldcg(reinterpret_cast<const uint4 *>(p)); }
 
 // ------------------------------------------------------------------------------ observation
-// Section observation with 4 sectors (bullet_paint_wrapper.py:1033-1061): classification by
-// precomputed coordinate ranks instead of FP64 subtraction: rx > 0 <=> rank >= hi0, rx < 0 <=>
-// rank < lo0, where [lo0, hi0) is the rank interval of texel coordinates equal to the pose's.
+// Section observation with 4 sectors (bullet_paint_wrapper.py:1033-1061).
+//
+// rx > 0 <=> rank >= hi, rx < 0 <=> rank < lo, where `rank` is the texel coordinate's index among
+// the sorted distinct coordinates of the part and [lo, hi) is the rank interval equal to the
+// pose's coordinate (found once per step by binary search): integer compares replace the FP64
+// subtraction and are exactly equivalent.  Texels are laid out in chunks of 16 (one 128-bit load
+// in RGB mode) with a precomputed rank bounding box per chunk; a chunk whose box lies strictly on
+// one side of the pose on both axes belongs wholly to one sector and is counted with byte-SIMD
+// popcounts, the others (the pose's row and column, ~15 %) are queued in shared memory and then
+// classified texel by texel, one queued chunk per lane.
 template <typename RankT>
-__device__ __forceinline__ void rank_bounds(const double *uniq, int n, double v, RankT &lo, RankT &hi) {
-    int a = 0, b = n;            // lower_bound
-    while (a < b) { int m = (a + b) >> 1; if (__ldg(&uniq[m]) < v) a = m + 1; else b = m; }
+__device__ __forceinline__ void rank_bounds(const double *uniq, int n, double v, int lane, RankT &lo, RankT &hi) {
+    // 32-ary search: every round each lane probes one pivot; ~3 rounds for 10^4 values
+    int a = 0, b = n;            // lower_bound: first index with uniq[i] >= v lies in [a, b]
+    while (b - a > 0) {
+        int span = b - a, step = (span + 31) >> 5;
+        int i = a + lane * step;
+        bool less = (i < b) && (__ldg(&uniq[i]) < v);
+        unsigned m = __ballot_sync(kFull, less);
+        int k = __popc(m);       // pivots 0..k-1 are < v (monotone)
+        int na = (k == 0) ? a : a + (k - 1) * step + 1;
+        int nb = (k == 32 || a + k * step >= b) ? b : a + k * step;
+        a = na; b = nb;
+        if (step == 1) break;
+    }
     int l = a;
-    b = n;                       // upper_bound
-    while (a < b) { int m = (a + b) >> 1; if (__ldg(&uniq[m]) <= v) a = m + 1; else b = m; }
+    int c = l, d = n;            // upper_bound from l
+    while (d - c > 0) {
+        int span = d - c, step = (span + 31) >> 5;
+        int i = c + lane * step;
+        bool le = (i < d) && (__ldg(&uniq[i]) <= v);
+        unsigned m = __ballot_sync(kFull, le);
+        int k = __popc(m);
+        int nc = (k == 0) ? c : c + (k - 1) * step + 1;
+        int nd = (k == 32 || c + k * step >= d) ? d : c + k * step;
+        c = nc; d = nd;
+        if (step == 1) break;
+    }
     lo = (RankT)l;
-    hi = (RankT)a;
+    hi = (RankT)c;
+}
+
+// number of painted (== 255) entries among the 16 status values of one chunk
+__device__ __forceinline__ int painted_in_word_u8(unsigned w) {
+    unsigned x = ~w;                                   // zero byte <=> painted
+    unsigned y = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    y = ~(y | x | 0x7F7F7F7Fu);                        // 0x80 in every zero byte, exact
+    return __popc(y);
+}
+__device__ __forceinline__ int painted_in_word_i16(unsigned w) {
+    unsigned x = w ^ 0x00FF00FFu;                      // zero halfword <=> value == 255
+    unsigned y = (x & 0x7FFF7FFFu) + 0x7FFF7FFFu;
+    y = ~(y | x | 0x7FFF7FFFu);                        // 0x8000 in every zero halfword, exact
+    return __popc(y);
+}
+template <int COLOR>
+__device__ __forceinline__ int painted_in_chunk(const typename StatusT<COLOR>::type *p) {
+    if (COLOR == 0) {
+        uint4 v = ldcg16(p);
+        return painted_in_word_u8(v.x) + painted_in_word_u8(v.y) + painted_in_word_u8(v.z) + painted_in_word_u8(v.w);
+    } else {
+        uint4 v = ldcg16(p), w = ldcg16(p + 8);
+        return painted_in_word_i16(v.x) + painted_in_word_i16(v.y) + painted_in_word_i16(v.z) + painted_in_word_i16(v.w) +
+               painted_in_word_i16(w.x) + painted_in_word_i16(w.y) + painted_in_word_i16(w.z) + painted_in_word_i16(w.w);
+    }
+}
+
+template <typename RankT> struct ChunkBox { RankT r0min, r0max, r1min, r1max; };
+
+constexpr int kMixedQueue = 128;   // per-warp queue of mixed chunks (ints, aliases the histogram area)
+
+// texel-by-texel classification of one chunk (lane-private); adds into 4x16-bit packed counters
+template <int COLOR, typename RankT>
+__device__ __forceinline__ void classify_chunk(const DevPack &pk, const typename StatusT<COLOR>::type *status, int chunk,
+                                               RankT lo0, RankT hi0, RankT lo1, RankT hi1,
+                                               unsigned long long &ptot, unsigned long long &popen) {
+    typedef typename StatusT<COLOR>::type S;
+    const RankT *r0 = reinterpret_cast<const RankT *>(pk.rank0) + (size_t)chunk * 16;
+    const RankT *r1 = reinterpret_cast<const RankT *>(pk.rank1) + (size_t)chunk * 16;
+    const RankT pad = (RankT)~(RankT)0;
+    RankT a0[16], a1[16];
+    S sv[16];
+    constexpr int kRankLoads = 16 * sizeof(RankT) / 16;
+#pragma unroll
+    for (int q = 0; q < kRankLoads; ++q) {
+        reinterpret_cast<uint4 *>(a0)[q] = __ldg(reinterpret_cast<const uint4 *>(r0) + q);
+        reinterpret_cast<uint4 *>(a1)[q] = __ldg(reinterpret_cast<const uint4 *>(r1) + q);
+    }
+#pragma unroll
+    for (int q = 0; q < (int)(16 * sizeof(S) / 16); ++q)
+        reinterpret_cast<uint4 *>(sv)[q] = ldcg16(status + (size_t)chunk * 16 + q * (16 / sizeof(S)));
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+        RankT x = a0[e], y = a1[e];
+        bool px = x >= hi0, nx = x < lo0, py = y >= hi1, ny = y < lo1;
+        bool skip = (x == pad) || !(px || nx || py || ny);
+        int q = (px && py) ? 0 : ((nx && py) ? 1 : ((nx && ny) ? 2 : 3));
+        unsigned long long one = skip ? 0ull : (1ull << (16 * q));
+        ptot += one;
+        popen += ((int)sv[e] != kPainted) ? one : 0ull;
+    }
 }
 
 template <int COLOR, typename RankT>
 __device__ __forceinline__ void section4_counts(const DevPack &pk, const typename StatusT<COLOR>::type *status,
-                                                const Vec3 &pose, int lane, int tot[4], int open[4]) {
-    typedef typename StatusT<COLOR>::type S;
+                                                const Vec3 &pose, int lane, int *queue /*smem, kMixedQueue ints*/,
+                                                int tot[4], int open[4]) {
     RankT lo0, hi0, lo1, hi1;
-    rank_bounds<RankT>(pk.uniq0, pk.n_uniq0, comp(pose, pk.axis0), lo0, hi0);
-    rank_bounds<RankT>(pk.uniq1, pk.n_uniq1, comp(pose, pk.axis1), lo1, hi1);
-    const RankT *r0 = reinterpret_cast<const RankT *>(pk.rank0);
-    const RankT *r1 = reinterpret_cast<const RankT *>(pk.rank1);
-    const RankT pad = (RankT)~(RankT)0;
-    constexpr int kPer = 16 / sizeof(S);          // status elements per 128-bit load
-    unsigned long long ptot = 0, popen = 0;       // 4 x 16-bit packed per-lane counters
-    int flushed_tot[4] = {0, 0, 0, 0}, flushed_open[4] = {0, 0, 0, 0};
-    int since_flush = 0;
-    for (int j0 = lane * kPer; j0 < pk.n_pad; j0 += 32 * kPer) {
-        uint4 raw = ldcg16(status + j0);
-        const S *sv = reinterpret_cast<const S *>(&raw);
-        RankT a0[kPer], a1[kPer];
-        constexpr int kRankLoads = kPer * sizeof(RankT) / 16;
+    rank_bounds<RankT>(pk.uniq0, pk.n_uniq0, comp(pose, pk.axis0), lane, lo0, hi0);
+    rank_bounds<RankT>(pk.uniq1, pk.n_uniq1, comp(pose, pk.axis1), lane, lo1, hi1);
+    const ChunkBox<RankT> *boxes = reinterpret_cast<const ChunkBox<RankT> *>(pk.chunk_box);
+    const int n_chunks = pk.n_pad >> 4;
+    // per-lane accumulators: pure chunks counted as (#chunks, open texels) per sector
+    int pure_chunks[4] = {0, 0, 0, 0}, pure_open[4] = {0, 0, 0, 0};
+    unsigned long long ptot = 0, popen = 0;   // texel-wise path, 4 x 16-bit fields
+    int mix_tot[4] = {0, 0, 0, 0}, mix_open[4] = {0, 0, 0, 0};
+    int queued = 0;                            // warp-uniform
+    auto drain = [&]() {
+        __syncwarp();
+        for (int base = 0; base < queued; base += 32) {
+            if (base + lane < queued)
+                classify_chunk<COLOR, RankT>(pk, status, queue[base + lane], lo0, hi0, lo1, hi1, ptot, popen);
+        }
 #pragma unroll
-        for (int q = 0; q < (kRankLoads > 0 ? kRankLoads : 1); ++q) {
-            if (kRankLoads > 0) {
-                reinterpret_cast<uint4 *>(a0)[q] = __ldg(reinterpret_cast<const uint4 *>(r0 + j0) + q);
-                reinterpret_cast<uint4 *>(a1)[q] = __ldg(reinterpret_cast<const uint4 *>(r1 + j0) + q);
+        for (int q = 0; q < 4; ++q) {          // fields hold at most 16 * (kMixedQueue/32) = 64 each
+            mix_tot[q] += (int)((ptot >> (16 * q)) & 0xffff);
+            mix_open[q] += (int)((popen >> (16 * q)) & 0xffff);
+        }
+        ptot = popen = 0;
+        queued = 0;
+        __syncwarp();
+    };
+    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+        const int c = c0 + lane;
+        bool mixed = false;
+        if (c < n_chunks) {
+            ChunkBox<RankT> bx = boxes[c];
+            bool nx = bx.r0max < lo0, px = bx.r0min >= hi0, ny = bx.r1max < lo1, py = bx.r1min >= hi1;
+            if ((nx || px) && (ny || py) && bx.r0min <= bx.r0max) {   // inverted box = chunk with padding
+                int painted = painted_in_chunk<COLOR>(status + (size_t)c * 16);
+                int q = py ? (px ? 0 : 1) : (px ? 3 : 2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    pure_chunks[k] += (q == k) ? 1 : 0;
+                    pure_open[k] += (q == k) ? 16 - painted : 0;
+                }
+            } else {
+                mixed = true;
             }
         }
-        if (kRankLoads == 0) {
-#pragma unroll
-            for (int e = 0; e < kPer; ++e) { a0[e] = __ldg(r0 + j0 + e); a1[e] = __ldg(r1 + j0 + e); }
-        }
-#pragma unroll
-        for (int e = 0; e < kPer; ++e) {
-            RankT x = a0[e], y = a1[e];
-            bool px = x >= hi0, nx = x < lo0, py = y >= hi1, ny = y < lo1;
-            bool skip = (x == pad) || !(px || nx || py || ny);
-            int q = (px && py) ? 0 : ((nx && py) ? 1 : ((nx && ny) ? 2 : 3));
-            unsigned long long one = skip ? 0ull : (1ull << (16 * q));
-            ptot += one;
-            popen += ((int)sv[e] != kPainted) ? one : 0ull;
-        }
-        since_flush += kPer;
-        if (since_flush > 60000) {   // keep the 16-bit fields from overflowing on huge planes
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                flushed_tot[q] += (int)((ptot >> (16 * q)) & 0xffff);
-                flushed_open[q] += (int)((popen >> (16 * q)) & 0xffff);
-            }
-            ptot = popen = 0;
-            since_flush = 0;
+        unsigned mm = __ballot_sync(kFull, mixed);
+        if (mm) {
+            if (mixed) queue[queued + __popc(mm & ((1u << lane) - 1))] = c;
+            queued += __popc(mm);
+            if (queued > kMixedQueue - 32) drain();
         }
     }
+    if (queued) drain();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        int t = flushed_tot[q] + (int)((ptot >> (16 * q)) & 0xffff);
-        int o = flushed_open[q] + (int)((popen >> (16 * q)) & 0xffff);
-        tot[q] = __reduce_add_sync(kFull, t);
-        open[q] = __reduce_add_sync(kFull, o);
+        tot[q] = __reduce_add_sync(kFull, pure_chunks[q] * 16 + mix_tot[q]);
+        open[q] = __reduce_add_sync(kFull, pure_open[q] + mix_open[q]);
     }
 }
 
@@ -171,7 +262,7 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const DevCo
     // section / discrete
     if (grad == 4) {
         int tot[4], open[4];
-        section4_counts<COLOR, RankT>(pk, status, pose, lane, tot, open);
+        section4_counts<COLOR, RankT>(pk, status, pose, lane, hist, tot, open);
         if (lane < 4) {
             int t = lane == 0 ? tot[0] : (lane == 1 ? tot[1] : (lane == 2 ? tot[2] : tot[3]));
             int o = lane == 0 ? open[0] : (lane == 1 ? open[1] : (lane == 2 ? open[2] : open[3]));
@@ -335,6 +426,7 @@ step_kernel(DevPack pk, DevConfig cfg, EnvState *states, typename StatusT<COLOR>
     const double delta1 = delta_axis1 / kPaintPerAction, delta2 = delta_axis2 / kPaintPerAction;
     const double delta2_scaled = delta2 * pk.lwr;
     Vec3 centers[kPaintPerAction];
+    int full_scans = 0;
     double quat[4] = {st.quat[0], st.quat[1], st.quat[2], st.quat[3]};
 #pragma unroll 1
     for (int s = 0; s < kPaintPerAction; ++s) {
@@ -343,7 +435,7 @@ step_kernel(DevPack pk, DevConfig cfg, EnvState *states, typename StatusT<COLOR>
         add_comp(p, pk.axis1, delta2_scaled);
         Vec3 end = {p.x + cur_n.x, p.y + cur_n.y, p.z + cur_n.z};
         Vec3 hit, pos, orn = cur_n;
-        bool ok = ray_test(pk, p, end, lane, hit);
+        bool ok = ray_test(pk, p, end, lane, hit, full_scans);
         if (ok) ok = hook_point(pk, hit, lane, pos, orn);
         if (!ok) orn = cur_n;
         quat_from_normal(orn, quat);
@@ -488,6 +580,7 @@ step_kernel(DevPack pk, DevConfig cfg, EnvState *states, typename StatusT<COLOR>
         atomicAdd(&io.stats[0], 1ull);
         atomicAdd(&io.stats[2], (unsigned long long)n_possible);
         if (done) atomicAdd(&io.stats[1], 1ull);
+        if (full_scans) atomicAdd(&io.stats[3], (unsigned long long)full_scans);
     }
 
     // ---- same-step auto-reset: `obs` keeps the terminal observation, `next_obs` gets reset()'s
