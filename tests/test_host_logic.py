@@ -1,0 +1,106 @@
+"""CPU checks of the host-side mirror: configuration parsing (robot_gym_env.py:126-157, 240-252),
+the discrete-action direction table (robot_gym_env.py:342-347, robot.py:151-160, 352-358), the
+algorithmic-bytes model of bench.py, and index sharding including a world_size-2 gloo run."""
+import math
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_extra_config_keys_are_all_required():
+    from paintrl_b200.config import DEFAULT_EXTRA_CONFIG, EnvConfig
+    EnvConfig(dict(DEFAULT_EXTRA_CONFIG))
+    for key in DEFAULT_EXTRA_CONFIG:
+        cfg = dict(DEFAULT_EXTRA_CONFIG)
+        del cfg[key]
+        with pytest.raises(KeyError):          # the reference reads every key with [] (:240-252)
+            EnvConfig(cfg)
+
+
+def test_obs_dim_follows_the_reference_spaces():
+    from paintrl_b200.config import obs_dim
+    assert obs_dim('section', 4) == 6 and obs_dim('section', 8) == 10      # :166-167
+    assert obs_dim('grid', 4) == 16 and obs_dim('grid', 10) == 100         # :168-169
+    assert obs_dim('simple', 4) == 2                                       # :170-171
+    assert obs_dim('discrete', 4) == 5                                     # :172-173
+
+
+def test_discrete_table_carries_the_reference_residues():
+    from paintrl_b200.config import STEP_SIZE, discrete_table
+    t = discrete_table(4)
+    # a = 0..3 -> act = -1, -.5, 0, .5 -> phi = 0, pi/2, pi, 3pi/2 (robot.py:153)
+    for a, act in enumerate((-1.0, -0.5, 0.0, 0.5)):
+        phi = (act + 1) * np.pi
+        assert t[a, 0] == np.cos(phi) and t[a, 1] == np.sin(phi)
+        d1, d2 = t[a, 0] * STEP_SIZE, t[a, 1] * STEP_SIZE
+        assert t[a, 2] == (math.atan(abs(d2 / d1)) if d1 != 0 else math.pi / 2)
+    assert t[0, 0] == 1.0 and t[0, 1] == 0.0
+    assert abs(t[1, 0]) < 1e-15 and t[1, 0] != 0.0 and t[1, 1] == 1.0      # the 6e-17 residue is kept
+    assert t[2, 0] == -1.0 and abs(t[2, 1]) < 1e-15 and t[2, 1] != 0.0
+
+
+def test_algorithmic_bytes_matches_survey_8d():
+    sys.path.insert(0, ROOT)
+    import bench
+    # C2 floor with U = 200, p_reset = 0
+    assert bench.algorithmic_bytes(1, 9663, 6, 1, True, 200, 0.0) == 9663 + 400 + 48 + 8 + 40 + 320
+    assert bench.algorithmic_bytes(2, 14482, 6, 1, True, 150, 0.0) == 28964 + 600 + 48 + 8 + 40 + 320
+    assert bench.algorithmic_bytes(1, 9663, 2, 1, False, 0, 0.0) == 16 + 8 + 40 + 320
+
+
+def test_shard_range_partitions_every_env_exactly_once():
+    from paintrl_b200.sharding import shard_range
+    for total in (0, 1, 7, 4096, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = shard_range(total, r, world)
+                assert 0 <= lo <= hi <= total
+                seen.extend(range(lo, hi))
+            assert seen == list(range(total))
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+from paintrl_b200 import sharding
+rank, local_rank, world = sharding.init_process_group(backend='gloo')
+assert world == 2 and dist.get_backend() == 'gloo'
+lo, hi = sharding.shard_range(65536, rank, world)
+stats = {'env_steps': hi - lo, 'episodes': 10 * (rank + 1), 'sum_reward': 1.5 * (rank + 1),
+         'max_episode_len': 100 + rank, 'max_step_ms': 2.0 - rank}
+out = sharding.allreduce_stats(stats)
+assert out['env_steps'] == 65536 and out['episodes'] == 30 and abs(out['sum_reward'] - 4.5) < 1e-12
+assert out['max_episode_len'] == 101 and out['max_step_ms'] == 2.0
+dist.barrier()
+dist.destroy_process_group()
+print('rank %%d ok' %% rank)
+'''
+
+
+def test_world_size_2_gloo_statistics_allreduce(tmp_path):
+    """The only exchange of the multi-GPU path (rollout statistics) on the gloo backend."""
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    script = tmp_path / 'worker.py'
+    script.write_text(_GLOO_WORKER % ROOT)
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1',
+                   MASTER_PORT=str(port), CUDA_VISIBLE_DEVICES='')
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    for rank, p in enumerate(procs):
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert 'rank %d ok' % rank in out
