@@ -19,7 +19,8 @@ HEADERS = [os.path.join(CSRC, 'paintrl_device.cuh'), os.path.join(CSRC, 'paintrl
 LIB = os.path.join(_DIR, 'libpaintrl_b200.so')
 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-fmad=false',
-              '-lineinfo', '-cudart', 'static', '-Xcompiler', '-fPIC', '-shared']
+              '-lineinfo', '-cudart', 'static', '-Xcompiler', '-fPIC', '-Xcompiler', '-ffp-contract=off',
+              '-shared']
 
 
 def nvcc_path():

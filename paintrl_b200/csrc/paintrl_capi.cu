@@ -62,113 +62,203 @@ struct PaintrlEngine {
     int device = 0;
     int num_envs = 0;
     int color = 0;
-    int rank_bytes = 2;
     DevPack pk{};
     DevConfig cfg{};
     DeviceArena arena;
     EnvState *states = nullptr;
     void *planes = nullptr;          // [num_envs][n_pad] uint8 (RGB) or int16 (HSI)
+    unsigned *bin_cnt = nullptr;     // [num_envs][n_bins_pad / 2]
+    unsigned *grid_cnt = nullptr;    // [num_envs][n_gcells_pad] (grid observation only)
     unsigned long long *stats = nullptr;
     // staging for the host-buffer entry points
     void *stage_actions = nullptr;
     double *stage_obs = nullptr, *stage_next_obs = nullptr, *stage_scalars = nullptr;   // scalars: reward|penalty|actual
     uint8_t *stage_done = nullptr;
     unsigned long long launches = 0;
-    double ray_cell_planes_mean = 0.0;
+    double move_cell_planes_mean = 0.0, move_cell_verts_mean = 0.0;
 };
 
 namespace {
 
-// Host copy of the slab test (same formula as the device's; used only to sample the hull's front
-// surface while building the ray cells, so its rounding does not matter).
-bool host_ray(const PaintrlPartPack *pack, const double *frm, const double *d, double *t_hit) {
+// Host copy of the slab test (same formula as the device's; used only to sample the hull while
+// building the move cells, so its rounding does not matter).  Optionally reports the planes that
+// attain t_in / t_out.
+bool host_ray(const PaintrlPartPack *pack, const double *frm, const double *d, double *t_hit, int *arg_in = nullptr,
+              int *arg_out = nullptr) {
     double t_in = -INFINITY, t_out = INFINITY;
+    int ai = -1, ao = -1;
+    bool outside = false;
     for (int i = 0; i < pack->n_planes; ++i) {
         const double *n = pack->plane_n + 3 * i;
         double den = n[0] * d[0] + n[1] * d[1] + n[2] * d[2];
         double num = pack->plane_off[i] - (n[0] * frm[0] + n[1] * frm[1] + n[2] * frm[2]);
         if (den == 0.0) {
-            if (num < 0.0) return false;
+            if (num < 0.0) { outside = true; if (ai < 0) ai = i; }
             continue;
         }
         double t = num / den;
-        if (den < 0.0) t_in = std::max(t_in, t);
-        else t_out = std::min(t_out, t);
+        if (den < 0.0) { if (t > t_in) { t_in = t; ai = i; } }
+        else { if (t < t_out) { t_out = t; ao = i; } }
     }
-    if (!(t_in <= t_out) || !std::isfinite(t_in)) return false;
+    if (arg_in) *arg_in = ai;
+    if (arg_out) *arg_out = ao;
+    if (outside || !(t_in <= t_out) || !std::isfinite(t_in)) return false;
     *t_hit = t_in;
     return true;
 }
 
-// Ray-test cells (see ray_test in paintrl_device.cuh): a grid over (axis0, axis1); per cell the
-// depth range of the hull's front surface (sampled, padded) and the list of planes that are not
-// satisfied with margin at every point of the cell's box.  Only the list must be conservative;
-// the depth range merely decides how often the fast path is accepted.
-int build_ray_cells(PaintrlEngine *e, const PaintrlPartPack *pack) {
+// Move cells (see ray_test / nearest_vertex_cell in paintrl_device.cuh): a grid over (axis0, axis1).
+// Cells under the hull: depth range [dlo, dhi] of the hull's tool-side surface over the cell
+// (sampled, padded), the planes not satisfied with margin at every point of the box
+// footprint x [dlo, dhi], and the front vertices that can be nearest to a point of the box.
+// Only the two lists must be conservative; the depth range merely decides how often the fast path
+// is accepted.  Cells beside the hull: the planes that decide a few sample rays (a miss is then
+// usually proven from the list alone; nothing depends on it).
+int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::vector<int> &front,
+                     const std::vector<unsigned> &vrec) {
     DevPack &pk = e->pk;
-    pk.rc_nx = pk.rc_ny = 0;
-    if (pack->n_planes >= 65535) return PAINTRL_OK;   // fast path disabled: plane ids are 16-bit
+    pk.mc_nx = pk.mc_ny = 0;
     const int a0 = pack->axis0, a1 = pack->axis1, np = 3 - a0 - a1;
-    const double cs = kPaintRadius / 2, pad = 0.1;
+    const double cs = kPaintRadius / 4, pad = 0.15;
     const double o0 = pack->range0_min - pad, o1 = pack->range1_min - pad;
-    const int nx = (int)std::ceil((pack->range0_max + pad - o0) / cs), ny = (int)std::ceil((pack->range1_max + pad - o1) / cs);
-    if (nx <= 0 || ny <= 0 || (long long)nx * ny > (1 << 20)) return PAINTRL_OK;
-    const double kDepthPad = 0.005, kFootSlack = 1e-6, kMargin = 1e-9;
-    const int K = 4;
-    std::vector<int> start((size_t)nx * ny + 1, 0);
-    std::vector<uint16_t> idx;
-    std::vector<double> dlo((size_t)nx * ny, 0.0), dhi((size_t)nx * ny, 0.0);
+    int nx = (int)std::ceil((pack->range0_max + pad - o0) / cs), ny = (int)std::ceil((pack->range1_max + pad - o1) / cs);
+    std::vector<MoveCell> cells;
+    std::vector<uint16_t> pidx;
+    std::vector<VertCand> vcs;
+    if (pack->n_planes >= 65535 || nx <= 0 || ny <= 0 || (long long)nx * ny > (1 << 21)) nx = ny = 0;   // fast path off
+    cells.resize((size_t)nx * ny);
+    const double kDepthPad = 5e-4, kFootSlack = 1e-6, kMargin = 1e-9, kVertSlack = 1e-9;
+    const int K = 5;
+    // the tool hovers on the side the start normals point away from and looks along them
+    const double side = pack->start_normal[np] <= 0.0 ? 1.0 : -1.0;
     double dir[3] = {0, 0, 0};
-    dir[np] = -1.0;   // the tool looks along -front_normal (bullet_paint_wrapper.py:500, 530)
+    dir[np] = -side;
+    double hull_top = -INFINITY;   // highest tool-side depth of the hull (in tool-side units)
+    for (int v = 0; v < pack->n_vertices; ++v) {
+        const double *p = pack->vertices + 3 * v;
+        if (p[0] == 10.0 && p[1] == 10.0 && p[2] == 10.0) continue;
+        hull_top = std::max(hull_top, side * p[np]);
+    }
+    size_t planes_total = 0, verts_total = 0, inside_cells = 0;
+    std::vector<int> tmp;
     for (int cy = 0; cy < ny; ++cy) {
         for (int cx = 0; cx < nx; ++cx) {
-            const int cell = cy * nx + cx;
+            MoveCell &mc = cells[(size_t)cy * nx + cx];
+            mc.plane_begin = (int)pidx.size();
+            mc.vert_begin = (int)vcs.size();
+            mc.n_planes = mc.n_verts = 0;
+            mc.dlo = 1.0; mc.dhi = -1.0;
             const double lo0 = o0 + cx * cs, hi0 = o0 + (cx + 1) * cs, lo1 = o1 + cy * cs, hi1 = o1 + (cy + 1) * cs;
             double zmin = INFINITY, zmax = -INFINITY;
+            int hits = 0;
             for (int i = 0; i < K; ++i) {
                 for (int j = 0; j < K; ++j) {
                     double frm[3];
                     frm[a0] = lo0 + (hi0 - lo0) * i / (K - 1);
                     frm[a1] = lo1 + (hi1 - lo1) * j / (K - 1);
-                    frm[np] = 100.0;
+                    frm[np] = side * 100.0;
                     double t;
                     if (host_ray(pack, frm, dir, &t)) {
-                        double depth = frm[np] - t;
+                        double depth = frm[np] + dir[np] * t;
                         zmin = std::min(zmin, depth);
                         zmax = std::max(zmax, depth);
+                        ++hits;
                     }
                 }
             }
-            if (zmin <= zmax) {
+            if (hits == K * K) {
+                // ---- under the hull
                 zmin -= kDepthPad;
                 zmax += kDepthPad;
-                dlo[cell] = zmin;
-                dhi[cell] = zmax;
+                mc.dlo = zmin;
+                mc.dhi = zmax;
+                double corner[8][3];
+                for (int c = 0; c < 8; ++c) {
+                    corner[c][a0] = (c & 1) ? hi0 + kFootSlack : lo0 - kFootSlack;
+                    corner[c][a1] = (c & 2) ? hi1 + kFootSlack : lo1 - kFootSlack;
+                    corner[c][np] = (c & 4) ? zmax : zmin;
+                }
                 for (int p = 0; p < pack->n_planes; ++p) {
                     const double *n = pack->plane_n + 3 * p;
                     double worst = -INFINITY;
-                    for (int c = 0; c < 8; ++c) {
-                        double pt[3];
-                        pt[a0] = (c & 1) ? hi0 + kFootSlack : lo0 - kFootSlack;
-                        pt[a1] = (c & 2) ? hi1 + kFootSlack : lo1 - kFootSlack;
-                        pt[np] = (c & 4) ? zmax : zmin;
-                        worst = std::max(worst, n[0] * pt[0] + n[1] * pt[1] + n[2] * pt[2]);
-                    }
-                    if (worst > pack->plane_off[p] - kMargin) idx.push_back((uint16_t)p);
+                    for (int c = 0; c < 8; ++c)
+                        worst = std::max(worst, n[0] * corner[c][0] + n[1] * corner[c][1] + n[2] * corner[c][2]);
+                    if (worst > pack->plane_off[p] - kMargin) pidx.push_back((uint16_t)p);
                 }
+                mc.n_planes = (int)pidx.size() - mc.plane_begin;
+                // candidates for the nearest front vertex of any point of the box
+                double blo[3], bhi[3];
+                blo[a0] = lo0 - kFootSlack; bhi[a0] = hi0 + kFootSlack;
+                blo[a1] = lo1 - kFootSlack; bhi[a1] = hi1 + kFootSlack;
+                blo[np] = zmin; bhi[np] = zmax;
+                double best_far = INFINITY;
+                for (int v : front) {
+                    const double *p = pack->vertices + 3 * v;
+                    double far2 = 0;
+                    for (int k = 0; k < 3; ++k) {
+                        double f = std::max(std::fabs(p[k] - blo[k]), std::fabs(p[k] - bhi[k]));
+                        far2 += f * f;
+                    }
+                    best_far = std::min(best_far, std::sqrt(far2));
+                }
+                for (int v : front) {
+                    const double *p = pack->vertices + 3 * v;
+                    double near2 = 0;
+                    for (int k = 0; k < 3; ++k) {
+                        double g = std::max(0.0, std::max(blo[k] - p[k], p[k] - bhi[k]));
+                        near2 += g * g;
+                    }
+                    if (std::sqrt(near2) <= best_far + kVertSlack) {
+                        VertCand vc;
+                        vc.x = p[0]; vc.y = p[1]; vc.z = p[2];
+                        vc.id = (unsigned)v;
+                        vc.rec = vrec[v];
+                        vcs.push_back(vc);
+                    }
+                }
+                mc.n_verts = (int)vcs.size() - mc.vert_begin;
+                planes_total += mc.n_planes;
+                verts_total += mc.n_verts;
+                ++inside_cells;
+            } else {
+                // ---- beside (or straddling the edge of) the hull: planes deciding a few sample rays
+                tmp.clear();
+                const double mid0 = 0.5 * (lo0 + hi0), mid1 = 0.5 * (lo1 + hi1);
+                const double tilt = 0.35;
+                const double sample[9][4] = {{mid0, mid1, 0, 0},    {mid0, mid1, tilt, 0}, {mid0, mid1, -tilt, 0},
+                                             {mid0, mid1, 0, tilt}, {mid0, mid1, 0, -tilt}, {lo0, lo1, 0, 0},
+                                             {hi0, lo1, 0, 0},      {lo0, hi1, 0, 0},       {hi0, hi1, 0, 0}};
+                for (int q = 0; q < 9; ++q) {
+                    double frm[3], d[3];
+                    frm[a0] = sample[q][0]; frm[a1] = sample[q][1];
+                    frm[np] = side * (hull_top + kHookDistance);
+                    d[a0] = sample[q][2]; d[a1] = sample[q][3]; d[np] = -side;
+                    double nrm = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                    for (int k = 0; k < 3; ++k) d[k] /= nrm;
+                    double t;
+                    int ai, ao;
+                    host_ray(pack, frm, d, &t, &ai, &ao);
+                    if (ai >= 0) tmp.push_back(ai);
+                    if (ao >= 0) tmp.push_back(ao);
+                }
+                std::sort(tmp.begin(), tmp.end());
+                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+                for (int p : tmp) pidx.push_back((uint16_t)p);
+                mc.n_planes = (int)tmp.size();
             }
-            start[cell + 1] = (int)idx.size();
         }
     }
-    pk.rc_nx = nx; pk.rc_ny = ny;
-    pk.rc_o0 = o0; pk.rc_o1 = o1; pk.rc_inv = 1.0 / cs;
-    CUDA_TRY(e->arena.upload(start, &pk.rc_start));
-    CUDA_TRY(e->arena.upload(idx, &pk.rc_idx));
-    CUDA_TRY(e->arena.upload(dlo, &pk.rc_dlo));
-    CUDA_TRY(e->arena.upload(dhi, &pk.rc_dhi));
-    e->ray_cell_planes_mean = idx.empty() ? 0.0 : (double)idx.size() / std::max<size_t>(1, (size_t)nx * ny);
+    pk.mc_nx = nx; pk.mc_ny = ny;
+    pk.mc_o0 = o0; pk.mc_o1 = o1; pk.mc_inv = 1.0 / cs;
+    CUDA_TRY(e->arena.upload(cells, &pk.mc));
+    CUDA_TRY(e->arena.upload(pidx, &pk.mc_pidx));
+    CUDA_TRY(e->arena.upload(vcs, &pk.mc_vc));
+    e->move_cell_planes_mean = inside_cells ? (double)planes_total / inside_cells : 0.0;
+    e->move_cell_verts_mean = inside_cells ? (double)verts_total / inside_cells : 0.0;
     return PAINTRL_OK;
 }
+
+inline float ulp_f32(float v) { return std::nextafter(std::fabs(v), INFINITY) - std::fabs(v); }
 
 // Host-side construction of the acceleration tables (see DESIGN.md "Data layout in HBM").
 int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlConfig *cfg) {
@@ -187,12 +277,45 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
     for (int i = 0; i < pack->n_planes; ++i)
         planes[i] = make_double4(pack->plane_n[3 * i], pack->plane_n[3 * i + 1], pack->plane_n[3 * i + 2], pack->plane_off[i]);
     CUDA_TRY(e->arena.upload(planes, &pk.planes));
+
+    // ---- incident-triangle records per vertex (uv_map order): barycentric constants, corrected
+    // normal n, and for orn = -n the quaternion (robot.py:93-100) and shot-centre offset
+    // R(q)(0,0,0.1) (robot.py:277-278), evaluated here with the very functions the device uses.
+    for (int i = 0; i < pack->vtri_start[pack->n_vertices]; ++i)
+        if (pack->vtri_idx[i] < 0 || pack->vtri_idx[i] >= pack->n_tris) return fail(PAINTRL_E_INVALID, "vtri_idx out of range");
+    std::vector<unsigned> vrec(pack->n_vertices, 0xFFFFFFFFu);
     {
-        int rc = build_ray_cells(e, pack);
-        if (rc != PAINTRL_OK) return rc;
+        const int n_rec = pack->vtri_start[pack->n_vertices];
+        if (n_rec >= (1 << 24)) return fail(PAINTRL_E_INVALID, "too many vertex-triangle incidences");
+        std::vector<double> rec((size_t)std::max(n_rec, 1) * kTriRec, 0.0);
+        for (int v = 0; v < pack->n_vertices; ++v) {
+            const int begin = pack->vtri_start[v], deg = pack->vtri_start[v + 1] - begin;
+            if (deg > 255) return fail(PAINTRL_E_INVALID, "vertex with more than 255 incident front triangles");
+            vrec[v] = ((unsigned)begin << 8) | (unsigned)deg;
+            for (int k = 0; k < deg; ++k) {
+                const int t = pack->vtri_idx[begin + k];
+                double *o = &rec[(size_t)(begin + k) * kTriRec];
+                for (int c = 0; c < 3; ++c) {
+                    o[c] = pack->tri_a[3 * t + c];
+                    o[3 + c] = pack->tri_v0[3 * t + c];
+                    o[6 + c] = pack->tri_v1[3 * t + c];
+                    o[13 + c] = pack->tri_n[3 * t + c];
+                }
+                o[9] = pack->tri_d00[t]; o[10] = pack->tri_d01[t]; o[11] = pack->tri_d11[t]; o[12] = pack->tri_inv_denom[t];
+                Vec3 orn = {-o[13], -o[14], -o[15]};
+                quat_from_normal(orn, o + 16);
+                const Vec3 zero = {0.0, 0.0, 0.0};
+                Vec3 off = transform_point(zero, o + 16, 0.0, 0.0, 0.1);
+                // transform_point adds pos last: (rot + 0.0) == rot exactly except for -0.0, which the
+                // device-side `off + pos` cannot distinguish either
+                o[20] = off.x; o[21] = off.y; o[22] = off.z;
+            }
+        }
+        CUDA_TRY(e->arena.upload(rec, &pk.trirec));
+        CUDA_TRY(e->arena.upload(vrec, &pk.vrec));
     }
 
-    // ---- vertex grid (vertices parked at IRRELEVANT_POSE (10,10,10) can never be nearest; skip them)
+    // ---- vertex grid for the slow path (vertices parked at IRRELEVANT_POSE (10,10,10) can never be nearest; skip them)
     std::vector<int> front;
     for (int v = 0; v < pack->n_vertices; ++v) {
         const double *p = pack->vertices + 3 * v;
@@ -244,170 +367,83 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
         CUDA_TRY(e->arena.upload(vid, &pk.vid));
     }
     {
-        std::vector<int> vs(pack->vtri_start, pack->vtri_start + pack->n_vertices + 1);
-        std::vector<int> vi(pack->vtri_idx, pack->vtri_idx + vs.back());
-        for (int t : vi)
-            if (t < 0 || t >= pack->n_tris) return fail(PAINTRL_E_INVALID, "vtri_idx out of range");
-        CUDA_TRY(e->arena.upload(vs, &pk.vtri_start));
-        CUDA_TRY(e->arena.upload(vi, &pk.vtri_idx));
-        std::vector<double> tri((size_t)pack->n_tris * 16);
-        for (int t = 0; t < pack->n_tris; ++t) {
-            double *o = &tri[(size_t)t * 16];
-            for (int k = 0; k < 3; ++k) {
-                o[k] = pack->tri_a[3 * t + k];
-                o[3 + k] = pack->tri_v0[3 * t + k];
-                o[6 + k] = pack->tri_v1[3 * t + k];
-                o[13 + k] = pack->tri_n[3 * t + k];
-            }
-            o[9] = pack->tri_d00[t]; o[10] = pack->tri_d01[t]; o[11] = pack->tri_d11[t]; o[12] = pack->tri_inv_denom[t];
-        }
-        CUDA_TRY(e->arena.upload(tri, &pk.tri));
+        int rc = build_move_cells(e, pack, front, vrec);
+        if (rc != PAINTRL_OK) return rc;
     }
 
-    // ---- texel bins: cell = PAINT_RADIUS, rows along axis1; texels sorted by cell (stable)
+    // ---- texel bins: texels sorted by bin (row-major, rows along axis1).  Bin size b = R / k balances
+    // the per-step cost of the observation: ~0.3 instructions per bin counter against ~0.8 per texel of
+    // the pose's bin row and column.
     double tmin0 = INFINITY, tmax0 = -INFINITY, tmin1 = INFINITY, tmax1 = -INFINITY;
+    double tmin[3] = {INFINITY, INFINITY, INFINITY}, tmax[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = 0; i < n; ++i) {
         const double *p = pack->texel_pos + 3 * i;
         tmin0 = std::min(tmin0, p[a0]); tmax0 = std::max(tmax0, p[a0]);
         tmin1 = std::min(tmin1, p[a1]); tmax1 = std::max(tmax1, p[a1]);
+        for (int k = 0; k < 3; ++k) { tmin[k] = std::min(tmin[k], p[k]); tmax[k] = std::max(tmax[k], p[k]); }
     }
-    pk.tb_inv = 1.0 / kPaintRadius;
+    int bin_div;
+    {
+        const double ext0 = std::max(tmax0 - tmin0, 1e-9), ext1 = std::max(tmax1 - tmin1, 1e-9);
+        const double b = 0.74 * std::cbrt(2.0 * ext0 * ext1 * ext0 * ext1 / ((ext0 + ext1) * (double)n));
+        bin_div = (int)std::lround(kPaintRadius / b);
+        bin_div = std::min(std::max(bin_div, 1), 8);
+        while (bin_div > 1 && (std::floor(ext0 * bin_div / kPaintRadius) + 2) * (std::floor(ext1 * bin_div / kPaintRadius) + 1) > 65000.0)
+            --bin_div;
+    }
+    const double bsz = kPaintRadius / bin_div;
+    pk.tb_inv = 1.0 / bsz;
     pk.tb_o0 = tmin0;
     pk.tb_o1 = tmin1;
-    pk.tb_nx = (int)std::floor((tmax0 - tmin0) * pk.tb_inv) + 1;
+    const int nx_real = (int)std::floor((tmax0 - tmin0) * pk.tb_inv) + 1;
+    pk.tb_nx = (nx_real + 1) & ~1;           // even: two 16-bit counters per word never straddle rows
     pk.tb_ny = (int)std::floor((tmax1 - tmin1) * pk.tb_inv) + 1;
-    if ((long long)pk.tb_nx * pk.tb_ny > (1 << 24)) return fail(PAINTRL_E_INVALID, "texel bin grid too large");
-    std::vector<int> order(n);
+    if ((long long)pk.tb_nx * pk.tb_ny > 65535) return fail(PAINTRL_E_INVALID, "texel bin grid too large");
+    const int n_bins = pk.tb_nx * pk.tb_ny;
+    pk.n_bins_pad = ((n_bins + 63) / 64) * 64;
+    std::vector<int> order(n), bin_of(n);
     {
-        const int cells = pk.tb_nx * pk.tb_ny;
-        std::vector<int> cell_of(n), start(cells + 1, 0);
+        std::vector<int> start(n_bins + 1, 0);
         for (int i = 0; i < n; ++i) {
             const double *p = pack->texel_pos + 3 * i;
-            int cx = std::min(std::max((int)std::floor((p[a0] - pk.tb_o0) * pk.tb_inv), 0), pk.tb_nx - 1);
-            int cy = std::min(std::max((int)std::floor((p[a1] - pk.tb_o1) * pk.tb_inv), 0), pk.tb_ny - 1);
-            cell_of[i] = cy * pk.tb_nx + cx;
-            start[cell_of[i] + 1]++;
+            // the same two FP64 operations the device applies to the pose (section4_counts)
+            int cx = (int)std::floor((p[a0] - pk.tb_o0) * pk.tb_inv);
+            int cy = (int)std::floor((p[a1] - pk.tb_o1) * pk.tb_inv);
+            if (cx < 0 || cx >= nx_real || cy < 0 || cy >= pk.tb_ny) return fail(PAINTRL_E_INVALID, "texel outside its own bin grid");
+            bin_of[i] = cy * pk.tb_nx + cx;
+            start[bin_of[i] + 1]++;
         }
-        for (int c = 0; c < cells; ++c) start[c + 1] += start[c];
-        // within a bin row texels are ordered by their axis0 coordinate: cells stay contiguous (the
-        // cell index is monotone in the coordinate) and every 16-texel chunk covers a narrow
-        // coordinate interval, which keeps the chunk rank boxes of the observation scan tight
+        int max_bin = 0;
+        for (int c = 0; c < n_bins; ++c) { max_bin = std::max(max_bin, start[c + 1]); start[c + 1] += start[c]; }
+        if ((long long)max_bin * pk.tb_ny > 65535 || max_bin > 65535)
+            return fail(PAINTRL_E_INVALID, "texel bins too full for 16-bit counters");
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-            int rx = cell_of[x] / pk.tb_nx, ry = cell_of[y] / pk.tb_nx;
-            if (rx != ry) return rx < ry;
+            if (bin_of[x] != bin_of[y]) return bin_of[x] < bin_of[y];
             return pack->texel_pos[3 * x + a0] < pack->texel_pos[3 * y + a0];
         });
         CUDA_TRY(e->arena.upload(start, &pk.tb_start));
-    }
-    {
-        std::vector<double> tx(pk.n_pad, 1e30), ty(pk.n_pad, 1e30), tz(pk.n_pad, 1e30);
-        for (int j = 0; j < n; ++j) {
-            const double *p = pack->texel_pos + 3 * order[j];
-            tx[j] = p[0]; ty[j] = p[1]; tz[j] = p[2];
-        }
-        CUDA_TRY(e->arena.upload(tx, &pk.tx));
-        CUDA_TRY(e->arena.upload(ty, &pk.ty));
-        CUDA_TRY(e->arena.upload(tz, &pk.tz));
-        CUDA_TRY(e->arena.upload(order, &pk.sorted_to_pack));
-    }
-
-    // ---- coordinate ranks for the 4-sector observation
-    {
-        std::vector<double> u0(n), u1(n);
-        for (int i = 0; i < n; ++i) {
-            u0[i] = pack->texel_pos[3 * i + a0];
-            u1[i] = pack->texel_pos[3 * i + a1];
-        }
-        std::sort(u0.begin(), u0.end());
-        u0.erase(std::unique(u0.begin(), u0.end()), u0.end());
-        std::sort(u1.begin(), u1.end());
-        u1.erase(std::unique(u1.begin(), u1.end()), u1.end());
-        pk.n_uniq0 = (int)u0.size();
-        pk.n_uniq1 = (int)u1.size();
-        e->rank_bytes = (u0.size() < 65535 && u1.size() < 65535) ? 2 : 4;
-        pk.rank_bytes = e->rank_bytes;
-        auto rank_of = [](const std::vector<double> &u, double v) {
-            return (unsigned)(std::lower_bound(u.begin(), u.end(), v) - u.begin());
-        };
-        if (e->rank_bytes == 2) {
-            std::vector<uint16_t> r0(pk.n_pad, 0xFFFF), r1(pk.n_pad, 0xFFFF);
-            for (int j = 0; j < n; ++j) {
-                const double *p = pack->texel_pos + 3 * order[j];
-                r0[j] = (uint16_t)rank_of(u0, p[a0]);
-                r1[j] = (uint16_t)rank_of(u1, p[a1]);
+        // exclusive 2-D prefix sums of the bin sizes
+        const int W = pk.tb_nx + 1;
+        std::vector<int> prefix((size_t)(pk.tb_ny + 1) * W, 0);
+        for (int iy = 0; iy < pk.tb_ny; ++iy)
+            for (int ix = 0; ix < pk.tb_nx; ++ix) {
+                const int size = start[iy * pk.tb_nx + ix + 1] - start[iy * pk.tb_nx + ix];
+                prefix[(size_t)(iy + 1) * W + ix + 1] = size + prefix[(size_t)iy * W + ix + 1] + prefix[(size_t)(iy + 1) * W + ix] -
+                                                        prefix[(size_t)iy * W + ix];
             }
-            const uint16_t *d0, *d1;
-            CUDA_TRY(e->arena.upload(r0, &d0));
-            CUDA_TRY(e->arena.upload(r1, &d1));
-            pk.rank0 = d0; pk.rank1 = d1;
-            std::vector<uint16_t> box((size_t)(pk.n_pad / 16) * 4);
-            for (int c = 0; c < pk.n_pad / 16; ++c) {
-                uint16_t b0 = 0xFFFF, b1 = 0, b2 = 0xFFFF, b3 = 0;
-                bool has_pad = false;
-                for (int k = 0; k < 16; ++k) {
-                    int j = c * 16 + k;
-                    if (j >= n) { has_pad = true; continue; }
-                    b0 = std::min(b0, r0[j]); b1 = std::max(b1, r0[j]);
-                    b2 = std::min(b2, r1[j]); b3 = std::max(b3, r1[j]);
-                }
-                if (has_pad) { b0 = 0xFFFF; b1 = 0; b2 = 0xFFFF; b3 = 0; }   // inverted box: never "pure"
-                box[4 * c] = b0; box[4 * c + 1] = b1; box[4 * c + 2] = b2; box[4 * c + 3] = b3;
-            }
-            const uint16_t *db;
-            CUDA_TRY(e->arena.upload(box, &db));
-            pk.chunk_box = db;
-        } else {
-            std::vector<uint32_t> r0(pk.n_pad, 0xFFFFFFFFu), r1(pk.n_pad, 0xFFFFFFFFu);
-            for (int j = 0; j < n; ++j) {
-                const double *p = pack->texel_pos + 3 * order[j];
-                r0[j] = rank_of(u0, p[a0]);
-                r1[j] = rank_of(u1, p[a1]);
-            }
-            const uint32_t *d0, *d1;
-            CUDA_TRY(e->arena.upload(r0, &d0));
-            CUDA_TRY(e->arena.upload(r1, &d1));
-            pk.rank0 = d0; pk.rank1 = d1;
-            std::vector<uint32_t> box((size_t)(pk.n_pad / 16) * 4);
-            for (int c = 0; c < pk.n_pad / 16; ++c) {
-                uint32_t b0 = 0xFFFFFFFFu, b1 = 0, b2 = 0xFFFFFFFFu, b3 = 0;
-                bool has_pad = false;
-                for (int k = 0; k < 16; ++k) {
-                    int j = c * 16 + k;
-                    if (j >= n) { has_pad = true; continue; }
-                    b0 = std::min(b0, r0[j]); b1 = std::max(b1, r0[j]);
-                    b2 = std::min(b2, r1[j]); b3 = std::max(b3, r1[j]);
-                }
-                if (has_pad) { b0 = 0xFFFFFFFFu; b1 = 0; b2 = 0xFFFFFFFFu; b3 = 0; }
-                box[4 * c] = b0; box[4 * c + 1] = b1; box[4 * c + 2] = b2; box[4 * c + 3] = b3;
-            }
-            const uint32_t *db;
-            CUDA_TRY(e->arena.upload(box, &db));
-            pk.chunk_box = db;
-        }
-        CUDA_TRY(e->arena.upload(u0, &pk.uniq0));
-        CUDA_TRY(e->arena.upload(u1, &pk.uniq1));
+        CUDA_TRY(e->arena.upload(prefix, &pk.tb_prefix));
     }
-
-    // ---- silhouette table, ranges
-    pk.grid_granularity = pack->grid_granularity;
-    {
-        std::vector<double> lo(pack->grid_lo, pack->grid_lo + pack->grid_granularity);
-        std::vector<double> hi(pack->grid_hi, pack->grid_hi + pack->grid_granularity);
-        CUDA_TRY(e->arena.upload(lo, &pk.grid_lo));
-        CUDA_TRY(e->arena.upload(hi, &pk.grid_hi));
-    }
-    pk.range0_min = pack->range0_min; pk.range0_max = pack->range0_max;
-    pk.range1_min = pack->range1_min; pk.range1_max = pack->range1_max;
-    pk.lwr = pack->length_width_ratio;
 
     // ---- grid-observation cells (bullet_paint_wrapper.py:1072-1112)
+    std::vector<uint16_t> gcell(n, 0);
+    pk.n_gcells = pk.n_gcells_pad = 0;
+    pk.gtotal = nullptr;
     if (cfg->obs_mode == PAINTRL_OBS_GRID) {
         const int g = cfg->obs_grad, vgran = pack->grid_granularity;
         const int v_interval = (int)((double)vgran / (double)g);
         if (v_interval <= 0) return fail(PAINTRL_E_INVALID, "OBS_GRAD larger than GRID_GRANULARITY");
         const double axis_2_step = (pack->range1_max - pack->range1_min) / vgran;
-        std::vector<uint16_t> gcell(pk.n_pad, 0xFFFF);
         std::vector<int> gtotal((size_t)g * g, 0);
         for (int j = 0; j < n; ++j) {
             const double *p = pack->texel_pos + 3 * order[j];
@@ -428,9 +464,48 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
             gcell[j] = (uint16_t)(v_target * g + x_grid);
             gtotal[v_target * g + x_grid]++;
         }
-        CUDA_TRY(e->arena.upload(gcell, &pk.gcell));
+        pk.n_gcells = g * g;
+        pk.n_gcells_pad = ((g * g + 3) / 4) * 4;
         CUDA_TRY(e->arena.upload(gtotal, &pk.gtotal));
     }
+
+    // ---- sorted texel tables: exact FP64 positions, and FP32 origin-relative positions + bin + grid cell
+    {
+        std::vector<double> tx(pk.n_pad, 1e30), ty(pk.n_pad, 1e30), tz(pk.n_pad, 1e30);
+        std::vector<float4> trel(pk.n_pad, make_float4(1e30f, 1e30f, 1e30f, 0.f));
+        pk.org0 = 0.5 * (tmin[0] + tmax[0]); pk.org1 = 0.5 * (tmin[1] + tmax[1]); pk.org2 = 0.5 * (tmin[2] + tmax[2]);
+        float max_abs = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const double *p = pack->texel_pos + 3 * order[j];
+            tx[j] = p[0]; ty[j] = p[1]; tz[j] = p[2];
+            float4 r;
+            r.x = (float)(p[0] - pk.org0); r.y = (float)(p[1] - pk.org1); r.z = (float)(p[2] - pk.org2);
+            const unsigned w = (unsigned)bin_of[order[j]] | ((unsigned)gcell[j] << 16);
+            std::memcpy(&r.w, &w, 4);
+            trel[j] = r;
+            max_abs = std::max(max_abs, std::max(std::fabs(r.x), std::max(std::fabs(r.y), std::fabs(r.z))));
+        }
+        // FP32 ball test error bound (see stamp()): |d2_f32 - d2_f64| < 4 ulp(2 max|coord|) * sqrt(3) * 2r
+        const double bound = 4.0 * (double)ulp_f32(2.f * max_abs + (float)(2 * kPaintRadius)) * 1.7320508 * 2 * kPaintRadius + 4e-9;
+        if (bound > (double)kBallEps) return fail(PAINTRL_E_INVALID, "part too large for the FP32 ball pre-test");
+        CUDA_TRY(e->arena.upload(tx, &pk.tx));
+        CUDA_TRY(e->arena.upload(ty, &pk.ty));
+        CUDA_TRY(e->arena.upload(tz, &pk.tz));
+        CUDA_TRY(e->arena.upload(trel, &pk.trel));
+        CUDA_TRY(e->arena.upload(order, &pk.sorted_to_pack));
+    }
+
+    // ---- silhouette table, ranges
+    pk.grid_granularity = pack->grid_granularity;
+    {
+        std::vector<double> lo(pack->grid_lo, pack->grid_lo + pack->grid_granularity);
+        std::vector<double> hi(pack->grid_hi, pack->grid_hi + pack->grid_granularity);
+        CUDA_TRY(e->arena.upload(lo, &pk.grid_lo));
+        CUDA_TRY(e->arena.upload(hi, &pk.grid_hi));
+    }
+    pk.range0_min = pack->range0_min; pk.range0_max = pack->range0_max;
+    pk.range1_min = pack->range1_min; pk.range1_max = pack->range1_max;
+    pk.lwr = pack->length_width_ratio;
 
     // ---- start points
     pk.n_starts = pack->n_starts;
@@ -456,9 +531,19 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 
 template <typename F>
 int dispatch(PaintrlEngine *e, F &&f) {
-    // (colour mode, rank width) -> kernel instantiation
-    if (e->color == 0) return e->rank_bytes == 2 ? f(std::integral_constant<int, 0>{}, uint16_t{}) : f(std::integral_constant<int, 0>{}, uint32_t{});
-    return e->rank_bytes == 2 ? f(std::integral_constant<int, 1>{}, uint16_t{}) : f(std::integral_constant<int, 1>{}, uint32_t{});
+    // colour mode -> kernel instantiation
+    if (e->color == 0) return f(std::integral_constant<int, 0>{});
+    return f(std::integral_constant<int, 1>{});
+}
+
+template <int C>
+EnvArrays<C> env_arrays(PaintrlEngine *e) {
+    EnvArrays<C> ea;
+    ea.states = e->states;
+    ea.planes = reinterpret_cast<typename StatusT<C>::type *>(e->planes);
+    ea.bin_cnt = e->bin_cnt;
+    ea.grid_cnt = e->grid_cnt;
+    return ea;
 }
 
 int launch_check(PaintrlEngine *e, const char *what) {
@@ -527,14 +612,21 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     c.episode_max_length = cfg->episode_max_length;
     c.turning_penalty = cfg->turning_penalty; c.overlap_penalty = cfg->overlap_penalty;
     c.max_possible_point = cfg->max_possible_point;
+    // robot_gym_env.py:297, 302 -- same operations, evaluated once
+    c.expected_avg_reward = cfg->max_possible_point / (double)(cfg->expected_episode_length * 100);
+    c.hybrid_threshold = cfg->switch_threshold * cfg->max_possible_point / 100;
     c.auto_reset = cfg->auto_reset;
     c.seed = cfg->seed;
 
     const size_t elem = e->color == 0 ? 1 : 2;
     const size_t plane_bytes = (size_t)num_envs * e->pk.n_pad * elem;
+    const size_t cnt_bytes = (size_t)num_envs * (e->pk.n_bins_pad / 2) * sizeof(unsigned);
+    const size_t gcnt_bytes = (size_t)num_envs * e->pk.n_gcells_pad * sizeof(unsigned);
     const size_t adim = c.action_mode == 0 ? sizeof(long long) : sizeof(double) * c.action_shape;
     bool ok = e->arena.alloc((void **)&e->states, sizeof(EnvState) * (size_t)num_envs) == cudaSuccess &&
               e->arena.alloc(&e->planes, plane_bytes) == cudaSuccess &&
+              e->arena.alloc((void **)&e->bin_cnt, cnt_bytes) == cudaSuccess &&
+              (gcnt_bytes == 0 || e->arena.alloc((void **)&e->grid_cnt, gcnt_bytes) == cudaSuccess) &&
               e->arena.alloc((void **)&e->stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               e->arena.alloc(&e->stage_actions, adim * num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&e->stage_obs, sizeof(double) * od * (size_t)num_envs) == cudaSuccess &&
@@ -544,6 +636,8 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     if (!ok) { delete e; return fail(PAINTRL_E_CUDA, "device allocation failed (state / status planes)"); }
     cudaMemset(e->states, 0, sizeof(EnvState) * (size_t)num_envs);
     cudaMemset(e->planes, 0, plane_bytes);
+    cudaMemset(e->bin_cnt, 0, cnt_bytes);
+    if (e->grid_cnt) cudaMemset(e->grid_cnt, 0, gcnt_bytes);
     cudaMemset(e->stats, 0, 4 * sizeof(unsigned long long));
     err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, cudaGetErrorString(err)); }
@@ -571,12 +665,10 @@ static int reset_like(PaintrlHandle h, const int32_t *env_ids, int32_t n, const 
     if (!env_ids && n != h->num_envs) return fail(PAINTRL_E_INVALID, "env_ids == NULL requires n == num_envs");
     CUDA_TRY(cudaSetDevice(h->device));
     const int blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    return dispatch(h, [&](auto color, auto rank) {
+    return dispatch(h, [&](auto color) {
         constexpr int C = decltype(color)::value;
-        typedef decltype(rank) R;
-        typedef typename StatusT<C>::type S;
-        reset_kernel<C, R><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(
-            h->pk, h->cfg, h->states, reinterpret_cast<S *>(h->planes), env_ids, n, start_idx, pos, normal, obs, mode);
+        reset_kernel<C><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays<C>(h), env_ids, n,
+                                                                                start_idx, pos, normal, obs, mode);
         return launch_check(h, "reset_kernel");
     });
 }
@@ -606,12 +698,9 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     io.reset_start_idx = reset_start_idx_dev;
     io.stats = h->stats;
     const int blocks = (h->num_envs + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    return dispatch(h, [&](auto color, auto rank) {
+    return dispatch(h, [&](auto color) {
         constexpr int C = decltype(color)::value;
-        typedef decltype(rank) R;
-        typedef typename StatusT<C>::type S;
-        step_kernel<C, R><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(
-            h->pk, h->cfg, h->states, reinterpret_cast<S *>(h->planes), h->num_envs, io);
+        step_kernel<C><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays<C>(h), h->num_envs, io);
         return launch_check(h, "step_kernel");
     });
 }
@@ -651,13 +740,12 @@ int paintrl_get_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, in
     if (n <= 0 || n > h->num_envs || (!env_ids_dev && n != h->num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
     CUDA_TRY(cudaSetDevice(h->device));
     dim3 grid(std::max(1, std::min(64, (h->pk.n_texels + 255) / 256)), n);
-    if (h->color == 0)
-        get_state_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(h->pk, h->states, (const uint8_t *)h->planes, env_ids_dev, n,
-                                                                   status_dev, pose_dev, quat_dev, scalars_dev);
-    else
-        get_state_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(h->pk, h->states, (const int16_t *)h->planes, env_ids_dev, n,
-                                                                   status_dev, pose_dev, quat_dev, scalars_dev);
-    return launch_check(h, "get_state_kernel");
+    return dispatch(h, [&](auto color) {
+        constexpr int C = decltype(color)::value;
+        get_state_kernel<C><<<grid, 256, 0, as_stream(stream)>>>(h->pk, env_arrays<C>(h), env_ids_dev, n, status_dev, pose_dev,
+                                                                  quat_dev, scalars_dev);
+        return launch_check(h, "get_state_kernel");
+    });
 }
 
 int paintrl_set_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, const int16_t *status_dev,
@@ -666,13 +754,16 @@ int paintrl_set_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, co
     if (n <= 0 || n > h->num_envs || (!env_ids_dev && n != h->num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
     CUDA_TRY(cudaSetDevice(h->device));
     dim3 grid(std::max(1, std::min(64, (h->pk.n_texels + 255) / 256)), n);
-    if (h->color == 0)
-        set_state_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(h->pk, h->states, (uint8_t *)h->planes, env_ids_dev, n,
-                                                                   status_dev, pose_dev, quat_dev, scalars_dev);
-    else
-        set_state_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(h->pk, h->states, (int16_t *)h->planes, env_ids_dev, n,
-                                                                   status_dev, pose_dev, quat_dev, scalars_dev);
-    return launch_check(h, "set_state_kernel");
+    return dispatch(h, [&](auto color) {
+        constexpr int C = decltype(color)::value;
+        set_state_kernel<C><<<grid, 256, 0, as_stream(stream)>>>(h->pk, env_arrays<C>(h), env_ids_dev, n, status_dev, pose_dev,
+                                                                  quat_dev, scalars_dev);
+        int rc = launch_check(h, "set_state_kernel");
+        if (rc != PAINTRL_OK || !status_dev) return rc;
+        // the flip counters follow the status plane
+        recount_kernel<C><<<(n + 3) / 4, 128, 0, as_stream(stream)>>>(h->pk, env_arrays<C>(h), env_ids_dev, n);
+        return launch_check(h, "recount_kernel");
+    });
 }
 
 int paintrl_job_status(PaintrlHandle h, int32_t *painted_dev, void *stream) {

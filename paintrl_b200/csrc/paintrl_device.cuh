@@ -45,6 +45,31 @@ struct alignas(128) EnvState {
 };
 static_assert(sizeof(EnvState) == 128, "EnvState must be one 128-byte line");
 
+// One cell of the move grid over (axis0, axis1) (see build_move_cells in paintrl_capi.cu).
+// Inside the hull's silhouette: the hull planes that are not satisfied with margin everywhere in
+// the cell's box (footprint x [dlo, dhi] along the non-principal axis) and the front vertices
+// that can be nearest to some point of that box.  Outside it: dlo > dhi (never accepted) and a
+// short list of planes that usually proves a miss.
+struct alignas(32) MoveCell {
+    int plane_begin, n_planes;    // into mc_pidx
+    int vert_begin, n_verts;      // into mc_vc
+    double dlo, dhi;
+};
+static_assert(sizeof(MoveCell) == 32, "MoveCell is one 32-byte sector");
+
+// Candidate nearest vertex: position, pack vertex index (tie-break), its incident-triangle
+// records [rec_begin, rec_begin + deg) in `trirec`.
+struct alignas(32) VertCand {
+    double x, y, z;
+    unsigned id;
+    unsigned rec;                 // rec_begin << 8 | deg
+};
+static_assert(sizeof(VertCand) == 32, "VertCand is one 32-byte sector");
+
+constexpr int kTriRec = 24;       // doubles per incident-triangle record:
+// [0..2] a  [3..5] v0  [6..8] v1  [9] d00 [10] d01 [11] d11 [12] inv_denom   (BarycentricInterpolator, :123-146)
+// [13..15] corrected normal n   [16..19] quat_from_normal(-n)   [20..22] R(quat)*(0,0,0.1)   [23] pad
+
 // Constant per-part tables in device memory (shared by all environments, L1/L2 resident).
 struct DevPack {
     int n_texels, n_pad;          // n_pad: status-plane length per env, multiple of 128
@@ -53,35 +78,31 @@ struct DevPack {
     // collision hull: (nx, ny, nz, off) per plane
     int n_planes;
     const double4 *planes;
-    // ray-test cells over (axis0, axis1): per cell the planes not trivially satisfied in its box
-    int rc_nx, rc_ny;
-    double rc_o0, rc_o1, rc_inv;
-    const int *rc_start;          // [rc_nx*rc_ny + 1]
-    const uint16_t *rc_idx;       // plane indices
-    const double *rc_dlo, *rc_dhi;  // depth (non-principal axis) range of each cell's box
-    // nearest-vertex grid over (axis0, axis1): front vertices sorted by cell
+    // move grid
+    int mc_nx, mc_ny;
+    double mc_o0, mc_o1, mc_inv;
+    const MoveCell *mc;
+    const uint16_t *mc_pidx;
+    const VertCand *mc_vc;
+    const double *trirec;         // [n_rec][kTriRec]
+    // slow-path nearest-vertex grid over (axis0, axis1): front vertices sorted by cell
     int vg_nx, vg_ny;
     double vg_o0, vg_o1, vg_cs, vg_inv;
     const int *vg_start;          // [vg_nx*vg_ny + 1]
     const double *vx, *vy, *vz;   // sorted vertex coordinates
     const int *vid;               // sorted -> pack vertex index
-    const int *vtri_start;        // CSR over pack vertex index
-    const int *vtri_idx;
-    const double *tri;            // [n_tris][16]: a(3) v0(3) v1(3) d00 d01 d11 inv_denom n(3)
-    // texel bins over (axis0, axis1): texels sorted by cell (row-major, axis1 = row)
-    int tb_nx, tb_ny;
+    const unsigned *vrec;         // [n_vertices] rec_begin << 8 | deg per pack vertex
+    // texel bins over (axis0, axis1): texels sorted by bin (row-major, axis1 = row)
+    int tb_nx, tb_ny;             // tb_nx is even
     double tb_o0, tb_o1, tb_inv;
     const int *tb_start;          // [tb_nx*tb_ny + 1]
+    const int *tb_prefix;         // [(tb_ny+1)*(tb_nx+1)] exclusive 2-D prefix sums of the bin sizes
+    int n_bins_pad;               // per-env flip counters (uint16), multiple of 64
+    const float4 *trel;           // [n_pad] position - origin in FP32, w = bin | gcell << 16 (bits)
+    double org0, org1, org2;
     const double *tx, *ty, *tz;   // [n_pad] sorted texel positions (world x, y, z)
-    // section observation: rank of each sorted texel's axis0 / axis1 coordinate among the
-    // sorted distinct values (0xFFFF / 0xFFFFFFFF marks padding)
-    const void *rank0, *rank1;    // uint16_t or uint32_t [n_pad]
-    const void *chunk_box;        // [n_pad/16] rank bounding box (r0min, r0max, r1min, r1max) per 16-texel chunk
-    int rank_bytes;
-    int n_uniq0, n_uniq1;
-    const double *uniq0, *uniq1;
     // grid observation (bullet_paint_wrapper.py:1072-1112)
-    const uint16_t *gcell;        // [n_pad] cell per sorted texel (0xFFFF padding)
+    int n_gcells, n_gcells_pad;
     const int *gtotal;            // [obs_grad^2]
     // normalised pose (bullet_paint_wrapper.py:965-978)
     int grid_granularity;
@@ -103,12 +124,14 @@ struct DevConfig {
     int expected_episode_length, episode_max_length;
     int turning_penalty, overlap_penalty;
     double max_possible_point;
+    double expected_avg_reward;     // max_possible_point / (Expected_Episode_Length * 100)   (robot_gym_env.py:297)
+    double hybrid_threshold;        // SWITCH_THRESHOLD * max_possible_point / 100            (robot_gym_env.py:302)
     int auto_reset;
     unsigned long long seed;
 };
 
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double npdot3(double x0, double x1, double x2, double y0, double y1, double y2) {
+__host__ __device__ __forceinline__ double npdot3(double x0, double x1, double x2, double y0, double y1, double y2) {
     return fma(x2, y2, fma(x1, y1, x0 * y0));
 }
 
@@ -120,7 +143,7 @@ __device__ __forceinline__ void add_comp(Vec3 &v, int a, double d) {
 }
 
 // oracle/shims/pybullet.py multiplyTransforms (Bullet btMatrix3x3::setRotation + btTransform())
-__device__ __forceinline__ Vec3 transform_point(const Vec3 &pos, const double q[4], double v0, double v1, double v2) {
+__host__ __device__ __forceinline__ Vec3 transform_point(const Vec3 &pos, const double q[4], double v0, double v1, double v2) {
     double x = q[0], y = q[1], z = q[2], w = q[3];
     double d = x * x + y * y + z * z + w * w;
     double s = 2.0 / d;
@@ -136,7 +159,7 @@ __device__ __forceinline__ Vec3 transform_point(const Vec3 &pos, const double q[
 }
 
 // robot.py:93-100 get_pose_orn + bullet_paint_wrapper.py:32-37 normalize
-__device__ __forceinline__ void quat_from_normal(const Vec3 &n, double q[4]) {
+__host__ __device__ __forceinline__ void quat_from_normal(const Vec3 &n, double q[4]) {
     double x = 0.0 * n.z - 1.0 * n.y;
     double y = 1.0 * n.x - 0.0 * n.z;
     double z = 0.0 * n.y - 0.0 * n.x;
@@ -158,19 +181,27 @@ __device__ __forceinline__ Vec3 tcp_orn_norm(const Vec3 &pose, const double q[4]
     return o;
 }
 
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
-    return v;
+// Warp max / min of doubles through two 32-bit REDUX steps on an order-preserving key.
+__device__ __forceinline__ unsigned long long ordered_key(double v) {
+    long long b = __double_as_longlong(v);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
 }
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, o));
-    return v;
+__device__ __forceinline__ double from_ordered_key(unsigned long long k) {
+    long long b = (long long)k;
+    b ^= ((~b) >> 63) | (long long)0x8000000000000000ull;
+    return __longlong_as_double(b);
 }
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k) {
+    unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    unsigned mhi = __reduce_max_sync(kFull, hi);
+    unsigned mlo = __reduce_max_sync(kFull, hi == mhi ? lo : 0u);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+__device__ __forceinline__ double warp_max(double v) { return from_ordered_key(warp_max_u64(ordered_key(v))); }
+__device__ __forceinline__ double warp_min(double v) { return from_ordered_key(~warp_max_u64(~ordered_key(v))); }
 
-// One pass of the slab test over a list of planes (all of them, or one cell's active list),
-// split across the warp; max/min are order-independent so the result equals the serial one.
+// One pass of the slab test over a list of planes (all of them, or one cell's list), split
+// across the warp; max/min are order-independent so the result equals the serial one.
 struct SlabResult { double t_in, t_out; bool outside; };
 
 template <bool INDEXED>
@@ -179,7 +210,7 @@ __device__ __forceinline__ SlabResult slab_pass(const DevPack &pk, const Vec3 &f
     double t_in = -INFINITY, t_out = INFINITY;
     bool outside = false;
     for (int i = begin + lane; i < end; i += 32) {
-        int pi = INDEXED ? (int)__ldg(&pk.rc_idx[i]) : i;
+        int pi = INDEXED ? (int)__ldg(&pk.mc_pidx[i]) : i;
         const double2 *p2 = reinterpret_cast<const double2 *>(pk.planes) + 2 * pi;
         double2 lo = __ldg(p2), hi2 = __ldg(p2 + 1);
         double den = (lo.x * d0 + lo.y * d1) + hi2.x * d2;
@@ -201,38 +232,44 @@ __device__ __forceinline__ SlabResult slab_pass(const DevPack &pk, const Vec3 &f
 
 // Exact slab test of the ray frm -> to against the hull half-spaces (shim S1).
 //
-// Fast path: the hull footprint is covered by a grid of cells over (axis0, axis1); each cell
-// lists the planes that are NOT satisfied with a safety margin everywhere in the cell's box
-// (footprint x the cell's depth range).  If the entry point h* found from one cell's list lies in
-// that same box, every unlisted plane j satisfies n_j.h* < off_j - margin, i.e. t_j < t* if it is
-// an entering plane and t_j > t* if it is an exiting one, so max/min over the list decide exactly
-// what max/min over all planes decide, and t* is the global t_in bit for bit.  Otherwise the
-// full plane list is scanned.  Either way the result is the serial slab test's.
+// For any subset S of the planes t_in(S) <= t_in and t_out(S) >= t_out, so
+//   (1) a miss is proven by S alone when outside(S), t_in(S) > t_out(S), t_in(S) > 1 or t_out(S) < 0;
+//   (2) if the entry point h* = frm + d t_in(S) of a move cell's list lies in that cell's box, every
+//       unlisted plane j satisfies n_j.h* < off_j - margin, i.e. t_j < t* if it is an entering plane
+//       and t_j > t* if it is an exiting one: t* is the global t_in bit for bit and the hit / miss
+//       decision over S equals the one over all planes.
+// Otherwise the full plane list is scanned.  Either way the result is the serial slab test's.
+// On an accepted hit `cell` is the move cell holding the hit point (for the vertex candidates), else -1.
 __device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, const Vec3 &to, int lane, Vec3 &hit,
-                                         int &full_scans) {
+                                         int &cell_out, int &full_scans) {
     double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
     SlabResult r;
     bool accepted = false;
-    if (pk.rc_nx > 0) {
-        // the TCP hovers kHookDistance above the surface: first guess = the point that far along the ray
-        Vec3 g = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
+    cell_out = -1;
+    // the TCP hovers kHookDistance above the surface: first guess = the point that far along the ray
+    Vec3 g = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
 #pragma unroll 1
-        for (int attempt = 0; attempt < 2 && !accepted; ++attempt) {
-            int cx = (int)floor((comp(g, pk.axis0) - pk.rc_o0) * pk.rc_inv);
-            int cy = (int)floor((comp(g, pk.axis1) - pk.rc_o1) * pk.rc_inv);
-            if (cx < 0 || cy < 0 || cx >= pk.rc_nx || cy >= pk.rc_ny) break;
-            int cell = cy * pk.rc_nx + cx;
-            int begin = __ldg(&pk.rc_start[cell]), end = __ldg(&pk.rc_start[cell + 1]);
-            if (end <= begin) break;
-            r = slab_pass<true>(pk, frm, d0, d1, d2, begin, end, lane);
-            if (!(r.t_in > -INFINITY) || !(r.t_in < INFINITY)) break;
-            Vec3 h = {frm.x + d0 * r.t_in, frm.y + d1 * r.t_in, frm.z + d2 * r.t_in};
-            int hx = (int)floor((comp(h, pk.axis0) - pk.rc_o0) * pk.rc_inv);
-            int hy = (int)floor((comp(h, pk.axis1) - pk.rc_o1) * pk.rc_inv);
-            double depth = comp(h, 3 - pk.axis0 - pk.axis1);
-            if (hx == cx && hy == cy && depth >= __ldg(&pk.rc_dlo[cell]) && depth <= __ldg(&pk.rc_dhi[cell])) accepted = true;
-            else g = h;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int cx = (int)floor((comp(g, pk.axis0) - pk.mc_o0) * pk.mc_inv);
+        int cy = (int)floor((comp(g, pk.axis1) - pk.mc_o1) * pk.mc_inv);
+        if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) break;
+        const int cell = cy * pk.mc_nx + cx;
+        const int4 hdr = __ldg(reinterpret_cast<const int4 *>(&pk.mc[cell]));
+        if (hdr.y <= 0) break;
+        r = slab_pass<true>(pk, frm, d0, d1, d2, hdr.x, hdr.x + hdr.y, lane);
+        if (r.outside || r.t_in > r.t_out || r.t_in > 1.0 || r.t_out < 0.0) return false;   // (1)
+        if (!(r.t_in > -INFINITY)) break;
+        Vec3 h = {frm.x + d0 * r.t_in, frm.y + d1 * r.t_in, frm.z + d2 * r.t_in};
+        int hx = (int)floor((comp(h, pk.axis0) - pk.mc_o0) * pk.mc_inv);
+        int hy = (int)floor((comp(h, pk.axis1) - pk.mc_o1) * pk.mc_inv);
+        double depth = comp(h, 3 - pk.axis0 - pk.axis1);
+        const double2 dr = __ldg(reinterpret_cast<const double2 *>(&pk.mc[cell]) + 1);
+        if (hx == cx && hy == cy && depth >= dr.x && depth <= dr.y) {                       // (2)
+            accepted = true;
+            cell_out = cell;
+            break;
         }
+        g = h;
     }
     if (!accepted) {
         r = slab_pass<false>(pk, frm, d0, d1, d2, 0, pk.n_planes, lane);
@@ -245,10 +282,34 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, con
     return true;
 }
 
-// cKDTree.query(point, k=1) over the side-masked vertices (bullet_paint_wrapper.py:526): grid
-// search over (axis0, axis1) with ring expansion; exact FP64 squared distances, lowest pack
-// index on ties.  Returns the pack vertex index.
-__device__ __forceinline__ int nearest_vertex(const DevPack &pk, const Vec3 &p, int lane) {
+// cKDTree.query(point, k=1) over the side-masked vertices (bullet_paint_wrapper.py:526): exact
+// FP64 squared distances, lowest pack index on ties.  Returns the vertex's record word
+// (rec_begin << 8 | deg), or 0xFFFFFFFF if there is none.
+//
+// Fast path: the move cell that holds the point lists every vertex that can be nearest to a
+// point of its box, so the arg-min over that list is the arg-min over all vertices.
+__device__ __forceinline__ unsigned nearest_vertex_cell(const DevPack &pk, const Vec3 &p, int cell, int lane) {
+    const int4 hdr = __ldg(reinterpret_cast<const int4 *>(&pk.mc[cell]));
+    unsigned long long best = ~0ull;   // ordered (d2 bits) -- d2 >= 0 so the raw bits order correctly
+    unsigned bid = 0xFFFFFFFFu, brec = 0xFFFFFFFFu;
+    for (int i = lane; i < hdr.w; i += 32) {
+        const double2 *c = reinterpret_cast<const double2 *>(&pk.mc_vc[hdr.z + i]);
+        double2 xy = __ldg(c), zr = __ldg(c + 1);
+        double dx = xy.x - p.x, dy = xy.y - p.y, dz = zr.x - p.z;
+        double d = dx * dx + dy * dy + dz * dz;
+        unsigned long long key = (unsigned long long)__double_as_longlong(d);
+        unsigned long long meta = (unsigned long long)__double_as_longlong(zr.y);
+        unsigned id = (unsigned)meta, rec = (unsigned)(meta >> 32);
+        if (key < best || (key == best && id < bid)) { best = key; bid = id; brec = rec; }
+    }
+    unsigned long long m = ~warp_max_u64(~best);
+    unsigned wid = __reduce_min_sync(kFull, best == m ? bid : 0xFFFFFFFFu);
+    unsigned src = __ffs(__ballot_sync(kFull, best == m && bid == wid)) - 1;
+    return __shfl_sync(kFull, brec, src);
+}
+
+// Slow path (point outside every accepted cell box): grid search over (axis0, axis1) with ring expansion.
+__device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const Vec3 &p, int lane) {
     double q0 = comp(p, pk.axis0), q1 = comp(p, pk.axis1);
     int cx = (int)floor((q0 - pk.vg_o0) * pk.vg_inv);
     int cy = (int)floor((q1 - pk.vg_o1) * pk.vg_inv);
@@ -290,30 +351,35 @@ __device__ __forceinline__ int nearest_vertex(const DevPack &pk, const Vec3 &p, 
         m -= 1e-9;
         if (m > 0.0 && best_d < m * m) break;
     }
-    return best_i;
+    if (best_i == 0x7fffffff) return 0xFFFFFFFFu;
+    return __ldg(&pk.vrec[best_i]);
 }
 
 // Part._get_hook_point + _get_closest_bary (bullet_paint_wrapper.py:525-534, 508-523, 154-185):
-// incident front triangles of the nearest vertex, one per lane.
-__device__ __forceinline__ bool hook_point(const DevPack &pk, const Vec3 &point, int lane, Vec3 &pose, Vec3 &orn) {
-    int v = nearest_vertex(pk, point, lane);
-    if (v == 0x7fffffff) return false;
-    int begin = __ldg(&pk.vtri_start[v]), end = __ldg(&pk.vtri_start[v + 1]);
-    int deg = end - begin;
-    if (deg <= 0) return false;
+// incident front triangles of the nearest vertex, one per lane.  Returns the picked triangle's
+// record (whose tail holds n, quat_from_normal(-n) and the shot-centre offset), or nullptr.
+__device__ __forceinline__ const double *hook_triangle(const DevPack &pk, const Vec3 &point, int cell, int lane) {
+    unsigned rec = cell >= 0 ? nearest_vertex_cell(pk, point, cell, lane) : nearest_vertex_grid(pk, point, lane);
+    if (rec == 0xFFFFFFFFu) return nullptr;
+    const int deg = (int)(rec & 0xffu);
+    const double *base = pk.trirec + (size_t)(rec >> 8) * kTriRec;
+    if (deg <= 0) return nullptr;
     int pick = -1;
     double run_max = -INFINITY;   // max of min_uvw over the lanes scanned so far
     int run_arg = -1;             // last list position attaining it
-    for (int base = 0; base < deg; base += 32) {
-        int k = base + lane;
+    for (int b0 = 0; b0 < deg; b0 += 32) {
+        int k = b0 + lane;
         bool inside = false;
         double m = -INFINITY;
         if (k < deg) {
-            const double *t = pk.tri + 16 * (size_t)__ldg(&pk.vtri_idx[begin + k]);
-            double v2x = point.x - __ldg(t + 0), v2y = point.y - __ldg(t + 1), v2z = point.z - __ldg(t + 2);
-            double d20 = npdot3(v2x, v2y, v2z, __ldg(t + 3), __ldg(t + 4), __ldg(t + 5));
-            double d21 = npdot3(v2x, v2y, v2z, __ldg(t + 6), __ldg(t + 7), __ldg(t + 8));
-            double d00 = __ldg(t + 9), d01 = __ldg(t + 10), d11 = __ldg(t + 11), inv = __ldg(t + 12);
+            const double2 *t = reinterpret_cast<const double2 *>(base + (size_t)k * kTriRec);
+            double2 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2), t3 = __ldg(t + 3), t4 = __ldg(t + 4),
+                    t5 = __ldg(t + 5), t6 = __ldg(t + 6);
+            // a = (t0.x t0.y t1.x)  v0 = (t1.y t2.x t2.y)  v1 = (t3.x t3.y t4.x)  d00 t4.y  d01 t5.x  d11 t5.y  inv t6.x
+            double v2x = point.x - t0.x, v2y = point.y - t0.y, v2z = point.z - t1.x;
+            double d20 = npdot3(v2x, v2y, v2z, t1.y, t2.x, t2.y);
+            double d21 = npdot3(v2x, v2y, v2z, t3.x, t3.y, t4.x);
+            double d00 = t4.y, d01 = t5.x, d11 = t5.y, inv = t6.x;
             double bv = (d11 * d20 - d01 * d21) * inv;
             double bw = (d00 * d21 - d01 * d20) * inv;
             double bu = 1.0 - bv - bw;
@@ -322,22 +388,16 @@ __device__ __forceinline__ bool hook_point(const DevPack &pk, const Vec3 &point,
             m = fmin(fmin(bu, bv), bw);
         }
         unsigned in_mask = __ballot_sync(kFull, inside);
-        if (in_mask) { pick = base + __ffs(in_mask) - 1; break; }
+        if (in_mask) { pick = b0 + __ffs(in_mask) - 1; break; }
         double cm = warp_max(m);
         if (cm >= run_max) {   // `>=`: a later triangle wins ties (bullet_paint_wrapper.py:520)
             unsigned eq = __ballot_sync(kFull, k < deg && m == cm);
             run_max = cm;
-            run_arg = base + 31 - __clz(eq);
+            run_arg = b0 + 31 - __clz(eq);
         }
     }
     if (pick < 0) pick = (run_max >= -1.0) ? run_arg : 0;   // closest_uvw starts at -1 (:509)
-    const double *t = pk.tri + 16 * (size_t)__ldg(&pk.vtri_idx[begin + pick]);
-    double nx = __ldg(t + 13), ny = __ldg(t + 14), nz = __ldg(t + 15);
-    pose.x = point.x + nx * kHookDistance;
-    pose.y = point.y + ny * kHookDistance;
-    pose.z = point.z + nz * kHookDistance;
-    orn.x = -nx; orn.y = -ny; orn.z = -nz;
-    return true;
+    return base + (size_t)pick * kTriRec;
 }
 
 // bullet_paint_wrapper.py:844-851

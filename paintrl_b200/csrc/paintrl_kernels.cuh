@@ -5,10 +5,13 @@
 //   stamp   5 ball queries over the binned texel table, colour update, overlap bookkeeping
 //                                                     bullet_paint_wrapper.py:568-577, 352-434
 //   score   reward / penalty / termination                                   robot_gym_env.py:289-340
-//   observe normalised pose + section/grid histogram over the env's whole status plane
+//   observe normalised pose + section/grid observation
 //                                                     bullet_paint_wrapper.py:965-978, 1045-1139
-// The status plane (1 byte per front texel in RGB mode, int16 in HSI mode) is the only per-env
-// array; it is read once in full per step (128-bit loads) and written only inside the footprint.
+// Per-environment arrays: the status plane (1 byte per front texel in RGB mode, int16 in HSI mode,
+// texels sorted by spatial bin) and one 16-bit counter per bin = number of texels of the bin whose
+// "painted" predicate (first channel == 255) differs from the fresh texture's.  The stamp keeps
+// the counters current, so the 4-sector observation reads the counters of the bins that lie
+// wholly inside one sector and classifies texel by texel only the pose's bin row and bin column.
 #pragma once
 #include "paintrl_device.cuh"
 
@@ -28,176 +31,186 @@ struct StepIO {
     unsigned long long *stats;   // [0] env steps, [1] episodes ended, [2] footprint texels, [3] full-plane ray scans
 };
 
-__device__ __forceinline__ uint4 ldcg16(const void *p) { return __ldcg(reinterpret_cast<const uint4 *>(p)); }
+// Per-environment dynamic arrays.
+template <int COLOR>
+struct EnvArrays {
+    EnvState *states;
+    typename StatusT<COLOR>::type *planes;   // [num_envs][n_pad]
+    unsigned *bin_cnt;                       // [num_envs][n_bins_pad / 2]   two 16-bit counters per word
+    unsigned *grid_cnt;                      // [num_envs][n_gcells_pad]     grid-observation cells (grid mode only)
+};
+
+// Per-warp shared scratch.
+struct WarpScratch {
+    double centers[kPaintPerAction][3];
+    int seg_begin[32];
+    int seg_cum[33];
+    int hist[2 * kMaxObs];                   // K != 4 section histogram
+};
+
+__device__ __forceinline__ int warp_inclusive_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+// Visits every index of a list of contiguous index ranges with all 32 lanes busy.
+//   seg(s, begin, len)   range s of n_seg (called by lane s % 32)
+//   body(j, active)      called warp-uniformly; j is valid when active
+template <typename SegFn, typename BodyFn>
+__device__ __forceinline__ void for_each_in_segments(int n_seg, int lane, WarpScratch &ws, SegFn seg, BodyFn body) {
+    for (int s0 = 0; s0 < n_seg; s0 += 32) {
+        int b = 0, l = 0;
+        if (s0 + lane < n_seg) seg(s0 + lane, b, l);
+        const int incl = warp_inclusive_scan(l, lane);
+        __syncwarp();
+        ws.seg_begin[lane] = b;
+        ws.seg_cum[lane + 1] = incl;
+        if (lane == 0) ws.seg_cum[0] = 0;
+        __syncwarp();
+        const int total = __shfl_sync(kFull, incl, 31);
+        int k = 0;
+        for (int it0 = 0; it0 < total; it0 += 32) {
+            const int it = it0 + lane;
+            const bool active = it < total;
+            int j = 0;
+            if (active) {
+                while (it >= ws.seg_cum[k + 1]) ++k;
+                j = ws.seg_begin[k] + (it - ws.seg_cum[k]);
+            }
+            body(j, active);
+        }
+    }
+    __syncwarp();
+}
 
 // ------------------------------------------------------------------------------ observation
-// Section observation with 4 sectors (bullet_paint_wrapper.py:1033-1061).
+// 4-sector observation (bullet_paint_wrapper.py:1033-1061): for every front texel, rx / ry = texel
+// position - TCP position along the principal axes; skipped if both are 0; sector 0 if rx>0,ry>0,
+// 1 if rx<0,ry>0, 2 if rx<0,ry<0, else 3; obs[s] = #(status != 255) / #texels of the sector.
 //
-// rx > 0 <=> rank >= hi, rx < 0 <=> rank < lo, where `rank` is the texel coordinate's index among
-// the sorted distinct coordinates of the part and [lo, hi) is the rank interval equal to the
-// pose's coordinate (found once per step by binary search): integer compares replace the FP64
-// subtraction and are exactly equivalent.  Texels are laid out in chunks of 16 (one 128-bit load
-// in RGB mode) with a precomputed rank bounding box per chunk; a chunk whose box lies strictly on
-// one side of the pose on both axes belongs wholly to one sector and is counted with byte-SIMD
-// popcounts, the others (the pose's row and column, ~15 %) are queued in shared memory and then
-// classified texel by texel, one queued chunk per lane.
-template <typename RankT>
-__device__ __forceinline__ void rank_bounds(const double *uniq, int n, double v, int lane, RankT &lo, RankT &hi) {
-    // 32-ary search: every round each lane probes one pivot; ~3 rounds for 10^4 values
-    int a = 0, b = n;            // lower_bound: first index with uniq[i] >= v lies in [a, b]
-    while (b - a > 0) {
-        int span = b - a, step = (span + 31) >> 5;
-        int i = a + lane * step;
-        bool less = (i < b) && (__ldg(&uniq[i]) < v);
-        unsigned m = __ballot_sync(kFull, less);
-        int k = __popc(m);       // pivots 0..k-1 are < v (monotone)
-        int na = (k == 0) ? a : a + (k - 1) * step + 1;
-        int nb = (k == 32 || a + k * step >= b) ? b : a + k * step;
-        a = na; b = nb;
-        if (step == 1) break;
-    }
-    int l = a;
-    int c = l, d = n;            // upper_bound from l
-    while (d - c > 0) {
-        int span = d - c, step = (span + 31) >> 5;
-        int i = c + lane * step;
-        bool le = (i < d) && (__ldg(&uniq[i]) <= v);
-        unsigned m = __ballot_sync(kFull, le);
-        int k = __popc(m);
-        int nc = (k == 0) ? c : c + (k - 1) * step + 1;
-        int nd = (k == 32 || c + k * step >= d) ? d : c + k * step;
-        c = nc; d = nd;
-        if (step == 1) break;
-    }
-    lo = (RankT)l;
-    hi = (RankT)c;
-}
-
-// number of painted (== 255) entries among the 16 status values of one chunk
-__device__ __forceinline__ int painted_in_word_u8(unsigned w) {
-    unsigned x = ~w;                                   // zero byte <=> painted
-    unsigned y = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-    y = ~(y | x | 0x7F7F7F7Fu);                        // 0x80 in every zero byte, exact
-    return __popc(y);
-}
-__device__ __forceinline__ int painted_in_word_i16(unsigned w) {
-    unsigned x = w ^ 0x00FF00FFu;                      // zero halfword <=> value == 255
-    unsigned y = (x & 0x7FFF7FFFu) + 0x7FFF7FFFu;
-    y = ~(y | x | 0x7FFF7FFFu);                        // 0x8000 in every zero halfword, exact
-    return __popc(y);
-}
+// A texel's bin index along an axis is a monotone function of its coordinate, evaluated with the
+// same two FP64 operations for texels (host) and pose (here), so every texel of a bin left of /
+// right of / above / below the pose's bin has rx < 0 / rx > 0 / ry > 0 / ry < 0: such bins belong
+// wholly to one sector and contribute their size (2-D prefix table) and their flip counter.
+// Only the texels of the pose's own bin row and bin column are compared coordinate by coordinate.
 template <int COLOR>
-__device__ __forceinline__ int painted_in_chunk(const typename StatusT<COLOR>::type *p) {
-    if (COLOR == 0) {
-        uint4 v = ldcg16(p);
-        return painted_in_word_u8(v.x) + painted_in_word_u8(v.y) + painted_in_word_u8(v.z) + painted_in_word_u8(v.w);
-    } else {
-        uint4 v = ldcg16(p), w = ldcg16(p + 8);
-        return painted_in_word_i16(v.x) + painted_in_word_i16(v.y) + painted_in_word_i16(v.z) + painted_in_word_i16(v.w) +
-               painted_in_word_i16(w.x) + painted_in_word_i16(w.y) + painted_in_word_i16(w.z) + painted_in_word_i16(w.w);
-    }
-}
-
-template <typename RankT> struct ChunkBox { RankT r0min, r0max, r1min, r1max; };
-
-constexpr int kMixedQueue = 128;   // per-warp queue of mixed chunks (ints, aliases the histogram area)
-
-// texel-by-texel classification of one chunk (lane-private); adds into 4x16-bit packed counters
-template <int COLOR, typename RankT>
-__device__ __forceinline__ void classify_chunk(const DevPack &pk, const typename StatusT<COLOR>::type *status, int chunk,
-                                               RankT lo0, RankT hi0, RankT lo1, RankT hi1,
-                                               unsigned long long &ptot, unsigned long long &popen) {
-    typedef typename StatusT<COLOR>::type S;
-    const RankT *r0 = reinterpret_cast<const RankT *>(pk.rank0) + (size_t)chunk * 16;
-    const RankT *r1 = reinterpret_cast<const RankT *>(pk.rank1) + (size_t)chunk * 16;
-    const RankT pad = (RankT)~(RankT)0;
-    RankT a0[16], a1[16];
-    S sv[16];
-    constexpr int kRankLoads = 16 * sizeof(RankT) / 16;
-#pragma unroll
-    for (int q = 0; q < kRankLoads; ++q) {
-        reinterpret_cast<uint4 *>(a0)[q] = __ldg(reinterpret_cast<const uint4 *>(r0) + q);
-        reinterpret_cast<uint4 *>(a1)[q] = __ldg(reinterpret_cast<const uint4 *>(r1) + q);
-    }
-#pragma unroll
-    for (int q = 0; q < (int)(16 * sizeof(S) / 16); ++q)
-        reinterpret_cast<uint4 *>(sv)[q] = ldcg16(status + (size_t)chunk * 16 + q * (16 / sizeof(S)));
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-        RankT x = a0[e], y = a1[e];
-        bool px = x >= hi0, nx = x < lo0, py = y >= hi1, ny = y < lo1;
-        bool skip = (x == pad) || !(px || nx || py || ny);
-        int q = (px && py) ? 0 : ((nx && py) ? 1 : ((nx && ny) ? 2 : 3));
-        unsigned long long one = skip ? 0ull : (1ull << (16 * q));
-        ptot += one;
-        popen += ((int)sv[e] != kPainted) ? one : 0ull;
-    }
-}
-
-template <int COLOR, typename RankT>
 __device__ __forceinline__ void section4_counts(const DevPack &pk, const typename StatusT<COLOR>::type *status,
-                                                const Vec3 &pose, int lane, int *queue /*smem, kMixedQueue ints*/,
+                                                const unsigned *bin_cnt, const Vec3 &pose, int lane, WarpScratch &ws,
                                                 int tot[4], int open[4]) {
-    RankT lo0, hi0, lo1, hi1;
-    rank_bounds<RankT>(pk.uniq0, pk.n_uniq0, comp(pose, pk.axis0), lane, lo0, hi0);
-    rank_bounds<RankT>(pk.uniq1, pk.n_uniq1, comp(pose, pk.axis1), lane, lo1, hi1);
-    const ChunkBox<RankT> *boxes = reinterpret_cast<const ChunkBox<RankT> *>(pk.chunk_box);
-    const int n_chunks = pk.n_pad >> 4;
-    // per-lane accumulators: pure chunks counted as (#chunks, open texels) per sector
-    int pure_chunks[4] = {0, 0, 0, 0}, pure_open[4] = {0, 0, 0, 0};
-    unsigned long long ptot = 0, popen = 0;   // texel-wise path, 4 x 16-bit fields
-    int mix_tot[4] = {0, 0, 0, 0}, mix_open[4] = {0, 0, 0, 0};
-    int queued = 0;                            // warp-uniform
-    auto drain = [&]() {
-        __syncwarp();
-        for (int base = 0; base < queued; base += 32) {
-            if (base + lane < queued)
-                classify_chunk<COLOR, RankT>(pk, status, queue[base + lane], lo0, hi0, lo1, hi1, ptot, popen);
+    const double p0 = comp(pose, pk.axis0), p1 = comp(pose, pk.axis1);
+    const int nx = pk.tb_nx, ny = pk.tb_ny;
+    double f0 = floor((p0 - pk.tb_o0) * pk.tb_inv), f1 = floor((p1 - pk.tb_o1) * pk.tb_inv);
+    const int px = (f0 < 0.0) ? -1 : (f0 >= (double)nx ? nx : (int)f0);
+    const int py = (f1 < 0.0) ? -1 : (f1 >= (double)ny ? ny : (int)f1);
+
+    // ---- bins wholly inside a sector: sizes from the static prefix table
+    const int W = nx + 1;
+    auto P = [&](int iy, int ix) { return __ldg(&pk.tb_prefix[iy * W + ix]); };   // sum over rows < iy, cols < ix
+    const int xl = max(px, 0), xr = min(px + 1, nx), yb = max(py, 0), ya = min(py + 1, ny);
+    const int P_ny_nx = P(ny, nx), P_ny_xr = P(ny, xr), P_ny_xl = P(ny, xl);
+    const int P_ya_nx = P(ya, nx), P_ya_xr = P(ya, xr), P_ya_xl = P(ya, xl);
+    const int P_yb_nx = P(yb, nx), P_yb_xr = P(yb, xr), P_yb_xl = P(yb, xl);
+    int pure_tot[4];
+    pure_tot[0] = (P_ny_nx - P_ny_xr) - (P_ya_nx - P_ya_xr);   // right, above
+    pure_tot[1] = P_ny_xl - P_ya_xl;                           // left, above
+    pure_tot[2] = P_yb_xl;                                     // left, below
+    pure_tot[3] = P_yb_nx - P_yb_xr;                           // right, below
+
+    // ---- their flip counters: two 16-bit counters per word, lanes own word columns
+    int flips[4] = {0, 0, 0, 0};
+    const int wpr = nx >> 1;
+    for (int w0 = 0; w0 < wpr; w0 += 32) {
+        const int w = w0 + lane;
+        unsigned mask_l = 0, mask_r = 0;
+        if (w < wpr) {
+            mask_l = (2 * w < px ? 0x0000ffffu : 0u) | (2 * w + 1 < px ? 0xffff0000u : 0u);
+            mask_r = (2 * w > px ? 0x0000ffffu : 0u) | (2 * w + 1 > px ? 0xffff0000u : 0u);
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {          // fields hold at most 16 * (kMixedQueue/32) = 64 each
-            mix_tot[q] += (int)((ptot >> (16 * q)) & 0xffff);
-            mix_open[q] += (int)((popen >> (16 * q)) & 0xffff);
-        }
-        ptot = popen = 0;
-        queued = 0;
-        __syncwarp();
-    };
-    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
-        const int c = c0 + lane;
-        bool mixed = false;
-        if (c < n_chunks) {
-            ChunkBox<RankT> bx = boxes[c];
-            bool nx = bx.r0max < lo0, px = bx.r0min >= hi0, ny = bx.r1max < lo1, py = bx.r1min >= hi1;
-            if ((nx || px) && (ny || py) && bx.r0min <= bx.r0max) {   // inverted box = chunk with padding
-                int painted = painted_in_chunk<COLOR>(status + (size_t)c * 16);
-                int q = py ? (px ? 0 : 1) : (px ? 3 : 2);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    pure_chunks[k] += (q == k) ? 1 : 0;
-                    pure_open[k] += (q == k) ? 16 - painted : 0;
-                }
-            } else {
-                mixed = true;
+        unsigned al = 0, ar = 0, bl = 0, br = 0;        // packed 2 x 16-bit partial sums
+        const unsigned *col = bin_cnt + w;
+        const int wl = (w < wpr) ? w : 0;
+        (void)wl;
+        int iy = 0;
+        const int below_end = min(max(py, 0), ny);
+        if (w < wpr) {
+#pragma unroll 4
+            for (iy = 0; iy < below_end; ++iy) {
+                unsigned c = __ldcg(col + (size_t)iy * wpr);
+                bl += c & mask_l;
+                br += c & mask_r;
+            }
+#pragma unroll 4
+            for (iy = min(py + 1, ny); iy < ny; ++iy) {
+                if (iy < 0) continue;
+                unsigned c = __ldcg(col + (size_t)iy * wpr);
+                al += c & mask_l;
+                ar += c & mask_r;
             }
         }
-        unsigned mm = __ballot_sync(kFull, mixed);
-        if (mm) {
-            if (mixed) queue[queued + __popc(mm & ((1u << lane) - 1))] = c;
-            queued += __popc(mm);
-            if (queued > kMixedQueue - 32) drain();
-        }
+        flips[0] += (int)(ar & 0xffffu) + (int)(ar >> 16);
+        flips[1] += (int)(al & 0xffffu) + (int)(al >> 16);
+        flips[2] += (int)(bl & 0xffffu) + (int)(bl >> 16);
+        flips[3] += (int)(br & 0xffffu) + (int)(br >> 16);
     }
-    if (queued) drain();
+
+    // ---- the pose's bin row and bin column, texel by texel
+    const double *c0 = pk.axis0 == 0 ? pk.tx : (pk.axis0 == 1 ? pk.ty : pk.tz);
+    const double *c1 = pk.axis1 == 0 ? pk.tx : (pk.axis1 == 1 ? pk.ty : pk.tz);
+    const bool row_ok = (py >= 0 && py < ny), col_ok = (px >= 0 && px < nx);
+    const int n_seg = (row_ok ? 1 : 0) + (col_ok ? ny - (row_ok ? 1 : 0) : 0);
+    unsigned long long ptot = 0, popen = 0;   // 4 x 16-bit fields per lane
+    int carry_tot[4] = {0, 0, 0, 0}, carry_open[4] = {0, 0, 0, 0};
+    int since_flush = 0;
+    for_each_in_segments(
+        n_seg, lane, ws,
+        [&](int s, int &b, int &l) {
+            if (row_ok && s == 0) {
+                b = __ldg(&pk.tb_start[py * nx]);
+                l = __ldg(&pk.tb_start[py * nx + nx]) - b;
+            } else {
+                int iy = s - (row_ok ? 1 : 0);
+                if (row_ok && iy >= py) ++iy;
+                b = __ldg(&pk.tb_start[iy * nx + px]);
+                l = __ldg(&pk.tb_start[iy * nx + px + 1]) - b;
+            }
+        },
+        [&](int j, bool active) {
+            if (active) {
+                const double x0 = __ldg(&c0[j]), x1 = __ldg(&c1[j]);
+                const int s = (int)__ldcg(&status[j]);
+                const bool gx = x0 > p0, lx = x0 < p0, gy = x1 > p1, ly = x1 < p1;
+                const bool skip = !(gx || lx || gy || ly);
+                const int q = (gx && gy) ? 0 : ((lx && gy) ? 1 : ((lx && ly) ? 2 : 3));
+                const unsigned long long one = skip ? 0ull : (1ull << (16 * q));
+                ptot += one;
+                popen += (s != kPainted) ? one : 0ull;
+            }
+            if (++since_flush == 0xffff) {      // keep the 16-bit fields from overflowing
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    carry_tot[q] += (int)((ptot >> (16 * q)) & 0xffff);
+                    carry_open[q] += (int)((popen >> (16 * q)) & 0xffff);
+                }
+                ptot = popen = 0;
+                since_flush = 0;
+            }
+        });
+    const bool init_painted = (pk.status_init == kPainted);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        tot[q] = __reduce_add_sync(kFull, pure_chunks[q] * 16 + mix_tot[q]);
-        open[q] = __reduce_add_sync(kFull, pure_open[q] + mix_open[q]);
+        const int st = __reduce_add_sync(kFull, carry_tot[q] + (int)((ptot >> (16 * q)) & 0xffff));
+        const int so = __reduce_add_sync(kFull, carry_open[q] + (int)((popen >> (16 * q)) & 0xffff));
+        const int fl = __reduce_add_sync(kFull, flips[q]);
+        tot[q] = pure_tot[q] + st;
+        open[q] = (init_painted ? fl : pure_tot[q] - fl) + so;
     }
 }
 
-// Section observation with K != 4 sectors (atan2 path, bullet_paint_wrapper.py:1026-1031) and the
-// grid observation (bullet_paint_wrapper.py:1126-1139) histogram into per-warp shared memory.
+// Section observation with K != 4 sectors (atan2 path, bullet_paint_wrapper.py:1026-1031): full scan.
 template <int COLOR>
 __device__ __forceinline__ void sectionk_counts(const DevPack &pk, const typename StatusT<COLOR>::type *status,
                                                 const Vec3 &pose, int section, int lane, int *hist /*[2*kMaxObs] smem*/) {
@@ -220,22 +233,12 @@ __device__ __forceinline__ void sectionk_counts(const DevPack &pk, const typenam
     __syncwarp();
 }
 
-template <int COLOR>
-__device__ __forceinline__ void grid_counts(const DevPack &pk, const typename StatusT<COLOR>::type *status,
-                                            int cells, int lane, int *hist /*smem*/) {
-    for (int i = lane; i < cells; i += 32) hist[i] = 0;
-    __syncwarp();
-    for (int j = lane; j < pk.n_texels; j += 32) {
-        if ((int)__ldcg(&status[j]) == kPainted) atomicAdd(&hist[__ldg(&pk.gcell[j])], 1);
-    }
-    __syncwarp();
-}
-
 // robot_gym_env.py:306-319 _augmented_observation; every lane returns, lanes < obs_dim write.
-template <int COLOR, typename RankT>
+template <int COLOR>
 __device__ __forceinline__ void write_observation(const DevPack &pk, const DevConfig &cfg,
-                                                  const typename StatusT<COLOR>::type *status, const Vec3 &pose,
-                                                  int lane, int *hist, double *obs_a, double *obs_b) {
+                                                  const typename StatusT<COLOR>::type *status, const unsigned *bin_cnt,
+                                                  const unsigned *grid_cnt, const Vec3 &pose, int lane, WarpScratch &ws,
+                                                  double *obs_a, double *obs_b) {
     double a1, a2;
     normalized_pose(pk, pose, a1, a2);
     const int grad = cfg.obs_grad;
@@ -247,22 +250,23 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const DevCo
         }
         return;
     }
-    if (cfg.obs_mode == 1) {   // grid
+    if (cfg.obs_mode == 1) {   // grid (bullet_paint_wrapper.py:1126-1139): painted texels per cell from the flip counters
         const int cells = grad * grad;
-        grid_counts<COLOR>(pk, status, cells, lane, hist);
+        const bool init_painted = (pk.status_init == kPainted);
         for (int c = lane; c < cells; c += 32) {
-            int total = __ldg(&pk.gtotal[c]);
-            double v = total == 0 ? 0.0 : 1.0 - (double)hist[c] / (double)total;
+            const int total = __ldg(&pk.gtotal[c]);
+            const int fl = (int)__ldcg(&grid_cnt[c]);
+            const int painted = init_painted ? total - fl : fl;
+            double v = total == 0 ? 0.0 : 1.0 - (double)painted / (double)total;
             if (obs_a) obs_a[c] = v;
             if (obs_b) obs_b[c] = v;
         }
-        __syncwarp();
         return;
     }
     // section / discrete
     if (grad == 4) {
         int tot[4], open[4];
-        section4_counts<COLOR, RankT>(pk, status, pose, lane, hist, tot, open);
+        section4_counts<COLOR>(pk, status, bin_cnt, pose, lane, ws, tot, open);
         if (lane < 4) {
             int t = lane == 0 ? tot[0] : (lane == 1 ? tot[1] : (lane == 2 ? tot[2] : tot[3]));
             int o = lane == 0 ? open[0] : (lane == 1 ? open[1] : (lane == 2 ? open[2] : open[3]));
@@ -271,9 +275,9 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const DevCo
             if (obs_b) obs_b[lane] = v;
         }
     } else {
-        sectionk_counts<COLOR>(pk, status, pose, grad, lane, hist);
+        sectionk_counts<COLOR>(pk, status, pose, grad, lane, ws.hist);
         for (int s = lane; s < grad; s += 32) {
-            int t = hist[s], o = hist[kMaxObs + s];
+            int t = ws.hist[s], o = ws.hist[kMaxObs + s];
             double v = t == 0 ? 0.0 : (double)o / (double)t;
             if (obs_a) obs_a[s] = v;
             if (obs_b) obs_b[s] = v;
@@ -294,9 +298,11 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const DevCo
 }
 
 // ------------------------------------------------------------------------------ reset pieces
-// Part.reset_part (bullet_paint_wrapper.py:706-708): restore the init colour, 128-bit stores.
+// Part.reset_part (bullet_paint_wrapper.py:706-708): restore the init colour and clear the flip
+// counters, 128-bit stores.
 template <int COLOR>
-__device__ __forceinline__ void fill_status(const DevPack &pk, typename StatusT<COLOR>::type *status, int lane) {
+__device__ __forceinline__ void fill_status(const DevPack &pk, typename StatusT<COLOR>::type *status, unsigned *bin_cnt,
+                                            unsigned *grid_cnt, int lane) {
     typedef typename StatusT<COLOR>::type S;
     constexpr int kPer = 16 / sizeof(S);
     uint4 v;
@@ -304,6 +310,10 @@ __device__ __forceinline__ void fill_status(const DevPack &pk, typename StatusT<
 #pragma unroll
     for (int k = 0; k < kPer; ++k) e[k] = (S)pk.status_init;
     for (int j0 = lane * kPer; j0 < pk.n_pad; j0 += 32 * kPer) *reinterpret_cast<uint4 *>(status + j0) = v;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int w = lane * 4; w < pk.n_bins_pad / 2; w += 128) *reinterpret_cast<uint4 *>(bin_cnt + w) = z;
+    if (grid_cnt)
+        for (int w = lane * 4; w < pk.n_gcells_pad; w += 128) *reinterpret_cast<uint4 *>(grid_cnt + w) = z;
 }
 
 // Robot.reset(pose) (robot.py:366-372, 208-212)
@@ -319,8 +329,8 @@ __device__ __forceinline__ void robot_reset(EnvState &st, const double *pos, con
 // PaintGymEnv.reset (robot_gym_env.py:370-387) minus the observation
 template <int COLOR>
 __device__ __forceinline__ void env_reset(const DevPack &pk, EnvState &st, typename StatusT<COLOR>::type *status,
-                                          int start_index, int lane) {
-    fill_status<COLOR>(pk, status, lane);
+                                          unsigned *bin_cnt, unsigned *grid_cnt, int start_index, int lane) {
+    fill_status<COLOR>(pk, status, bin_cnt, grid_cnt, lane);
     st.flags &= ~kFlagHasLast;                 // _last_painted_pixels = []
     st.step_counter = 0;
     st.total_return = 0.0;
@@ -344,49 +354,198 @@ __device__ __forceinline__ void store_state(EnvState *g, const EnvState &st, int
     if (lane < 8) reinterpret_cast<double2 *>(g)[lane] = v;
 }
 
+template <int COLOR>
+__device__ __forceinline__ unsigned *bin_cnt_of(const DevPack &pk, const EnvArrays<COLOR> &ea, int env) {
+    return ea.bin_cnt + (size_t)env * (pk.n_bins_pad >> 1);
+}
+template <int COLOR>
+__device__ __forceinline__ unsigned *grid_cnt_of(const DevPack &pk, const EnvArrays<COLOR> &ea, int env) {
+    return ea.grid_cnt ? ea.grid_cnt + (size_t)env * pk.n_gcells_pad : nullptr;
+}
+
+__device__ __forceinline__ int auto_start_index(const DevPack &pk, const DevConfig &cfg, int env, int episode) {
+    return (int)(splitmix64(cfg.seed ^ splitmix64(((unsigned long long)env << 32) | (unsigned)episode)) %
+                 (unsigned long long)pk.n_starts);
+}
+
+// ------------------------------------------------------------------------------ stamp
+// Part.fast_paint x 5 (bullet_paint_wrapper.py:568-577) + colour handlers (:352-434).
+//
+// Candidates come from the texel bins overlapping the shots' bounding box, flattened over the bin
+// rows.  The ball test `dx*dx + dy*dy + dz*dz <= r*r` (FP64, exactly the kd-tree's) is decided in
+// FP32 on origin-relative coordinates whenever the FP32 value is further than kBallEps from r*r --
+// the FP32 evaluation differs from the FP64 one by < 2e-8 for |d| <= 2r -- and in FP64 otherwise.
+constexpr float kBallEps = 1e-7f;
+
+template <int COLOR>
+__device__ __forceinline__ void stamp(const DevPack &pk, const DevConfig &cfg, typename StatusT<COLOR>::type *status,
+                                      unsigned *bin_cnt, unsigned *grid_cnt, const Vec3 &lastc, bool has_last, int lane,
+                                      WarpScratch &ws, int &n_new_out, int &n_possible_out) {
+    typedef typename StatusT<COLOR>::type S;
+    constexpr int NS = kPaintPerAction;
+    const double r2 = kPaintRadius * kPaintRadius;
+    const float r2f = (float)r2;
+    double cx[NS + 1], cy[NS + 1], cz[NS + 1];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { cx[s] = ws.centers[s][0]; cy[s] = ws.centers[s][1]; cz[s] = ws.centers[s][2]; }
+    cx[NS] = lastc.x; cy[NS] = lastc.y; cz[NS] = lastc.z;
+    float fx[NS + 1], fy[NS + 1], fz[NS + 1];
+#pragma unroll
+    for (int s = 0; s <= NS; ++s) {
+        fx[s] = (float)(cx[s] - pk.org0); fy[s] = (float)(cy[s] - pk.org1); fz[s] = (float)(cz[s] - pk.org2);
+    }
+    double lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        double c0 = pk.axis0 == 0 ? cx[s] : (pk.axis0 == 1 ? cy[s] : cz[s]);
+        double c1 = pk.axis1 == 0 ? cx[s] : (pk.axis1 == 1 ? cy[s] : cz[s]);
+        lo0 = fmin(lo0, c0); hi0 = fmax(hi0, c0);
+        lo1 = fmin(lo1, c1); hi1 = fmax(hi1, c1);
+    }
+    const double margin = kPaintRadius + 1e-9;
+    // clamp in FP64 first: an off-part TCP can be far away from the bin grid
+    double b0 = floor((lo0 - margin - pk.tb_o0) * pk.tb_inv), b1 = floor((hi0 + margin - pk.tb_o0) * pk.tb_inv);
+    double b2 = floor((lo1 - margin - pk.tb_o1) * pk.tb_inv), b3 = floor((hi1 + margin - pk.tb_o1) * pk.tb_inv);
+    const int bx0 = (int)fmax(b0, 0.0), bx1 = (int)fmin(b1, (double)(pk.tb_nx - 1));
+    const int by0 = (int)fmax(b2, 0.0), by1 = (int)fmin(b3, (double)(pk.tb_ny - 1));
+    const bool empty = !(b1 >= 0.0 && b3 >= 0.0 && b0 <= (double)(pk.tb_nx - 1) && b2 <= (double)(pk.tb_ny - 1));
+    const int n_rows = empty ? 0 : (by1 - by0 + 1);
+    const int nx = pk.tb_nx;
+    auto row_seg = [&](int s, int &b, int &l) {
+        b = __ldg(&pk.tb_start[(by0 + s) * nx + bx0]);
+        l = __ldg(&pk.tb_start[(by0 + s) * nx + bx1 + 1]) - b;
+    };
+    // which shots (bits 0..4) and the previous step's last shot (bit 5) contain texel j
+    auto ball_mask = [&](int j, const float4 &t) -> unsigned {
+        unsigned in = 0, amb = 0;
+#pragma unroll
+        for (int s = 0; s <= NS; ++s) {
+            float dx = t.x - fx[s], dy = t.y - fy[s], dz = t.z - fz[s];
+            float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            in |= (d2 <= r2f ? 1u : 0u) << s;
+            amb |= (fabsf(d2 - r2f) <= kBallEps ? 1u : 0u) << s;
+        }
+        if (amb) {
+            const double x = __ldg(&pk.tx[j]), y = __ldg(&pk.ty[j]), z = __ldg(&pk.tz[j]);
+            in = 0;
+#pragma unroll
+            for (int s = 0; s <= NS; ++s) {
+                double dx = x - cx[s], dy = y - cy[s], dz = z - cz[s];
+                in |= ((dx * dx + dy * dy + dz * dz) <= r2 ? 1u : 0u) << s;
+            }
+        }
+        if (!has_last) in &= (1u << NS) - 1u;
+        return in;
+    };
+
+    double rmax[NS];
+    if (COLOR == 1) {   // HSI: r = distances.max() per shot (bullet_paint_wrapper.py:423-424)
+#pragma unroll
+        for (int s = 0; s < NS; ++s) rmax[s] = -1.0;
+        for_each_in_segments(n_rows, lane, ws, row_seg, [&](int j, bool active) {
+            if (!active) return;
+            const float4 t = __ldg(&pk.trel[j]);
+            const unsigned in = ball_mask(j, t) & ((1u << NS) - 1u);
+            if (in) {
+                const double x = __ldg(&pk.tx[j]), y = __ldg(&pk.ty[j]), z = __ldg(&pk.tz[j]);
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    if (in & (1u << s)) {
+                        double dx = x - cx[s], dy = y - cy[s], dz = z - cz[s];
+                        rmax[s] = fmax(rmax[s], dx * dx + dy * dy + dz * dz);
+                    }
+                }
+            }
+        });
+#pragma unroll
+        for (int s = 0; s < NS; ++s) rmax[s] = sqrt(warp_max(rmax[s]));   // sqrt is monotone
+    }
+
+    int n_new = 0, n_possible = 0;   // per-lane partial counts
+    for_each_in_segments(n_rows, lane, ws, row_seg, [&](int j, bool active) {
+        if (!active) return;
+        const float4 t = __ldg(&pk.trel[j]);
+        const unsigned in = ball_mask(j, t);
+        const unsigned shots = in & ((1u << NS) - 1u);
+        if (!shots) return;
+        // affected \ last_affected, shot by shot (:575): shot s counts if the previous shot missed the texel
+        const unsigned prev = ((shots << 1) | (in >> NS)) & ((1u << NS) - 1u);
+        n_possible += (shots & ~prev) ? 1 : 0;
+        bool flipped = false;
+        if (COLOR == 0) {                              // :358-365
+            if ((int)__ldcg(&status[j]) != kPainted) { status[j] = (S)kPainted; n_new += 1; flipped = true; }
+        } else {                                       // :411-434
+            const int sv0 = (int)__ldcg(&status[j]);
+            int sv = sv0;
+            const double x = __ldg(&pk.tx[j]), y = __ldg(&pk.ty[j]), z = __ldg(&pk.tz[j]);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                if ((shots & (1u << s)) && sv > 0) {
+                    double dx = x - cx[s], dy = y - cy[s], dz = z - cz[s];
+                    double ratio = sqrt(dx * dx + dy * dy + dz * dz) / rmax[s];
+                    int quantity = (int)(kHsiTargetMax * (1.0 - ratio * ratio)) + 1;   // :429
+                    sv -= quantity;
+                    n_new += quantity;
+                }
+            }
+            if (sv != sv0) {
+                status[j] = (S)sv;
+                flipped = (sv0 == kPainted);           // values only decrease: 255 is left once
+            }
+        }
+        if (flipped) {
+            const unsigned w = __float_as_uint(t.w);
+            const unsigned bin = w & 0xffffu;
+            atomicAdd(bin_cnt + (bin >> 1), 1u << ((bin & 1u) * 16));
+            if (grid_cnt) atomicAdd(grid_cnt + (w >> 16), 1u);
+        }
+    });
+    n_new_out = __reduce_add_sync(kFull, n_new);
+    n_possible_out = __reduce_add_sync(kFull, n_possible);
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------ kernels
-template <int COLOR, typename RankT>
+template <int COLOR>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-reset_kernel(DevPack pk, DevConfig cfg, EnvState *states, typename StatusT<COLOR>::type *planes,
-             const int32_t *env_ids, int n, const int32_t *start_idx, const double *set_pos,
-             const double *set_normal, double *obs_out, int mode /*0 reset, 1 set_pose*/) {
-    __shared__ int hist_all[kWarpsPerBlock][2 * kMaxObs];
+reset_kernel(DevPack pk, DevConfig cfg, EnvArrays<COLOR> ea, const int32_t *env_ids, int n, const int32_t *start_idx,
+             const double *set_pos, const double *set_normal, double *obs_out, int mode /*0 reset, 1 set_pose*/) {
+    __shared__ WarpScratch scratch[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = blockIdx.x * kWarpsPerBlock + warp;
     if (k >= n) return;
     const int env = env_ids ? env_ids[k] : k;
-    typename StatusT<COLOR>::type *status = planes + (size_t)env * pk.n_pad;
+    typename StatusT<COLOR>::type *status = ea.planes + (size_t)env * pk.n_pad;
+    unsigned *bin_cnt = bin_cnt_of<COLOR>(pk, ea, env), *grid_cnt = grid_cnt_of<COLOR>(pk, ea, env);
     EnvState st;
-    load_state(&states[env], st);
+    load_state(&ea.states[env], st);
     if (mode == 0) {
-        int idx;
-        if (start_idx) idx = start_idx[k];
-        else idx = (int)(splitmix64(cfg.seed ^ splitmix64(((unsigned long long)env << 32) | (unsigned)st.episode)) %
-                         (unsigned long long)pk.n_starts);
+        int idx = start_idx ? start_idx[k] : auto_start_index(pk, cfg, env, st.episode);
         idx = min(max(idx, 0), pk.n_starts - 1);
-        env_reset<COLOR>(pk, st, status, idx, lane);
+        env_reset<COLOR>(pk, st, status, bin_cnt, grid_cnt, idx, lane);
     } else {
         robot_reset(st, set_pos + 3 * k, set_normal + 3 * k);
     }
     __syncwarp();
     Vec3 pose = {st.pose[0], st.pose[1], st.pose[2]};
-    write_observation<COLOR, RankT>(pk, cfg, status, pose, lane, hist_all[warp],
-                                    obs_out ? obs_out + (size_t)k * cfg.obs_dim : nullptr, nullptr);
-    store_state(&states[env], st, lane);
+    write_observation<COLOR>(pk, cfg, status, bin_cnt, grid_cnt, pose, lane, scratch[warp],
+                             obs_out ? obs_out + (size_t)k * cfg.obs_dim : nullptr, nullptr);
+    store_state(&ea.states[env], st, lane);
 }
 
-template <int COLOR, typename RankT>
+template <int COLOR>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-step_kernel(DevPack pk, DevConfig cfg, EnvState *states, typename StatusT<COLOR>::type *planes, int num_envs,
-            StepIO io) {
+step_kernel(DevPack pk, DevConfig cfg, EnvArrays<COLOR> ea, int num_envs, StepIO io) {
     typedef typename StatusT<COLOR>::type S;
-    __shared__ int hist_all[kWarpsPerBlock][2 * kMaxObs];
+    __shared__ WarpScratch scratch[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int env = blockIdx.x * kWarpsPerBlock + warp;
     if (env >= num_envs) return;
-    S *status = planes + (size_t)env * pk.n_pad;
+    WarpScratch &ws = scratch[warp];
+    S *status = ea.planes + (size_t)env * pk.n_pad;
+    unsigned *bin_cnt = bin_cnt_of<COLOR>(pk, ea, env), *grid_cnt = grid_cnt_of<COLOR>(pk, ea, env);
     EnvState st;
-    load_state(&states[env], st);
+    load_state(&ea.states[env], st);
 
     // ---- action -> direction (robot_gym_env.py:342-347, robot.py:390-398, 352-358)
     double u1, u2, new_angle;
@@ -425,121 +584,61 @@ step_kernel(DevPack pk, DevConfig cfg, EnvState *states, typename StatusT<COLOR>
     Vec3 cur_n = tcp_orn_norm(cur_p, st.quat);
     const double delta1 = delta_axis1 / kPaintPerAction, delta2 = delta_axis2 / kPaintPerAction;
     const double delta2_scaled = delta2 * pk.lwr;
-    Vec3 centers[kPaintPerAction];
     int full_scans = 0;
     double quat[4] = {st.quat[0], st.quat[1], st.quat[2], st.quat[3]};
+    bool miss_quat_valid = false;   // quat == quat_from_normal(cur_n) from an earlier miss of this step
 #pragma unroll 1
     for (int s = 0; s < kPaintPerAction; ++s) {
         Vec3 p = cur_p;
         add_comp(p, pk.axis0, delta1);
         add_comp(p, pk.axis1, delta2_scaled);
         Vec3 end = {p.x + cur_n.x, p.y + cur_n.y, p.z + cur_n.z};
-        Vec3 hit, pos, orn = cur_n;
-        bool ok = ray_test(pk, p, end, lane, hit, full_scans);
-        if (ok) ok = hook_point(pk, hit, lane, pos, orn);
-        if (!ok) orn = cur_n;
-        quat_from_normal(orn, quat);
-        if (!ok) {
+        Vec3 hit, pos, center;
+        int cell;
+        const double *rec = nullptr;
+        if (ray_test(pk, p, end, lane, hit, cell, full_scans)) rec = hook_triangle(pk, hit, cell, lane);
+        if (rec) {
+            // pose = hit + 0.1 n, orn = -n (bullet_paint_wrapper.py:529-530); quaternion and shot-centre
+            // offset of -n come from the record (computed by the host with these same operations)
+            const double2 *t = reinterpret_cast<const double2 *>(rec + 12);   // [12] inv, [13..15] n, [16..19] q, [20..22] off
+            const double2 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2), t3 = __ldg(t + 3), t4 = __ldg(t + 4),
+                          t5 = __ldg(t + 5);
+            const double nx = t0.y, ny = t1.x, nz = t1.y;
+            pos.x = hit.x + nx * kHookDistance;
+            pos.y = hit.y + ny * kHookDistance;
+            pos.z = hit.z + nz * kHookDistance;
+            quat[0] = t2.x; quat[1] = t2.y; quat[2] = t3.x; quat[3] = t3.y;
+            center.x = t4.x + pos.x; center.y = t4.y + pos.y; center.z = t5.x + pos.z;   // robot.py:277-278
+            cur_n.x = -nx; cur_n.y = -ny; cur_n.z = -nz;
+            st.flags |= kFlagLastOnPart;
+            miss_quat_valid = false;
+        } else {
+            if (!miss_quat_valid) { quat_from_normal(cur_n, quat); miss_quat_valid = true; }
             pos = transform_point(cur_p, quat, delta2, delta1, 0.0);   // robot.py:317 (sic)
+            center = transform_point(pos, quat, 0.0, 0.0, 0.1);        // robot.py:277-278
             if (st.flags & kFlagLastOnPart) {                           // robot.py:292-300
                 st.flags &= ~kFlagLastOnPart;
             } else {
                 st.term_counter += 1;
                 if (st.term_counter > kNotOnPartTerminateSteps) st.flags |= kFlagTerminate;
             }
-        } else {
-            st.flags |= kFlagLastOnPart;
         }
-        centers[s] = transform_point(pos, quat, 0.0, 0.0, 0.1);        // robot.py:277-278
+        if (lane == 0) { ws.centers[s][0] = center.x; ws.centers[s][1] = center.y; ws.centers[s][2] = center.z; }
         cur_p = pos;
-        cur_n = orn;
     }
     st.pose[0] = cur_p.x; st.pose[1] = cur_p.y; st.pose[2] = cur_p.z;
     st.quat[0] = quat[0]; st.quat[1] = quat[1]; st.quat[2] = quat[2]; st.quat[3] = quat[3];
+    __syncwarp();
 
-    // ---- stamp the 5 shots, texel-major over the binned candidates (bullet_paint_wrapper.py:568-577)
-    const double r2 = kPaintRadius * kPaintRadius;
+    // ---- stamp the 5 shots (bullet_paint_wrapper.py:568-577)
     const bool has_last = (st.flags & kFlagHasLast) != 0;
     const Vec3 lastc = {st.last_center[0], st.last_center[1], st.last_center[2]};
-    double lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
-#pragma unroll
-    for (int s = 0; s < kPaintPerAction; ++s) {
-        double c0 = comp(centers[s], pk.axis0), c1 = comp(centers[s], pk.axis1);
-        lo0 = fmin(lo0, c0); hi0 = fmax(hi0, c0);
-        lo1 = fmin(lo1, c1); hi1 = fmax(hi1, c1);
-    }
-    const double margin = kPaintRadius + 1e-9;
-    int bx0 = (int)floor((lo0 - margin - pk.tb_o0) * pk.tb_inv), bx1 = (int)floor((hi0 + margin - pk.tb_o0) * pk.tb_inv);
-    int by0 = (int)floor((lo1 - margin - pk.tb_o1) * pk.tb_inv), by1 = (int)floor((hi1 + margin - pk.tb_o1) * pk.tb_inv);
-    bx0 = max(bx0, 0); by0 = max(by0, 0);
-    bx1 = min(bx1, pk.tb_nx - 1); by1 = min(by1, pk.tb_ny - 1);
-
-    double rmax[kPaintPerAction];
-    if (COLOR == 1) {   // HSI: r = distances.max() per shot (bullet_paint_wrapper.py:423-424)
-#pragma unroll
-        for (int s = 0; s < kPaintPerAction; ++s) rmax[s] = -1.0;
-        for (int row = by0; row <= by1; ++row) {
-            if (bx0 > bx1) break;
-            int begin = __ldg(&pk.tb_start[row * pk.tb_nx + bx0]), end = __ldg(&pk.tb_start[row * pk.tb_nx + bx1 + 1]);
-            for (int j = begin + lane; j < end; j += 32) {
-                double x = __ldg(&pk.tx[j]), y = __ldg(&pk.ty[j]), z = __ldg(&pk.tz[j]);
-#pragma unroll
-                for (int s = 0; s < kPaintPerAction; ++s) {
-                    double dx = x - centers[s].x, dy = y - centers[s].y, dz = z - centers[s].z;
-                    double d2 = dx * dx + dy * dy + dz * dz;
-                    if (d2 <= r2) rmax[s] = fmax(rmax[s], d2);
-                }
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < kPaintPerAction; ++s) rmax[s] = sqrt(warp_max(rmax[s]));   // sqrt is monotone
-    }
-
-    int n_new = 0, n_possible = 0;   // per-lane partial counts
-    for (int row = by0; row <= by1; ++row) {
-        if (bx0 > bx1) break;
-        int begin = __ldg(&pk.tb_start[row * pk.tb_nx + bx0]), end = __ldg(&pk.tb_start[row * pk.tb_nx + bx1 + 1]);
-        for (int j = begin + lane; j < end; j += 32) {
-            double x = __ldg(&pk.tx[j]), y = __ldg(&pk.ty[j]), z = __ldg(&pk.tz[j]);
-            bool prev_in = false;
-            if (has_last) {
-                double dx = x - lastc.x, dy = y - lastc.y, dz = z - lastc.z;
-                prev_in = (dx * dx + dy * dy + dz * dz) <= r2;
-            }
-            bool any = false, valid = false;
-            int sv = 0;
-            bool loaded = false, dirty = false;
-#pragma unroll
-            for (int s = 0; s < kPaintPerAction; ++s) {
-                double dx = x - centers[s].x, dy = y - centers[s].y, dz = z - centers[s].z;
-                double d2 = dx * dx + dy * dy + dz * dz;
-                bool in = d2 <= r2;
-                if (in) {
-                    any = true;
-                    if (!prev_in) valid = true;          // affected \ last_affected (:575)
-                    if (COLOR == 1) {
-                        if (!loaded) { sv = (int)__ldcg(&status[j]); loaded = true; }
-                        double ratio = sqrt(d2) / rmax[s];
-                        int quantity = (int)(kHsiTargetMax * (1.0 - ratio * ratio)) + 1;   // :429
-                        if (sv > 0) { sv -= quantity; n_new += quantity; dirty = true; }  // :411-418
-                    }
-                }
-                prev_in = in;
-            }
-            if (COLOR == 0 && any) {                      // :358-365
-                if ((int)__ldcg(&status[j]) != kPainted) { status[j] = (S)kPainted; n_new += 1; }
-            }
-            if (COLOR == 1 && dirty) status[j] = (S)sv;
-            n_possible += valid ? 1 : 0;
-        }
-    }
-    n_new = __reduce_add_sync(kFull, n_new);
-    n_possible = __reduce_add_sync(kFull, n_possible);
-    st.last_center[0] = centers[kPaintPerAction - 1].x;
-    st.last_center[1] = centers[kPaintPerAction - 1].y;
-    st.last_center[2] = centers[kPaintPerAction - 1].z;
+    int n_new, n_possible;
+    stamp<COLOR>(pk, cfg, status, bin_cnt, grid_cnt, lastc, has_last, lane, ws, n_new, n_possible);
+    st.last_center[0] = ws.centers[kPaintPerAction - 1][0];
+    st.last_center[1] = ws.centers[kPaintPerAction - 1][1];
+    st.last_center[2] = ws.centers[kPaintPerAction - 1][2];
     st.flags |= kFlagHasLast;
-    __syncwarp();
 
     // ---- robot.py:425-433, robot_gym_env.py:321-340
     const double succeeded = (COLOR == 0) ? (double)n_new : (double)n_new / 255.0;
@@ -557,11 +656,10 @@ step_kernel(DevPack pk, DevConfig cfg, EnvState *states, typename StatusT<COLOR>
     const double max_pts = cfg.max_possible_point;
     const bool finished = !(max_pts > st.total_reward * 100);
     const double avg_reward = st.total_reward / st.step_counter;
-    const double expected_avg = max_pts / (double)(cfg.expected_episode_length * 100);
     bool done, decided = false;
-    if (avg_reward < expected_avg && cfg.termination_mode != 0) {
+    if (avg_reward < cfg.expected_avg_reward && cfg.termination_mode != 0) {
         if (cfg.termination_mode == 1) { done = true; decided = true; }
-        else if (st.total_reward < cfg.switch_threshold * max_pts / 100) { done = true; decided = true; }
+        else if (st.total_reward < cfg.hybrid_threshold) { done = true; decided = true; }
     }
     if (!decided) done = finished || (st.flags & kFlagTerminate) || st.step_counter > cfg.episode_max_length - 1;
 
@@ -569,7 +667,7 @@ step_kernel(DevPack pk, DevConfig cfg, EnvState *states, typename StatusT<COLOR>
     const bool resetting = done && cfg.auto_reset;
     double *obs = io.obs + (size_t)env * cfg.obs_dim;
     double *next_obs = io.next_obs ? io.next_obs + (size_t)env * cfg.obs_dim : nullptr;
-    write_observation<COLOR, RankT>(pk, cfg, status, cur_p, lane, hist_all[warp], obs, resetting ? nullptr : next_obs);
+    write_observation<COLOR>(pk, cfg, status, bin_cnt, grid_cnt, cur_p, lane, ws, obs, resetting ? nullptr : next_obs);
     if (!done) st.total_return += actual;
     if (lane == 0) {
         io.reward[env] = reward;
@@ -585,34 +683,30 @@ step_kernel(DevPack pk, DevConfig cfg, EnvState *states, typename StatusT<COLOR>
 
     // ---- same-step auto-reset: `obs` keeps the terminal observation, `next_obs` gets reset()'s
     if (resetting) {
-        int idx;
-        if (io.reset_start_idx) idx = io.reset_start_idx[env];
-        else idx = (int)(splitmix64(cfg.seed ^ splitmix64(((unsigned long long)env << 32) | (unsigned)st.episode)) %
-                         (unsigned long long)pk.n_starts);
+        int idx = io.reset_start_idx ? io.reset_start_idx[env] : auto_start_index(pk, cfg, env, st.episode);
         idx = min(max(idx, 0), pk.n_starts - 1);
         __syncwarp();
-        env_reset<COLOR>(pk, st, status, idx, lane);
+        env_reset<COLOR>(pk, st, status, bin_cnt, grid_cnt, idx, lane);
         __syncwarp();
         Vec3 pose = {st.pose[0], st.pose[1], st.pose[2]};
-        write_observation<COLOR, RankT>(pk, cfg, status, pose, lane, hist_all[warp], next_obs, nullptr);
+        write_observation<COLOR>(pk, cfg, status, bin_cnt, grid_cnt, pose, lane, ws, next_obs, nullptr);
     }
-    store_state(&states[env], st, lane);
+    store_state(&ea.states[env], st, lane);
 }
 
 // ------------------------------------------------------------------------------ state access
 template <int COLOR>
-__global__ void get_state_kernel(DevPack pk, const EnvState *states, const typename StatusT<COLOR>::type *planes,
-                                 const int32_t *env_ids, int n, int16_t *status_out, double *pose_out,
-                                 double *quat_out, double *scalars_out) {
+__global__ void get_state_kernel(DevPack pk, EnvArrays<COLOR> ea, const int32_t *env_ids, int n, int16_t *status_out,
+                                 double *pose_out, double *quat_out, double *scalars_out) {
     const int k = blockIdx.y;
     const int env = env_ids ? env_ids[k] : k;
-    const typename StatusT<COLOR>::type *status = planes + (size_t)env * pk.n_pad;
+    const typename StatusT<COLOR>::type *status = ea.planes + (size_t)env * pk.n_pad;
     if (status_out) {
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pk.n_texels; j += gridDim.x * blockDim.x)
             status_out[(size_t)k * pk.n_texels + pk.sorted_to_pack[j]] = (int16_t)status[j];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const EnvState &st = states[env];
+        const EnvState &st = ea.states[env];
         if (pose_out) for (int i = 0; i < 3; ++i) pose_out[3 * k + i] = st.pose[i];
         if (quat_out) for (int i = 0; i < 4; ++i) quat_out[4 * k + i] = st.quat[i];
         if (scalars_out) {
@@ -625,19 +719,18 @@ __global__ void get_state_kernel(DevPack pk, const EnvState *states, const typen
 }
 
 template <int COLOR>
-__global__ void set_state_kernel(DevPack pk, EnvState *states, typename StatusT<COLOR>::type *planes,
-                                 const int32_t *env_ids, int n, const int16_t *status_in, const double *pose_in,
-                                 const double *quat_in, const double *scalars_in) {
+__global__ void set_state_kernel(DevPack pk, EnvArrays<COLOR> ea, const int32_t *env_ids, int n, const int16_t *status_in,
+                                 const double *pose_in, const double *quat_in, const double *scalars_in) {
     typedef typename StatusT<COLOR>::type S;
     const int k = blockIdx.y;
     const int env = env_ids ? env_ids[k] : k;
-    S *status = planes + (size_t)env * pk.n_pad;
+    S *status = ea.planes + (size_t)env * pk.n_pad;
     if (status_in) {
         for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pk.n_texels; j += gridDim.x * blockDim.x)
             status[j] = (S)status_in[(size_t)k * pk.n_texels + pk.sorted_to_pack[j]];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        EnvState &st = states[env];
+        EnvState &st = ea.states[env];
         if (pose_in) for (int i = 0; i < 3; ++i) st.pose[i] = pose_in[3 * k + i];
         if (quat_in) for (int i = 0; i < 4; ++i) st.quat[i] = quat_in[4 * k + i];
         if (scalars_in) {
@@ -652,6 +745,30 @@ __global__ void set_state_kernel(DevPack pk, EnvState *states, typename StatusT<
         // the overlap reference set cannot be expressed through this interface: clear it, as
         // reset_part does (bullet_paint_wrapper.py:708)
         if (status_in) st.flags &= ~kFlagHasLast;
+    }
+}
+
+// Rebuilds the flip counters of the listed environments from their status planes (after set_state).
+template <int COLOR>
+__global__ void recount_kernel(DevPack pk, EnvArrays<COLOR> ea, const int32_t *env_ids, int n) {
+    const int lane = threadIdx.x & 31;
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const int env = env_ids ? env_ids[k] : k;
+    const typename StatusT<COLOR>::type *status = ea.planes + (size_t)env * pk.n_pad;
+    unsigned *bin_cnt = bin_cnt_of<COLOR>(pk, ea, env), *grid_cnt = grid_cnt_of<COLOR>(pk, ea, env);
+    for (int w = lane; w < pk.n_bins_pad / 2; w += 32) bin_cnt[w] = 0;
+    if (grid_cnt) for (int w = lane; w < pk.n_gcells_pad; w += 32) grid_cnt[w] = 0;
+    __syncwarp();
+    const bool init_painted = (pk.status_init == kPainted);
+    for (int j = lane; j < pk.n_texels; j += 32) {
+        const bool painted = ((int)status[j] == kPainted);
+        if (painted != init_painted) {
+            const unsigned w = __float_as_uint(__ldg(&pk.trel[j]).w);
+            const unsigned bin = w & 0xffffu;
+            atomicAdd(bin_cnt + (bin >> 1), 1u << ((bin & 1u) * 16));
+            if (grid_cnt) atomicAdd(grid_cnt + (w >> 16), 1u);
+        }
     }
 }
 
