@@ -208,7 +208,8 @@ def main():
 
     gen = torch.Generator(device=device)
     gen.manual_seed(1234 + rank)
-    total = warmup + args.steps
+    e2e_steps = max(10, min(args.steps, 200))
+    total = warmup + max(args.steps, e2e_steps)
     if cfg.action_mode == 'discrete':
         actions = torch.randint(0, cfg.discrete_granularity, (total, n_env), generator=gen, device=device,
                                 dtype=torch.int64)
@@ -251,7 +252,6 @@ def main():
     dev_ms = float(step_ms.sum())
 
     # ---- end-to-end through the host-buffer API (pinned host actions in, results out, every step)
-    e2e_steps = max(10, min(args.steps, 200))
     host_out = env.host_buffers(pinned=True)
     host_actions = actions[warmup:warmup + e2e_steps].cpu().pin_memory().numpy()
     for i in range(3):

@@ -66,8 +66,10 @@ struct PaintrlEngine {
     DevConfig cfg{};
     DeviceArena arena;
     EnvState *states = nullptr;
-    void *planes = nullptr;          // [num_envs][n_pad] uint8 (RGB) or int16 (HSI)
-    unsigned *bin_cnt = nullptr;     // [num_envs][n_bins_pad / 2]
+    MoveOut *moves = nullptr;
+    EnvStat *env_stats = nullptr;
+    unsigned *bits = nullptr;        // [num_envs][n_words_pad] flip bit per texel slot
+    int16_t *thick = nullptr;        // [num_envs][n_slots] HSI thickness plane (HSI only)
     unsigned *grid_cnt = nullptr;    // [num_envs][n_gcells_pad] (grid observation only)
     unsigned long long *stats = nullptr;
     // staging for the host-buffer entry points
@@ -266,7 +268,6 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
     const int n = pack->n_texels;
     const int a0 = pack->axis0, a1 = pack->axis1;
     pk.n_texels = n;
-    pk.n_pad = ((n + 127) / 128) * 128;
     pk.axis0 = a0;
     pk.axis1 = a1;
     pk.status_init = pack->status_init;
@@ -371,9 +372,10 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
         if (rc != PAINTRL_OK) return rc;
     }
 
-    // ---- texel bins: texels sorted by bin (row-major, rows along axis1).  Bin size b = R / k balances
-    // the per-step cost of the observation: ~0.3 instructions per bin counter against ~0.8 per texel of
-    // the pose's bin row and column.
+    // ---- texel layout "rows and words": rows = strips along axis1 (row(y) = floor((y - o1) * inv)),
+    // the texels of a row sorted by their axis0 coordinate and packed 32 to a word, every row starting
+    // a new word.  A static cell table along axis0 (cell(x) = floor((x - o0) * inv)) gives, per row,
+    // the index of the first texel of each cell.
     double tmin0 = INFINITY, tmax0 = -INFINITY, tmin1 = INFINITY, tmax1 = -INFINITY;
     double tmin[3] = {INFINITY, INFINITY, INFINITY}, tmax[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int i = 0; i < n; ++i) {
@@ -382,71 +384,82 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
         tmin1 = std::min(tmin1, p[a1]); tmax1 = std::max(tmax1, p[a1]);
         for (int k = 0; k < 3; ++k) { tmin[k] = std::min(tmin[k], p[k]); tmax[k] = std::max(tmax[k], p[k]); }
     }
-    int bin_div;
-    {
-        const double ext0 = std::max(tmax0 - tmin0, 1e-9), ext1 = std::max(tmax1 - tmin1, 1e-9);
-        const double b = 0.74 * std::cbrt(2.0 * ext0 * ext1 * ext0 * ext1 / ((ext0 + ext1) * (double)n));
-        bin_div = (int)std::lround(kPaintRadius / b);
-        bin_div = std::min(std::max(bin_div, 1), 8);
-        while (bin_div > 1 && (std::floor(ext0 * bin_div / kPaintRadius) + 2) * (std::floor(ext1 * bin_div / kPaintRadius) + 1) > 65000.0)
-            --bin_div;
+    const double ext0 = std::max(tmax0 - tmin0, 1e-9), ext1 = std::max(tmax1 - tmin1, 1e-9);
+    pk.n_rows = (n / 32 <= 4096) ? 32 : kMaxRows;
+    pk.row_h = ext1 * (1.0 + 1e-9) / pk.n_rows;
+    pk.row_inv = 1.0 / pk.row_h;
+    pk.row_o1 = tmin1;
+    pk.ncx = (int)std::min<long long>(std::max<long long>((long long)n / (2 * pk.n_rows), 16), 1 << 20);
+    pk.cx_inv = pk.ncx / (ext0 * (1.0 + 1e-9));
+    pk.cx_o0 = tmin0;
+    std::vector<int> row_of(n), cell_of(n);
+    std::vector<int> row_count(pk.n_rows, 0);
+    for (int i = 0; i < n; ++i) {
+        const double *p = pack->texel_pos + 3 * i;
+        // the same two FP64 operations the device applies to the TCP (section4_counts / row_ranks)
+        const int r = (int)std::floor((p[a1] - pk.row_o1) * pk.row_inv);
+        const int c = (int)std::floor((p[a0] - pk.cx_o0) * pk.cx_inv);
+        if (r < 0 || r >= pk.n_rows || c < 0 || c >= pk.ncx) return fail(PAINTRL_E_INVALID, "texel outside its own row / cell grid");
+        row_of[i] = r;
+        cell_of[i] = c;
+        row_count[r]++;
     }
-    const double bsz = kPaintRadius / bin_div;
-    pk.tb_inv = 1.0 / bsz;
-    pk.tb_o0 = tmin0;
-    pk.tb_o1 = tmin1;
-    const int nx_real = (int)std::floor((tmax0 - tmin0) * pk.tb_inv) + 1;
-    pk.tb_nx = (nx_real + 1) & ~1;           // even: two 16-bit counters per word never straddle rows
-    pk.tb_ny = (int)std::floor((tmax1 - tmin1) * pk.tb_inv) + 1;
-    if ((long long)pk.tb_nx * pk.tb_ny > 65535) return fail(PAINTRL_E_INVALID, "texel bin grid too large");
-    const int n_bins = pk.tb_nx * pk.tb_ny;
-    pk.n_bins_pad = ((n_bins + 63) / 64) * 64;
-    std::vector<int> order(n), bin_of(n);
+    std::vector<int> row_word0(pk.n_rows + 1, 0);
+    for (int r = 0; r < pk.n_rows; ++r) {
+        const int words = (row_count[r] + 31) / 32;
+        if (words > 0xffffff) return fail(PAINTRL_E_INVALID, "texel row too long");
+        row_word0[r + 1] = row_word0[r] + words;
+    }
+    pk.n_words = std::max(row_word0[pk.n_rows], 1);
+    pk.n_words_pad = ((pk.n_words + 31) / 32) * 32;
+    pk.n_slots = pk.n_words * 32;
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        if (row_of[x] != row_of[y]) return row_of[x] < row_of[y];
+        return pack->texel_pos[3 * x + a0] < pack->texel_pos[3 * y + a0];
+    });
+    std::vector<int> slot_to_pack(pk.n_slots, -1), pack_to_slot(n, 0);
+    std::vector<int> cell_start((size_t)pk.n_rows * (pk.ncx + 1), 0);
+    std::vector<unsigned> word_info(pk.n_words, 0);
     {
-        std::vector<int> start(n_bins + 1, 0);
-        for (int i = 0; i < n; ++i) {
-            const double *p = pack->texel_pos + 3 * i;
-            // the same two FP64 operations the device applies to the pose (section4_counts)
-            int cx = (int)std::floor((p[a0] - pk.tb_o0) * pk.tb_inv);
-            int cy = (int)std::floor((p[a1] - pk.tb_o1) * pk.tb_inv);
-            if (cx < 0 || cx >= nx_real || cy < 0 || cy >= pk.tb_ny) return fail(PAINTRL_E_INVALID, "texel outside its own bin grid");
-            bin_of[i] = cy * pk.tb_nx + cx;
-            start[bin_of[i] + 1]++;
-        }
-        int max_bin = 0;
-        for (int c = 0; c < n_bins; ++c) { max_bin = std::max(max_bin, start[c + 1]); start[c + 1] += start[c]; }
-        if ((long long)max_bin * pk.tb_ny > 65535 || max_bin > 65535)
-            return fail(PAINTRL_E_INVALID, "texel bins too full for 16-bit counters");
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-            if (bin_of[x] != bin_of[y]) return bin_of[x] < bin_of[y];
-            return pack->texel_pos[3 * x + a0] < pack->texel_pos[3 * y + a0];
-        });
-        CUDA_TRY(e->arena.upload(start, &pk.tb_start));
-        // exclusive 2-D prefix sums of the bin sizes
-        const int W = pk.tb_nx + 1;
-        std::vector<int> prefix((size_t)(pk.tb_ny + 1) * W, 0);
-        for (int iy = 0; iy < pk.tb_ny; ++iy)
-            for (int ix = 0; ix < pk.tb_nx; ++ix) {
-                const int size = start[iy * pk.tb_nx + ix + 1] - start[iy * pk.tb_nx + ix];
-                prefix[(size_t)(iy + 1) * W + ix + 1] = size + prefix[(size_t)iy * W + ix + 1] + prefix[(size_t)(iy + 1) * W + ix] -
-                                                        prefix[(size_t)iy * W + ix];
+        int pos = 0;
+        for (int r = 0; r < pk.n_rows; ++r) {
+            int *cs = &cell_start[(size_t)r * (pk.ncx + 1)];
+            int c_next = 0;
+            for (int i = 0; i < row_count[r]; ++i) {
+                const int t = order[pos + i];
+                const int slot = row_word0[r] * 32 + i;
+                slot_to_pack[slot] = t;
+                pack_to_slot[t] = slot;
+                while (c_next <= cell_of[t]) cs[c_next++] = i;   // monotone: the row is sorted by axis0
             }
-        CUDA_TRY(e->arena.upload(prefix, &pk.tb_prefix));
+            while (c_next <= pk.ncx) cs[c_next++] = row_count[r];
+            for (int w = row_word0[r]; w < row_word0[r + 1]; ++w) word_info[w] = (unsigned)r | ((unsigned)(w - row_word0[r]) << 8);
+            pos += row_count[r];
+        }
     }
+    CUDA_TRY(e->arena.upload(row_word0, &pk.row_word0));
+    CUDA_TRY(e->arena.upload(row_count, &pk.row_count));
+    CUDA_TRY(e->arena.upload(cell_start, &pk.cell_start));
+    CUDA_TRY(e->arena.upload(word_info, &pk.word_info));
+    CUDA_TRY(e->arena.upload(slot_to_pack, &pk.slot_to_pack));
+    CUDA_TRY(e->arena.upload(pack_to_slot, &pk.pack_to_slot));
 
     // ---- grid-observation cells (bullet_paint_wrapper.py:1072-1112)
-    std::vector<uint16_t> gcell(n, 0);
+    std::vector<uint16_t> gcell(pk.n_slots, 0);
     pk.n_gcells = pk.n_gcells_pad = 0;
     pk.gtotal = nullptr;
+    pk.gcell = nullptr;
     if (cfg->obs_mode == PAINTRL_OBS_GRID) {
         const int g = cfg->obs_grad, vgran = pack->grid_granularity;
         const int v_interval = (int)((double)vgran / (double)g);
         if (v_interval <= 0) return fail(PAINTRL_E_INVALID, "OBS_GRAD larger than GRID_GRANULARITY");
         const double axis_2_step = (pack->range1_max - pack->range1_min) / vgran;
         std::vector<int> gtotal((size_t)g * g, 0);
-        for (int j = 0; j < n; ++j) {
-            const double *p = pack->texel_pos + 3 * order[j];
+        for (int j = 0; j < pk.n_slots; ++j) {
+            if (slot_to_pack[j] < 0) continue;
+            const double *p = pack->texel_pos + 3 * slot_to_pack[j];
             double yq = (p[a1] - pack->range1_min) / axis_2_step;
             if (!(yq > -1.0)) return fail(PAINTRL_E_INVALID, "texel below the silhouette table (reference KeyError)");
             int y_grid = std::min(vgran - 1, (int)yq);
@@ -467,23 +480,21 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
         pk.n_gcells = g * g;
         pk.n_gcells_pad = ((g * g + 3) / 4) * 4;
         CUDA_TRY(e->arena.upload(gtotal, &pk.gtotal));
+        CUDA_TRY(e->arena.upload(gcell, &pk.gcell));
     }
 
-    // ---- sorted texel tables: exact FP64 positions, and FP32 origin-relative positions + bin + grid cell
+    // ---- slot tables: exact FP64 positions, and FP32 origin-relative positions (ball pre-test)
     {
-        std::vector<double> tx(pk.n_pad, 1e30), ty(pk.n_pad, 1e30), tz(pk.n_pad, 1e30);
-        std::vector<float4> trel(pk.n_pad, make_float4(1e30f, 1e30f, 1e30f, 0.f));
+        std::vector<double> tx(pk.n_slots, 1e30), ty(pk.n_slots, 1e30), tz(pk.n_slots, 1e30);
+        std::vector<float> fx(pk.n_slots, 1e30f), fy(pk.n_slots, 1e30f), fz(pk.n_slots, 1e30f);
         pk.org0 = 0.5 * (tmin[0] + tmax[0]); pk.org1 = 0.5 * (tmin[1] + tmax[1]); pk.org2 = 0.5 * (tmin[2] + tmax[2]);
         float max_abs = 0.f;
-        for (int j = 0; j < n; ++j) {
-            const double *p = pack->texel_pos + 3 * order[j];
+        for (int j = 0; j < pk.n_slots; ++j) {
+            if (slot_to_pack[j] < 0) continue;
+            const double *p = pack->texel_pos + 3 * slot_to_pack[j];
             tx[j] = p[0]; ty[j] = p[1]; tz[j] = p[2];
-            float4 r;
-            r.x = (float)(p[0] - pk.org0); r.y = (float)(p[1] - pk.org1); r.z = (float)(p[2] - pk.org2);
-            const unsigned w = (unsigned)bin_of[order[j]] | ((unsigned)gcell[j] << 16);
-            std::memcpy(&r.w, &w, 4);
-            trel[j] = r;
-            max_abs = std::max(max_abs, std::max(std::fabs(r.x), std::max(std::fabs(r.y), std::fabs(r.z))));
+            fx[j] = (float)(p[0] - pk.org0); fy[j] = (float)(p[1] - pk.org1); fz[j] = (float)(p[2] - pk.org2);
+            max_abs = std::max(max_abs, std::max(std::fabs(fx[j]), std::max(std::fabs(fy[j]), std::fabs(fz[j]))));
         }
         // FP32 ball test error bound (see stamp()): |d2_f32 - d2_f64| < 4 ulp(2 max|coord|) * sqrt(3) * 2r
         const double bound = 4.0 * (double)ulp_f32(2.f * max_abs + (float)(2 * kPaintRadius)) * 1.7320508 * 2 * kPaintRadius + 4e-9;
@@ -491,8 +502,9 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
         CUDA_TRY(e->arena.upload(tx, &pk.tx));
         CUDA_TRY(e->arena.upload(ty, &pk.ty));
         CUDA_TRY(e->arena.upload(tz, &pk.tz));
-        CUDA_TRY(e->arena.upload(trel, &pk.trel));
-        CUDA_TRY(e->arena.upload(order, &pk.sorted_to_pack));
+        CUDA_TRY(e->arena.upload(fx, &pk.fx));
+        CUDA_TRY(e->arena.upload(fy, &pk.fy));
+        CUDA_TRY(e->arena.upload(fz, &pk.fz));
     }
 
     // ---- silhouette table, ranges
@@ -529,19 +541,13 @@ int obs_dim_of(const PaintrlConfig *cfg) {
 
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
-template <typename F>
-int dispatch(PaintrlEngine *e, F &&f) {
-    // colour mode -> kernel instantiation
-    if (e->color == 0) return f(std::integral_constant<int, 0>{});
-    return f(std::integral_constant<int, 1>{});
-}
-
-template <int C>
-EnvArrays<C> env_arrays(PaintrlEngine *e) {
-    EnvArrays<C> ea;
+EnvArrays env_arrays(PaintrlEngine *e) {
+    EnvArrays ea;
     ea.states = e->states;
-    ea.planes = reinterpret_cast<typename StatusT<C>::type *>(e->planes);
-    ea.bin_cnt = e->bin_cnt;
+    ea.moves = e->moves;
+    ea.env_stats = e->env_stats;
+    ea.bits = e->bits;
+    ea.thick = e->thick;
     ea.grid_cnt = e->grid_cnt;
     return ea;
 }
@@ -618,16 +624,19 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     c.auto_reset = cfg->auto_reset;
     c.seed = cfg->seed;
 
-    const size_t elem = e->color == 0 ? 1 : 2;
-    const size_t plane_bytes = (size_t)num_envs * e->pk.n_pad * elem;
-    const size_t cnt_bytes = (size_t)num_envs * (e->pk.n_bins_pad / 2) * sizeof(unsigned);
+    const size_t bits_bytes = (size_t)num_envs * e->pk.n_words_pad * sizeof(unsigned);
+    const size_t thick_bytes = e->color == 1 ? (size_t)num_envs * e->pk.n_slots * sizeof(int16_t) : 0;
     const size_t gcnt_bytes = (size_t)num_envs * e->pk.n_gcells_pad * sizeof(unsigned);
     const size_t adim = c.action_mode == 0 ? sizeof(long long) : sizeof(double) * c.action_shape;
+    double *reset_obs = nullptr;
     bool ok = e->arena.alloc((void **)&e->states, sizeof(EnvState) * (size_t)num_envs) == cudaSuccess &&
-              e->arena.alloc(&e->planes, plane_bytes) == cudaSuccess &&
-              e->arena.alloc((void **)&e->bin_cnt, cnt_bytes) == cudaSuccess &&
+              e->arena.alloc((void **)&e->moves, sizeof(MoveOut) * (size_t)num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&e->env_stats, sizeof(EnvStat) * (size_t)num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&e->bits, bits_bytes) == cudaSuccess &&
+              (thick_bytes == 0 || e->arena.alloc((void **)&e->thick, thick_bytes) == cudaSuccess) &&
               (gcnt_bytes == 0 || e->arena.alloc((void **)&e->grid_cnt, gcnt_bytes) == cudaSuccess) &&
               e->arena.alloc((void **)&e->stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              e->arena.alloc((void **)&reset_obs, sizeof(double) * od * (size_t)e->pk.n_starts) == cudaSuccess &&
               e->arena.alloc(&e->stage_actions, adim * num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&e->stage_obs, sizeof(double) * od * (size_t)num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&e->stage_next_obs, sizeof(double) * od * (size_t)num_envs) == cudaSuccess &&
@@ -635,11 +644,18 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
               e->arena.alloc((void **)&e->stage_done, (size_t)num_envs) == cudaSuccess;
     if (!ok) { delete e; return fail(PAINTRL_E_CUDA, "device allocation failed (state / status planes)"); }
     cudaMemset(e->states, 0, sizeof(EnvState) * (size_t)num_envs);
-    cudaMemset(e->planes, 0, plane_bytes);
-    cudaMemset(e->bin_cnt, 0, cnt_bytes);
+    cudaMemset(e->moves, 0, sizeof(MoveOut) * (size_t)num_envs);
+    cudaMemset(e->env_stats, 0, sizeof(EnvStat) * (size_t)num_envs);
+    cudaMemset(e->bits, 0, bits_bytes);
+    if (e->thick) cudaMemset(e->thick, 0, thick_bytes);
     if (e->grid_cnt) cudaMemset(e->grid_cnt, 0, gcnt_bytes);
     cudaMemset(e->stats, 0, 4 * sizeof(unsigned long long));
-    err = cudaDeviceSynchronize();
+    // observation of a fresh environment at every start point, from environment 0's all-zero planes
+    e->pk.reset_obs = reset_obs;
+    reset_obs_kernel<<<(e->pk.n_starts + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32>>>(
+        e->pk, e->cfg, e->bits, e->grid_cnt, reset_obs);
+    err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, cudaGetErrorString(err)); }
     *out = e;
     return PAINTRL_OK;
@@ -665,12 +681,9 @@ static int reset_like(PaintrlHandle h, const int32_t *env_ids, int32_t n, const 
     if (!env_ids && n != h->num_envs) return fail(PAINTRL_E_INVALID, "env_ids == NULL requires n == num_envs");
     CUDA_TRY(cudaSetDevice(h->device));
     const int blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    return dispatch(h, [&](auto color) {
-        constexpr int C = decltype(color)::value;
-        reset_kernel<C><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays<C>(h), env_ids, n,
-                                                                                start_idx, pos, normal, obs, mode);
-        return launch_check(h, "reset_kernel");
-    });
+    reset_kernel<<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), env_ids, n, start_idx,
+                                                                         pos, normal, obs, mode);
+    return launch_check(h, "reset_kernel");
 }
 
 int paintrl_reset(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, const int32_t *start_idx_dev, double *obs_dev,
@@ -696,13 +709,15 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     io.actual = actual_dev; io.done = done_dev; io.new_texels = new_texels_dev;
     io.next_obs = h->cfg.auto_reset ? next_obs_dev : nullptr;
     io.reset_start_idx = reset_start_idx_dev;
-    io.stats = h->stats;
     const int blocks = (h->num_envs + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    return dispatch(h, [&](auto color) {
-        constexpr int C = decltype(color)::value;
-        step_kernel<C><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays<C>(h), h->num_envs, io);
-        return launch_check(h, "step_kernel");
-    });
+    move_kernel<<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
+    int rc = launch_check(h, "move_kernel");
+    if (rc != PAINTRL_OK) return rc;
+    if (h->color == 0)
+        paint_kernel<0><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
+    else
+        paint_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
+    return launch_check(h, "paint_kernel");
 }
 
 int paintrl_step_host(PaintrlHandle h, const void *actions_host, double *obs_host, double *reward_host,
@@ -740,12 +755,9 @@ int paintrl_get_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, in
     if (n <= 0 || n > h->num_envs || (!env_ids_dev && n != h->num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
     CUDA_TRY(cudaSetDevice(h->device));
     dim3 grid(std::max(1, std::min(64, (h->pk.n_texels + 255) / 256)), n);
-    return dispatch(h, [&](auto color) {
-        constexpr int C = decltype(color)::value;
-        get_state_kernel<C><<<grid, 256, 0, as_stream(stream)>>>(h->pk, env_arrays<C>(h), env_ids_dev, n, status_dev, pose_dev,
-                                                                  quat_dev, scalars_dev);
-        return launch_check(h, "get_state_kernel");
-    });
+    get_state_kernel<<<grid, 256, 0, as_stream(stream)>>>(h->pk, env_arrays(h), env_ids_dev, n, status_dev, pose_dev, quat_dev,
+                                                          scalars_dev);
+    return launch_check(h, "get_state_kernel");
 }
 
 int paintrl_set_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, const int16_t *status_dev,
@@ -753,27 +765,19 @@ int paintrl_set_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, co
     if (!h) return fail(PAINTRL_E_INVALID, "null handle");
     if (n <= 0 || n > h->num_envs || (!env_ids_dev && n != h->num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
     CUDA_TRY(cudaSetDevice(h->device));
-    dim3 grid(std::max(1, std::min(64, (h->pk.n_texels + 255) / 256)), n);
-    return dispatch(h, [&](auto color) {
-        constexpr int C = decltype(color)::value;
-        set_state_kernel<C><<<grid, 256, 0, as_stream(stream)>>>(h->pk, env_arrays<C>(h), env_ids_dev, n, status_dev, pose_dev,
-                                                                  quat_dev, scalars_dev);
-        int rc = launch_check(h, "set_state_kernel");
-        if (rc != PAINTRL_OK || !status_dev) return rc;
-        // the flip counters follow the status plane
-        recount_kernel<C><<<(n + 3) / 4, 128, 0, as_stream(stream)>>>(h->pk, env_arrays<C>(h), env_ids_dev, n);
-        return launch_check(h, "recount_kernel");
-    });
+    set_scalars_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(env_arrays(h), env_ids_dev, n, pose_dev, quat_dev,
+                                                                        scalars_dev, status_dev ? 1 : 0);
+    int rc = launch_check(h, "set_scalars_kernel");
+    if (rc != PAINTRL_OK || !status_dev) return rc;
+    set_status_kernel<<<(n + 3) / 4, 128, 0, as_stream(stream)>>>(h->pk, env_arrays(h), env_ids_dev, n, status_dev);
+    return launch_check(h, "set_status_kernel");
 }
 
 int paintrl_job_status(PaintrlHandle h, int32_t *painted_dev, void *stream) {
     if (!h || !painted_dev) return fail(PAINTRL_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
     const int blocks = (h->num_envs + 3) / 4;
-    if (h->color == 0)
-        job_status_kernel<0><<<blocks, 128, 0, as_stream(stream)>>>(h->pk, (const uint8_t *)h->planes, h->num_envs, painted_dev);
-    else
-        job_status_kernel<1><<<blocks, 128, 0, as_stream(stream)>>>(h->pk, (const int16_t *)h->planes, h->num_envs, painted_dev);
+    job_status_kernel<<<blocks, 128, 0, as_stream(stream)>>>(h->pk, env_arrays(h), h->num_envs, painted_dev);
     return launch_check(h, "job_status_kernel");
 }
 
@@ -781,12 +785,15 @@ int paintrl_stats(PaintrlHandle h, PaintrlStats *out) {
     if (!h || !out) return fail(PAINTRL_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
     unsigned long long host[4];
+    CUDA_TRY(cudaMemset(h->stats, 0, sizeof(host)));
+    stats_kernel<<<std::max(1, std::min(64, (h->num_envs + 255) / 256)), 256>>>(h->env_stats, h->num_envs, h->stats);
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(host, h->stats, sizeof(host), cudaMemcpyDeviceToHost));
-    out->env_steps = host[0];
-    out->episodes_ended = host[1];
-    out->footprint_texels = host[2];
+    out->episodes_ended = host[0];
+    out->footprint_texels = host[1];
+    out->ray_full_scans = host[2];
+    out->env_steps = host[3];
     out->kernel_launches = h->launches;
-    out->ray_full_scans = host[3];
     return PAINTRL_OK;
 }
 

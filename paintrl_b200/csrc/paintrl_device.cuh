@@ -22,6 +22,7 @@ constexpr int kPainted = 255;                 // bullet_paint_wrapper.py:354, 49
 constexpr double kPi = 3.141592653589793;     // math.pi / np.pi
 constexpr int kMaxObs = 128;                  // largest observation vector (OBS_GRAD^2 or OBS_GRAD+2)
 constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxRows = 128;                // rows of the texel layout
 constexpr unsigned kFull = 0xffffffffu;
 
 enum : int { kFlagLastOnPart = 1, kFlagTerminate = 2, kFlagHasLast = 4 };
@@ -44,6 +45,20 @@ struct alignas(128) EnvState {
     int32_t episode;
 };
 static_assert(sizeof(EnvState) == 128, "EnvState must be one 128-byte line");
+
+// What the move kernel hands to the paint kernel: the five shot centres of the step
+// (robot.py:277-278) and how many off-part sub-steps it counted (robot.py:427-430).
+struct alignas(128) MoveOut {
+    double centers[kPaintPerAction][3];
+    int32_t offpart_added;
+    int32_t full_scans;
+};
+static_assert(sizeof(MoveOut) == 128, "MoveOut must be one 128-byte line");
+
+// Per-environment counters behind paintrl_stats (summed on request; no atomics on the step path).
+struct alignas(32) EnvStat {
+    unsigned long long episodes_ended, footprint_texels, full_scans, env_steps;
+};
 
 // One cell of the move grid over (axis0, axis1) (see build_move_cells in paintrl_capi.cu).
 // Inside the hull's silhouette: the hull planes that are not satisfied with margin everywhere in
@@ -72,7 +87,7 @@ constexpr int kTriRec = 24;       // doubles per incident-triangle record:
 
 // Constant per-part tables in device memory (shared by all environments, L1/L2 resident).
 struct DevPack {
-    int n_texels, n_pad;          // n_pad: status-plane length per env, multiple of 128
+    int n_texels;
     int axis0, axis1;
     int status_init;
     // collision hull: (nx, ny, nz, off) per plane
@@ -92,15 +107,25 @@ struct DevPack {
     const double *vx, *vy, *vz;   // sorted vertex coordinates
     const int *vid;               // sorted -> pack vertex index
     const unsigned *vrec;         // [n_vertices] rec_begin << 8 | deg per pack vertex
-    // texel bins over (axis0, axis1): texels sorted by bin (row-major, axis1 = row)
-    int tb_nx, tb_ny;             // tb_nx is even
-    double tb_o0, tb_o1, tb_inv;
-    const int *tb_start;          // [tb_nx*tb_ny + 1]
-    const int *tb_prefix;         // [(tb_ny+1)*(tb_nx+1)] exclusive 2-D prefix sums of the bin sizes
-    int n_bins_pad;               // per-env flip counters (uint16), multiple of 64
-    const float4 *trel;           // [n_pad] position - origin in FP32, w = bin | gcell << 16 (bits)
+    // texel layout "rows and words" (see build_tables in paintrl_capi.cu): rows = strips along
+    // axis1, texels of a row sorted by their axis0 coordinate and packed 32 to a word; every row
+    // starts a new word.  A slot is (word, bit); pad slots hold far-away positions.
+    int n_words, n_words_pad;     // n_words_pad: per-env bit-plane stride in words (multiple of 32)
+    int n_slots;                  // n_words * 32
+    int n_rows;                   // <= kMaxRows
+    double row_o1, row_inv, row_h;   // row(y) = floor((y - row_o1) * row_inv)
+    int ncx;                      // cells along axis0, cell(x) = floor((x - cx_o0) * cx_inv)
+    double cx_o0, cx_inv;
+    const int *row_word0;         // [n_rows + 1] first word of each row
+    const int *row_count;         // [n_rows] texels in the row
+    const int *cell_start;        // [n_rows][ncx + 1] index in the row of the first texel with cell >= c
+    const unsigned *word_info;    // [n_words] row | (word index within the row) << 8
+    const float *fx, *fy, *fz;    // [n_slots] position - origin in FP32 (ball pre-test)
     double org0, org1, org2;
-    const double *tx, *ty, *tz;   // [n_pad] sorted texel positions (world x, y, z)
+    const double *tx, *ty, *tz;   // [n_slots] exact texel positions (world x, y, z)
+    const uint16_t *gcell;        // [n_slots] grid-observation cell (grid mode only)
+    const int *slot_to_pack;      // [n_slots] part-pack texel index, -1 for pad slots
+    const int *pack_to_slot;      // [n_texels]
     // grid observation (bullet_paint_wrapper.py:1072-1112)
     int n_gcells, n_gcells_pad;
     const int *gtotal;            // [obs_grad^2]
@@ -111,8 +136,7 @@ struct DevPack {
     // start points
     int n_starts;
     const double *start_pos, *start_normal;
-    // pack order <-> sorted order (state export)
-    const int *sorted_to_pack;    // [n_texels]
+    const double *reset_obs;      // [n_starts][obs_dim] observation of a fresh environment at each start point
 };
 
 struct DevConfig {
