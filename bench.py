@@ -304,9 +304,10 @@ def main():
                     'd2h_bytes_per_step': d2h_bytes, 'steps': e2e_steps, 'api': 'BatchedPaintEnv.step_host -> paintrl_step_host'},
             'gpu_launches': s1['kernel_launches'] - s0['kernel_launches'],
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src, 'kernel': 'paintrl::step_kernel',
+                         'traffic': None, 'peak_source': peak_src, 'kernel': 'paintrl::move_kernel + paintrl::paint_kernel (one step = two launches)',
                          'kernel_ms': kernel_ms, 'algorithmic_bytes_per_env_step': b_alg,
-                         'footprint_union_texels_mean': u_mean, 'p_reset': p_reset},
+                         'footprint_union_texels_mean': u_mean, 'p_reset': p_reset,
+                         'ray_full_scans_per_env_step': (s1['ray_full_scans'] - s0['ray_full_scans']) / max(1, steps_done)},
             'rollout_stats': rollout, 'wall_s_timed_region': wall_s,
         }
         if world_size == 1 and not args.no_cpu_baseline:

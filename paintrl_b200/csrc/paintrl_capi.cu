@@ -257,6 +257,9 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
     CUDA_TRY(e->arena.upload(vcs, &pk.mc_vc));
     e->move_cell_planes_mean = inside_cells ? (double)planes_total / inside_cells : 0.0;
     e->move_cell_verts_mean = inside_cells ? (double)verts_total / inside_cells : 0.0;
+    if (getenv("PAINTRL_DEBUG"))
+        fprintf(stderr, "[paintrl] move cells %d x %d, %zu under the hull: %.2f planes, %.2f vertex candidates per cell; %zu plane refs\n",
+                nx, ny, inside_cells, e->move_cell_planes_mean, e->move_cell_verts_mean, pidx.size());
     return PAINTRL_OK;
 }
 
@@ -407,7 +410,7 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
     std::vector<int> row_word0(pk.n_rows + 1, 0);
     for (int r = 0; r < pk.n_rows; ++r) {
         const int words = (row_count[r] + 31) / 32;
-        if (words > 0xffffff) return fail(PAINTRL_E_INVALID, "texel row too long");
+        if (words >= (1 << 18)) return fail(PAINTRL_E_INVALID, "texel row too long");
         row_word0[r + 1] = row_word0[r] + words;
     }
     pk.n_words = std::max(row_word0[pk.n_rows], 1);
@@ -435,7 +438,11 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
                 while (c_next <= cell_of[t]) cs[c_next++] = i;   // monotone: the row is sorted by axis0
             }
             while (c_next <= pk.ncx) cs[c_next++] = row_count[r];
-            for (int w = row_word0[r]; w < row_word0[r + 1]; ++w) word_info[w] = (unsigned)r | ((unsigned)(w - row_word0[r]) << 8);
+            for (int w = row_word0[r]; w < row_word0[r + 1]; ++w) {
+                const int wi = w - row_word0[r];
+                const int valid = std::min(32, row_count[r] - 32 * wi);
+                word_info[w] = (unsigned)r | ((unsigned)valid << 8) | ((unsigned)wi << 14);
+            }
             pos += row_count[r];
         }
     }
@@ -505,6 +512,13 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
         CUDA_TRY(e->arena.upload(fx, &pk.fx));
         CUDA_TRY(e->arena.upload(fy, &pk.fy));
         CUDA_TRY(e->arena.upload(fz, &pk.fz));
+        // origin-relative FP32 copies of the row / cell grids (stamp_ranges)
+        const double org_a0 = a0 == 0 ? pk.org0 : (a0 == 1 ? pk.org1 : pk.org2);
+        const double org_a1 = a1 == 0 ? pk.org0 : (a1 == 1 ? pk.org1 : pk.org2);
+        pk.rel_row_o1 = (float)(pk.row_o1 - org_a1);
+        pk.rel_row_h = (float)pk.row_h;
+        pk.rel_cx_o0 = (float)(pk.cx_o0 - org_a0);
+        pk.rel_cx_inv = (float)pk.cx_inv;
     }
 
     // ---- silhouette table, ranges
@@ -713,10 +727,16 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     move_kernel<<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
     int rc = launch_check(h, "move_kernel");
     if (rc != PAINTRL_OK) return rc;
-    if (h->color == 0)
-        paint_kernel<0><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
-    else
-        paint_kernel<1><<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
+    const bool staged = h->pk.n_words_pad <= kStageWords;
+    const dim3 grid(blocks), block(kWarpsPerBlock * 32);
+    cudaStream_t s = as_stream(stream);
+    if (h->color == 0) {
+        if (staged) paint_kernel<0, true><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
+        else paint_kernel<0, false><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
+    } else {
+        if (staged) paint_kernel<1, true><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
+        else paint_kernel<1, false><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
+    }
     return launch_check(h, "paint_kernel");
 }
 

@@ -116,10 +116,11 @@ struct DevPack {
     double row_o1, row_inv, row_h;   // row(y) = floor((y - row_o1) * row_inv)
     int ncx;                      // cells along axis0, cell(x) = floor((x - cx_o0) * cx_inv)
     double cx_o0, cx_inv;
+    float rel_row_o1, rel_row_h, rel_cx_o0, rel_cx_inv;   // the two grids relative to the origin, FP32 (stamp_ranges)
     const int *row_word0;         // [n_rows + 1] first word of each row
     const int *row_count;         // [n_rows] texels in the row
     const int *cell_start;        // [n_rows][ncx + 1] index in the row of the first texel with cell >= c
-    const unsigned *word_info;    // [n_words] row | (word index within the row) << 8
+    const unsigned *word_info;    // [n_words] row | valid slots << 8 | (word index within the row) << 14
     const float *fx, *fy, *fz;    // [n_slots] position - origin in FP32 (ball pre-test)
     double org0, org1, org2;
     const double *tx, *ty, *tz;   // [n_slots] exact texel positions (world x, y, z)

@@ -44,13 +44,67 @@ struct EnvArrays {
     unsigned *grid_cnt;    // [num_envs][n_gcells_pad] flipped texels per grid-observation cell (grid mode only)
 };
 
+// Words of the per-environment bit-plane a warp stages in shared memory (one TMA bulk copy in,
+// one out); larger planes are accessed in global memory.
+constexpr int kStageWords = 512;
+
 // Per-warp shared scratch.
-struct WarpScratch {
-    double centers[kPaintPerAction + 1][3];   // the step's shot centres, then the previous step's last one
-    int rowL[kMaxRows], rowU[kMaxRows];       // texels of the row with axis0 coordinate <  / <= the TCP's
-    int rowWa[kMaxRows], rowWn[kMaxRows];     // stamp candidates of the row: first word, word count
-    int hist[2 * kMaxObs];                    // K != 4 section histogram
+template <bool STAGED>
+struct alignas(128) WarpScratch {
+    unsigned sbits[STAGED ? kStageWords : 32];   // the environment's flip bits (STAGED only)
+    EnvState st;                                  // the environment's record
+    MoveOut mv;                                   // the step's shot centres (from move_kernel)
+    int rowL[kMaxRows], rowU[kMaxRows];           // texels of the row with axis0 coordinate <  / <= the TCP's
+    int rowWa[kMaxRows], rowWn[kMaxRows];         // stamp candidates of the row: first word, word count
+                                                  // (reused as the K != 4 section histogram)
+    unsigned long long bar;                       // mbarrier of the bulk copies
 };
+static_assert(2 * kMaxRows >= 2 * kMaxObs, "the section histogram aliases rowWa / rowWn");
+
+// The environment's flip bits: staged in shared memory or in place in global memory (L2).
+template <bool STAGED>
+struct Bits {
+    unsigned *g;
+    unsigned *s;
+    __device__ __forceinline__ unsigned ld(int w) const { return STAGED ? s[w] : __ldcg(g + w); }
+    __device__ __forceinline__ void st(int w, unsigned v) const {
+        if (STAGED) s[w] = v; else __stcg(g + w, v);
+    }
+};
+
+// ---- TMA bulk copies (cp.async.bulk) between global memory and the warp's scratch
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}" ::"r"(smem_addr(bar)), "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned lowmask(int n) {   // n in [0, 32]
     return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
@@ -75,7 +129,8 @@ __device__ __forceinline__ const double *axis_table(const DevPack &pk, int a) {
 // coordinate is a monotone function evaluated with the same two FP64 operations for texels (host)
 // and the TCP (here), so texels of lower cells are < p0, those of higher cells are > p0, and only
 // the TCP's own cell of each row is compared value by value.
-__device__ __forceinline__ void row_ranks(const DevPack &pk, double p0, int lane, WarpScratch &ws) {
+template <typename WS>
+__device__ __forceinline__ void row_ranks(const DevPack &pk, double p0, int lane, WS &ws) {
     const double f = floor((p0 - pk.cx_o0) * pk.cx_inv);
     const double *kx = axis_table(pk, pk.axis0);
     for (int r = lane; r < pk.n_rows; r += 32) {
@@ -105,13 +160,15 @@ __device__ __forceinline__ void row_ranks(const DevPack &pk, double p0, int lane
 // 4-sector observation (bullet_paint_wrapper.py:1033-1061): for every front texel, rx / ry = texel
 // position - TCP position along the principal axes; skipped if both are 0; sector 0 if rx>0,ry>0,
 // 1 if rx<0,ry>0, 2 if rx<0,ry<0, else 3; obs[s] = #(status != 255) / #texels of the sector.
-__device__ __forceinline__ void section4_counts(const DevPack &pk, const unsigned *bits, const Vec3 &pose, int lane,
-                                                WarpScratch &ws, int tot[4], int open[4]) {
+template <typename WS, typename BITS>
+__device__ __forceinline__ void section4_counts(const DevPack &pk, const BITS &bits, const Vec3 &pose, int lane, WS &ws,
+                                                int tot[4], int open[4]) {
     const double p0 = comp(pose, pk.axis0), p1 = comp(pose, pk.axis1);
     row_ranks(pk, p0, lane, ws);
     const double f1 = floor((p1 - pk.row_o1) * pk.row_inv);
     const int prow = !(f1 >= 0.0) ? -1 : (f1 >= (double)pk.n_rows ? pk.n_rows : (int)f1);
     const bool init_painted = (pk.status_init == kPainted);
+    const unsigned flip = init_painted ? 0u : 0xffffffffu;   // open = bits ^ flip
 
     // ---- rows above / below the TCP's row: totals are static
     int t0 = 0, t1 = 0, t2 = 0, t3 = 0;
@@ -123,14 +180,12 @@ __device__ __forceinline__ void section4_counts(const DevPack &pk, const unsigne
     // ---- their open texels: prefix / suffix masks of each word
     int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
     for (int w = lane; w < pk.n_words; w += 32) {
-        const unsigned info = __ldg(&pk.word_info[w]);
+        const unsigned info = __ldg(&pk.word_info[w]);   // row | valid slots << 8 | word index in the row << 14
         const int r = (int)(info & 0xffu);
         if (r == prow) continue;
-        const int s = (int)(info >> 8) << 5;
-        const unsigned b = __ldcg(&bits[w]);
-        const unsigned mV = lowmask(clamp32(__ldg(&pk.row_count[r]) - s));
+        const int s = (int)(info >> 14) << 5;
+        const unsigned o = (bits.ld(w) ^ flip) & lowmask((int)((info >> 8) & 0x3fu));
         const unsigned mL = lowmask(clamp32(ws.rowL[r] - s));
-        const unsigned o = (init_painted ? b : ~b) & mV;
         if (r > prow) {
             const unsigned mU = lowmask(clamp32(ws.rowU[r] - s));
             o1 += __popc(o & mL);
@@ -149,13 +204,10 @@ __device__ __forceinline__ void section4_counts(const DevPack &pk, const unsigne
         for (int w = w0; w < w1; ++w) {
             const int idx = ((w - w0) << 5) + lane;
             const double y = __ldg(&ky[(size_t)w * 32 + lane]);
-            const unsigned b = __ldcg(&bits[w]);
-            const bool bit = (b >> lane) & 1u;
-            const bool is_open = init_painted ? bit : !bit;
+            const int op = (int)(((bits.ld(w) ^ flip) >> lane) & 1u);
             const bool gx = idx >= U, lx = idx < L, gy = y > p1, ly = y < p1;
             if (idx < n && (gx || lx || gy || ly)) {
                 const int q = (gx && gy) ? 0 : ((lx && gy) ? 1 : ((lx && ly) ? 2 : 3));
-                const int op = is_open ? 1 : 0;
                 if (q == 0) { t0 += 1; o0 += op; }
                 else if (q == 1) { t1 += 1; o1 += op; }
                 else if (q == 2) { t2 += 1; o2 += op; }
@@ -170,7 +222,8 @@ __device__ __forceinline__ void section4_counts(const DevPack &pk, const unsigne
 }
 
 // Section observation with K != 4 sectors (atan2 path, bullet_paint_wrapper.py:1026-1031): full scan.
-__device__ __forceinline__ void sectionk_counts(const DevPack &pk, const unsigned *bits, const Vec3 &pose, int section,
+template <typename BITS>
+__device__ __forceinline__ void sectionk_counts(const DevPack &pk, const BITS &bits, const Vec3 &pose, int section,
                                                 int lane, int *hist /*[2*kMaxObs] smem*/) {
     for (int i = lane; i < 2 * kMaxObs; i += 32) hist[i] = 0;
     __syncwarp();
@@ -188,15 +241,16 @@ __device__ __forceinline__ void sectionk_counts(const DevPack &pk, const unsigne
         int idx = (int)np_floor_divide(angle, basis);
         if (idx >= section) idx = section - 1;
         atomicAdd(&hist[idx], 1);
-        const bool bit = (__ldcg(&bits[w]) >> lane) & 1u;
+        const bool bit = (bits.ld(w) >> lane) & 1u;
         if (init_painted ? bit : !bit) atomicAdd(&hist[kMaxObs + idx], 1);
     }
     __syncwarp();
 }
 
 // robot_gym_env.py:306-319 _augmented_observation; every lane returns, lanes < obs_dim write.
-__device__ __forceinline__ void write_observation(const DevPack &pk, const DevConfig &cfg, const unsigned *bits,
-                                                  const unsigned *grid_cnt, const Vec3 &pose, int lane, WarpScratch &ws,
+template <typename WS, typename BITS>
+__device__ __forceinline__ void write_observation(const DevPack &pk, const DevConfig &cfg, const BITS &bits,
+                                                  const unsigned *grid_cnt, const Vec3 &pose, int lane, WS &ws,
                                                   double *obs_a, double *obs_b) {
     double a1, a2;
     normalized_pose(pk, pose, a1, a2);
@@ -234,9 +288,10 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const DevCo
             if (obs_b) obs_b[lane] = v;
         }
     } else {
-        sectionk_counts(pk, bits, pose, grad, lane, ws.hist);
+        int *hist = ws.rowWa;   // rowWa / rowWn are contiguous and free once the stamp is done
+        sectionk_counts(pk, bits, pose, grad, lane, hist);
         for (int s = lane; s < grad; s += 32) {
-            int t = ws.hist[s], o = ws.hist[kMaxObs + s];
+            int t = hist[s], o = hist[kMaxObs + s];
             double v = t == 0 ? 0.0 : (double)o / (double)t;
             if (obs_a) obs_a[s] = v;
             if (obs_b) obs_b[s] = v;
@@ -280,10 +335,8 @@ __device__ __forceinline__ void robot_reset(EnvState &st, const double *pos, con
     st.last_angle = 0.0;
 }
 
-// PaintGymEnv.reset (robot_gym_env.py:370-387) minus the observation
-__device__ __forceinline__ void env_reset(const DevPack &pk, EnvState &st, unsigned *bits, int16_t *thick,
-                                          unsigned *grid_cnt, int start_index, int lane) {
-    clear_planes(pk, bits, thick, grid_cnt, lane);
+// PaintGymEnv.reset (robot_gym_env.py:370-387) minus the planes and the observation
+__device__ __forceinline__ void state_reset(const DevPack &pk, EnvState &st, int start_index) {
     st.flags &= ~kFlagHasLast;                 // _last_painted_pixels = []
     st.step_counter = 0;
     st.total_return = 0.0;
@@ -324,8 +377,15 @@ constexpr int NS = kPaintPerAction;
 
 struct ShotsF { float x[NS + 1], y[NS + 1], z[NS + 1]; };
 
+// exact centre of shot s (s == NS: the previous step's last shot)
+template <typename WS>
+__device__ __forceinline__ double cen(const WS &ws, int s, int k) {
+    return s < NS ? ws.mv.centers[s][k] : ws.st.last_center[k];
+}
+
 // which shots (bits 0..4) and the previous step's last shot (bit 5) contain slot j
-__device__ __forceinline__ unsigned ball_mask(const DevPack &pk, const ShotsF &c, const WarpScratch &ws, int j, bool has_last) {
+template <typename WS>
+__device__ __forceinline__ unsigned ball_mask(const DevPack &pk, const ShotsF &c, const WS &ws, int j, bool has_last) {
     const float r2f = (float)(kPaintRadius * kPaintRadius);
     const float tx = __ldg(&pk.fx[j]), ty = __ldg(&pk.fy[j]), tz = __ldg(&pk.fz[j]);
     unsigned in = 0, amb = 0;
@@ -342,7 +402,7 @@ __device__ __forceinline__ unsigned ball_mask(const DevPack &pk, const ShotsF &c
         in = 0;
 #pragma unroll
         for (int s = 0; s <= NS; ++s) {
-            const double dx = x - ws.centers[s][0], dy = y - ws.centers[s][1], dz = z - ws.centers[s][2];
+            const double dx = x - cen(ws, s, 0), dy = y - cen(ws, s, 1), dz = z - cen(ws, s, 2);
             in |= ((dx * dx + dy * dy + dz * dz) <= r2 ? 1u : 0u) << s;
         }
     }
@@ -352,21 +412,22 @@ __device__ __forceinline__ unsigned ball_mask(const DevPack &pk, const ShotsF &c
 
 // Per row, the words whose texels can lie inside one of the step's shots: the row's axis1 interval
 // against the shots' axis1 extent gives a half-width along axis0 (the ball projects to a disc of
-// the same radius), the static cell table turns the axis0 interval into a slot range.  Only has
-// to be conservative: every slot of a candidate word is tested exactly.
-__device__ __forceinline__ void stamp_ranges(const DevPack &pk, double lo0, double hi0, double lo1, double hi1, int lane,
-                                             WarpScratch &ws) {
-    const double rr = kPaintRadius + 1e-6;
+// the same radius), the static cell table turns the axis0 interval into a slot range.  FP32 on
+// origin-relative coordinates with margins: it only has to be conservative, every slot of a
+// candidate word is tested exactly.
+template <typename WS>
+__device__ __forceinline__ void stamp_ranges(const DevPack &pk, float lo0, float hi0, float lo1, float hi1, int lane, WS &ws) {
+    const float rr = (float)kPaintRadius + 4e-5f;
     for (int r = lane; r < pk.n_rows; r += 32) {
         int wa = 0, wn = 0;
-        const double ylo = pk.row_o1 + r * pk.row_h - 1e-6, yhi = pk.row_o1 + (r + 1) * pk.row_h + 1e-6;
-        const double dy = fmax(0.0, fmax(ylo - hi1, lo1 - yhi));
+        const float ylo = fmaf((float)r, pk.rel_row_h, pk.rel_row_o1) - 2e-5f, yhi = ylo + pk.rel_row_h + 4e-5f;
+        const float dy = fmaxf(0.f, fmaxf(ylo - hi1, lo1 - yhi));
         if (dy <= rr) {
-            const double hw = (double)(sqrtf((float)(rr * rr - dy * dy)) * 1.0001f) + 1e-6;
-            const double fa = floor((lo0 - hw - pk.cx_o0) * pk.cx_inv) - 1.0;
-            const double fb = floor((hi0 + hw - pk.cx_o0) * pk.cx_inv) + 1.0;
-            if (fb >= 0.0 && fa < (double)pk.ncx) {
-                const int ca = (int)fmax(fa, 0.0), cb = (int)fmin(fb, (double)(pk.ncx - 1));
+            const float hw = sqrtf(rr * rr - dy * dy) + 4e-5f;
+            const float fa = floorf((lo0 - hw - pk.rel_cx_o0) * pk.rel_cx_inv) - 1.f;
+            const float fb = floorf((hi0 + hw - pk.rel_cx_o0) * pk.rel_cx_inv) + 1.f;
+            if (fb >= 0.f && fa < (float)pk.ncx) {
+                const int ca = (int)fmaxf(fa, 0.f), cb = (int)fminf(fb, (float)(pk.ncx - 1));
                 const int *cs = pk.cell_start + (size_t)r * (pk.ncx + 1);
                 const int i0 = __ldg(cs + ca), i1 = __ldg(cs + cb + 1);
                 if (i1 > i0) {
@@ -382,8 +443,8 @@ __device__ __forceinline__ void stamp_ranges(const DevPack &pk, double lo0, doub
 }
 
 // Calls body(w) warp-uniformly for every candidate word.
-template <typename BodyFn>
-__device__ __forceinline__ void for_each_stamp_word(const DevPack &pk, int lane, const WarpScratch &ws, BodyFn body) {
+template <typename WS, typename BodyFn>
+__device__ __forceinline__ void for_each_stamp_word(const DevPack &pk, int lane, const WS &ws, BodyFn body) {
     for (int r0 = 0; r0 < pk.n_rows; r0 += 32) {
         const int r = r0 + lane;
         const int wa = r < pk.n_rows ? ws.rowWa[r] : 0, wn = r < pk.n_rows ? ws.rowWn[r] : 0;
@@ -397,22 +458,25 @@ __device__ __forceinline__ void for_each_stamp_word(const DevPack &pk, int lane,
     }
 }
 
-template <int COLOR>
-__device__ __forceinline__ void stamp(const DevPack &pk, unsigned *bits, int16_t *thick, unsigned *grid_cnt, bool has_last,
-                                      int lane, WarpScratch &ws, int &n_new_out, int &n_possible_out) {
+// Returns (warp-uniform) the newly painted count (RGB) / removed thickness units (HSI), the
+// |union of valid pixels| of robot.py:425 and whether any flip bit changed.
+template <int COLOR, typename WS, typename BITS>
+__device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16_t *thick, unsigned *grid_cnt, bool has_last,
+                                      int lane, WS &ws, int &n_new_out, int &n_possible_out, bool &dirty_out) {
     ShotsF c;
 #pragma unroll
     for (int s = 0; s <= NS; ++s) {
-        c.x[s] = (float)(ws.centers[s][0] - pk.org0);
-        c.y[s] = (float)(ws.centers[s][1] - pk.org1);
-        c.z[s] = (float)(ws.centers[s][2] - pk.org2);
+        c.x[s] = (float)(cen(ws, s, 0) - pk.org0);
+        c.y[s] = (float)(cen(ws, s, 1) - pk.org1);
+        c.z[s] = (float)(cen(ws, s, 2) - pk.org2);
     }
-    double lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
+    float lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        const double c0 = ws.centers[s][pk.axis0], c1 = ws.centers[s][pk.axis1];
-        lo0 = fmin(lo0, c0); hi0 = fmax(hi0, c0);
-        lo1 = fmin(lo1, c1); hi1 = fmax(hi1, c1);
+        const float c0 = pk.axis0 == 0 ? c.x[s] : (pk.axis0 == 1 ? c.y[s] : c.z[s]);
+        const float c1 = pk.axis1 == 0 ? c.x[s] : (pk.axis1 == 1 ? c.y[s] : c.z[s]);
+        lo0 = fminf(lo0, c0); hi0 = fmaxf(hi0, c0);
+        lo1 = fminf(lo1, c1); hi1 = fmaxf(hi1, c1);
     }
     stamp_ranges(pk, lo0, hi0, lo1, hi1, lane, ws);
 
@@ -428,7 +492,7 @@ __device__ __forceinline__ void stamp(const DevPack &pk, unsigned *bits, int16_t
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     if (in & (1u << s)) {
-                        const double dx = x - ws.centers[s][0], dy = y - ws.centers[s][1], dz = z - ws.centers[s][2];
+                        const double dx = x - cen(ws, s, 0), dy = y - cen(ws, s, 1), dz = z - cen(ws, s, 2);
                         rmax[s] = fmax(rmax[s], dx * dx + dy * dy + dz * dz);
                     }
                 }
@@ -439,6 +503,7 @@ __device__ __forceinline__ void stamp(const DevPack &pk, unsigned *bits, int16_t
     }
 
     int n_new = 0, n_possible = 0;   // RGB: warp-uniform; HSI n_new: per-lane partial
+    unsigned any = 0;
     for_each_stamp_word(pk, lane, ws, [&](int w) {
         const int j = w * 32 + lane;
         const unsigned in = ball_mask(pk, c, ws, j, has_last);
@@ -450,10 +515,10 @@ __device__ __forceinline__ void stamp(const DevPack &pk, unsigned *bits, int16_t
         n_possible += __popc(__ballot_sync(kFull, (shots & ~prev) != 0u));
         unsigned flipped;                                  // slots whose painted predicate changes
         if (COLOR == 0) {                                  // :358-365
-            const unsigned old = __ldcg(&bits[w]);
+            const unsigned old = bits.ld(w);
             flipped = uni & ~old;
             n_new += __popc(flipped);
-            if (flipped && lane == 0) __stcg(&bits[w], old | uni);
+            if (flipped && lane == 0) bits.st(w, old | uni);
         } else {                                           // :411-434
             bool fl = false;
             if (shots) {
@@ -463,7 +528,7 @@ __device__ __forceinline__ void stamp(const DevPack &pk, unsigned *bits, int16_t
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     if ((shots & (1u << s)) && sv > 0) {
-                        const double dx = x - ws.centers[s][0], dy = y - ws.centers[s][1], dz = z - ws.centers[s][2];
+                        const double dx = x - cen(ws, s, 0), dy = y - cen(ws, s, 1), dz = z - cen(ws, s, 2);
                         const double ratio = sqrt(dx * dx + dy * dy + dz * dz) / rmax[s];
                         const int quantity = (int)(kHsiTargetMax * (1.0 - ratio * ratio)) + 1;   // :429
                         sv -= quantity;
@@ -476,12 +541,14 @@ __device__ __forceinline__ void stamp(const DevPack &pk, unsigned *bits, int16_t
                 }
             }
             flipped = __ballot_sync(kFull, fl);
-            if (flipped && lane == 0) __stcg(&bits[w], __ldcg(&bits[w]) | flipped);
+            if (flipped && lane == 0) bits.st(w, bits.ld(w) | flipped);
         }
+        any |= flipped;
         if (grid_cnt && ((flipped >> lane) & 1u)) atomicAdd(grid_cnt + __ldg(&pk.gcell[j]), 1u);
     });
     n_new_out = (COLOR == 0) ? n_new : __reduce_add_sync(kFull, n_new);
     n_possible_out = n_possible;
+    dirty_out = any != 0u;
     __syncwarp();
 }
 
@@ -584,58 +651,62 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
     store_state(&ea.states[env], st, lane);
 }
 
-// Everything after the move: stamp, score, observe, auto-reset.
-template <int COLOR>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// Everything after the move: stamp, score, observe, auto-reset.  The environment's record, the
+// move kernel's output and (STAGED) its flip bits come in through one TMA bulk-copy group per warp
+// and the bits go back the same way.
+template <int COLOR, bool STAGED>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, STAGED ? 8 : 4)
 paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
-    __shared__ WarpScratch scratch[kWarpsPerBlock];
+    typedef WarpScratch<STAGED> WS;
+    __shared__ WS scratch[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int env = blockIdx.x * kWarpsPerBlock + warp;
     if (env >= num_envs) return;
-    WarpScratch &ws = scratch[warp];
-    unsigned *bits = bits_of(pk, ea, env), *grid_cnt = grid_cnt_of(pk, ea, env);
+    WS &ws = scratch[warp];
+    unsigned *gbits = bits_of(pk, ea, env), *grid_cnt = grid_cnt_of(pk, ea, env);
     int16_t *thick = thick_of(pk, ea, env);
-    EnvState st;
-    load_state(&ea.states[env], st);
-    const MoveOut *mv = &ea.moves[env];
-    if (lane < 3 * NS) ws.centers[lane / 3][lane % 3] = __ldcg(&mv->centers[0][0] + lane);
-    if (lane == 16) ws.centers[NS][0] = st.last_center[0];
-    if (lane == 17) ws.centers[NS][1] = st.last_center[1];
-    if (lane == 18) ws.centers[NS][2] = st.last_center[2];
-    const int offpart_added = __ldcg(&mv->offpart_added), full_scans = __ldcg(&mv->full_scans);
+    const unsigned plane_bytes = (unsigned)pk.n_words_pad * 4u;
+    if (lane == 0) {
+        mbar_init(&ws.bar, 1);
+        mbar_expect_tx(&ws.bar, (unsigned)(sizeof(EnvState) + sizeof(MoveOut)) + (STAGED ? plane_bytes : 0u));
+        bulk_g2s(&ws.st, &ea.states[env], (unsigned)sizeof(EnvState), &ws.bar);
+        bulk_g2s(&ws.mv, &ea.moves[env], (unsigned)sizeof(MoveOut), &ws.bar);
+        if (STAGED) bulk_g2s(ws.sbits, gbits, plane_bytes, &ws.bar);
+    }
     __syncwarp();
+    mbar_wait(&ws.bar, 0);
+    const Bits<STAGED> bits = {gbits, ws.sbits};
+    EnvState &st = ws.st;
 
     // ---- stamp the 5 shots (bullet_paint_wrapper.py:568-577)
     const bool has_last = (st.flags & kFlagHasLast) != 0;
     int n_new, n_possible;
-    stamp<COLOR>(pk, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible);
-    st.last_center[0] = ws.centers[NS - 1][0];
-    st.last_center[1] = ws.centers[NS - 1][1];
-    st.last_center[2] = ws.centers[NS - 1][2];
-    st.flags |= kFlagHasLast;
+    bool dirty;
+    stamp<COLOR>(pk, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible, dirty);
 
-    // ---- robot.py:425-433, robot_gym_env.py:321-340
+    // ---- robot.py:425-433, robot_gym_env.py:321-340 (every lane computes the same scalars)
+    int flags = st.flags | kFlagHasLast;
     const double succeeded = (COLOR == 0) ? (double)n_new : (double)n_new / 255.0;
     const double rate = n_possible ? succeeded / (double)n_possible : 0.0;
-    if (offpart_added >= kPaintPerAction && n_possible == 0) st.flags |= kFlagTerminate;
+    if (ws.mv.offpart_added >= kPaintPerAction && n_possible == 0) flags |= kFlagTerminate;
     const double reward = succeeded / 100;
-    st.total_reward += reward;
+    const double total_reward = st.total_reward + reward;
     double penalty = 0.2;
     if (cfg.overlap_penalty) penalty += 0.1 * (1 - rate);
     if (cfg.turning_penalty) penalty += 0.1 * (st.angle_diff / kPi);
     const double actual = reward - penalty;
 
     // ---- robot_gym_env.py:289-304 _termination
-    st.step_counter += 1;
+    const int step_counter = st.step_counter + 1;
     const double max_pts = cfg.max_possible_point;
-    const bool finished = !(max_pts > st.total_reward * 100);
-    const double avg_reward = st.total_reward / st.step_counter;
+    const bool finished = !(max_pts > total_reward * 100);
+    const double avg_reward = total_reward / step_counter;
     bool done, decided = false;
     if (avg_reward < cfg.expected_avg_reward && cfg.termination_mode != 0) {
         if (cfg.termination_mode == 1) { done = true; decided = true; }
-        else if (st.total_reward < cfg.hybrid_threshold) { done = true; decided = true; }
+        else if (total_reward < cfg.hybrid_threshold) { done = true; decided = true; }
     }
-    if (!decided) done = finished || (st.flags & kFlagTerminate) || st.step_counter > cfg.episode_max_length - 1;
+    if (!decided) done = finished || (flags & kFlagTerminate) || step_counter > cfg.episode_max_length - 1;
 
     // ---- observation (computed even when done, robot_gym_env.py:358)
     const bool resetting = done && cfg.auto_reset;
@@ -643,71 +714,87 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     double *next_obs = io.next_obs ? io.next_obs + (size_t)env * cfg.obs_dim : nullptr;
     const Vec3 cur_p = {st.pose[0], st.pose[1], st.pose[2]};
     write_observation(pk, cfg, bits, grid_cnt, cur_p, lane, ws, obs, resetting ? nullptr : next_obs);
-    if (!done) st.total_return += actual;
+    __syncwarp();
     if (lane == 0) {
         io.reward[env] = reward;
         io.penalty[env] = penalty;
         io.actual[env] = actual;
         io.done[env] = done ? 1 : 0;
         if (io.new_texels) io.new_texels[env] = n_new;
-        EnvStat *es = &ea.env_stats[env];
-        ulonglong4 v = *reinterpret_cast<ulonglong4 *>(es);
-        v.x += done ? 1ull : 0ull;
-        v.y += (unsigned long long)n_possible;
-        v.z += (unsigned long long)full_scans;
-        v.w += 1ull;
-        *reinterpret_cast<ulonglong4 *>(es) = v;
+        EnvStat *es = &ea.env_stats[env];       // no other thread touches this record: plain reductions, no return value
+        if (done) atomicAdd(&es->episodes_ended, 1ull);
+        if (n_possible) atomicAdd(&es->footprint_texels, (unsigned long long)n_possible);
+        if (ws.mv.full_scans) atomicAdd(&es->full_scans, (unsigned long long)ws.mv.full_scans);
+        atomicAdd(&es->env_steps, 1ull);
+        // the record
+        st.last_center[0] = ws.mv.centers[NS - 1][0];
+        st.last_center[1] = ws.mv.centers[NS - 1][1];
+        st.last_center[2] = ws.mv.centers[NS - 1][2];
+        st.flags = flags;
+        st.total_reward = total_reward;
+        st.step_counter = step_counter;
+        if (!done) st.total_return += actual;
     }
 
     // ---- same-step auto-reset: `obs` keeps the terminal observation, `next_obs` gets reset()'s
     if (resetting) {
         int idx = io.reset_start_idx ? io.reset_start_idx[env] : auto_start_index(pk, cfg, env, st.episode);
         idx = min(max(idx, 0), pk.n_starts - 1);
+        clear_planes(pk, gbits, thick, grid_cnt, lane);
         __syncwarp();
-        env_reset(pk, st, bits, thick, grid_cnt, idx, lane);
+        if (lane == 0) state_reset(pk, st, idx);
         if (next_obs) {
             const double *src = pk.reset_obs + (size_t)idx * cfg.obs_dim;
             for (int i = lane; i < cfg.obs_dim; i += 32) next_obs[i] = __ldg(&src[i]);
         }
+    } else if (STAGED && dirty) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_s2g(gbits, ws.sbits, plane_bytes);
     }
-    store_state(&ea.states[env], st, lane);
+    __syncwarp();
+    if (lane < 8) reinterpret_cast<double2 *>(&ea.states[env])[lane] = reinterpret_cast<const double2 *>(&st)[lane];
+    if (STAGED && lane == 0) bulk_wait_read();
 }
 
 // PaintGymEnv.reset / Robot.reset(pose) for the listed environments, with their first observation.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, const int32_t *env_ids, int n, const int32_t *start_idx,
              const double *set_pos, const double *set_normal, double *obs_out, int mode /*0 reset, 1 set_pose*/) {
-    __shared__ WarpScratch scratch[kWarpsPerBlock];
+    __shared__ WarpScratch<false> scratch[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = blockIdx.x * kWarpsPerBlock + warp;
     if (k >= n) return;
     const int env = env_ids ? env_ids[k] : k;
-    unsigned *bits = bits_of(pk, ea, env), *grid_cnt = grid_cnt_of(pk, ea, env);
+    unsigned *gbits = bits_of(pk, ea, env), *grid_cnt = grid_cnt_of(pk, ea, env);
     int16_t *thick = thick_of(pk, ea, env);
     EnvState st;
     load_state(&ea.states[env], st);
     if (mode == 0) {
         int idx = start_idx ? start_idx[k] : auto_start_index(pk, cfg, env, st.episode);
         idx = min(max(idx, 0), pk.n_starts - 1);
-        env_reset(pk, st, bits, thick, grid_cnt, idx, lane);
+        clear_planes(pk, gbits, thick, grid_cnt, lane);
+        state_reset(pk, st, idx);
     } else {
         robot_reset(st, set_pos + 3 * k, set_normal + 3 * k);
     }
     __syncwarp();
+    const Bits<false> bits = {gbits, nullptr};
     Vec3 pose = {st.pose[0], st.pose[1], st.pose[2]};
-    write_observation(pk, cfg, bits, grid_cnt, pose, lane, scratch[warp],
-                      obs_out ? obs_out + (size_t)k * cfg.obs_dim : nullptr, nullptr);
+    write_observation(pk, cfg, bits, grid_cnt, pose, lane, scratch[warp], obs_out ? obs_out + (size_t)k * cfg.obs_dim : nullptr,
+                      nullptr);
     store_state(&ea.states[env], st, lane);
 }
 
 // Observation of a fresh environment standing at each start point (paint_kernel's auto-reset
-// copies it instead of scanning the cleared planes again).  `bits` / `grid_cnt` are all-zero planes.
+// copies it instead of scanning the cleared planes again).  `zero_bits` / `grid_cnt` are all-zero planes.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-reset_obs_kernel(DevPack pk, DevConfig cfg, const unsigned *bits, const unsigned *grid_cnt, double *table) {
-    __shared__ WarpScratch scratch[kWarpsPerBlock];
+reset_obs_kernel(DevPack pk, DevConfig cfg, unsigned *zero_bits, const unsigned *grid_cnt, double *table) {
+    __shared__ WarpScratch<false> scratch[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = blockIdx.x * kWarpsPerBlock + warp;
     if (k >= pk.n_starts) return;
+    const Bits<false> bits = {zero_bits, nullptr};
     Vec3 pose = {pk.start_pos[3 * k], pk.start_pos[3 * k + 1], pk.start_pos[3 * k + 2]};
     write_observation(pk, cfg, bits, grid_cnt, pose, lane, scratch[warp], table + (size_t)k * cfg.obs_dim, nullptr);
 }
