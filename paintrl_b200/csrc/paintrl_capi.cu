@@ -78,6 +78,7 @@ struct PaintrlEngine {
     uint8_t *stage_done = nullptr;
     unsigned long long launches = 0;
     double move_cell_planes_mean = 0.0, move_cell_verts_mean = 0.0;
+    int move_lanes = 32;             // lanes per environment in move_kernel (8, 16 or 32)
 };
 
 namespace {
@@ -129,7 +130,7 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
     std::vector<VertCand> vcs;
     if (pack->n_planes >= 65535 || nx <= 0 || ny <= 0 || (long long)nx * ny > (1 << 21)) nx = ny = 0;   // fast path off
     cells.resize((size_t)nx * ny);
-    const double kDepthPad = 5e-4, kFootSlack = 1e-6, kMargin = 1e-9, kVertSlack = 1e-9;
+    const double kPadBelow = 5e-4, kPadAbove = 1e-4, kFootSlack = 1e-6, kMargin = 1e-9, kVertSlack = 1e-9;
     const int K = 5;
     // the tool hovers on the side the start normals point away from and looks along them
     const double side = pack->start_normal[np] <= 0.0 ? 1.0 : -1.0;
@@ -149,9 +150,13 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
             mc.plane_begin = (int)pidx.size();
             mc.vert_begin = (int)vcs.size();
             mc.n_planes = mc.n_verts = 0;
-            mc.dlo = 1.0; mc.dhi = -1.0;
+            mc.a = mc.b = mc.c = 0.0;
+            mc.rlo = 1.0; mc.rhi = -1.0;
+            mc.pad_ = 0.0;
             const double lo0 = o0 + cx * cs, hi0 = o0 + (cx + 1) * cs, lo1 = o1 + cy * cs, hi1 = o1 + (cy + 1) * cs;
-            double zmin = INFINITY, zmax = -INFINITY;
+            const double mid0 = 0.5 * (lo0 + hi0), mid1 = 0.5 * (lo1 + hi1);
+            // sample the hull's tool-side surface over the footprint
+            double sx[K * K], sy[K * K], sd[K * K];
             int hits = 0;
             for (int i = 0; i < K; ++i) {
                 for (int j = 0; j < K; ++j) {
@@ -161,25 +166,53 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
                     frm[np] = side * 100.0;
                     double t;
                     if (host_ray(pack, frm, dir, &t)) {
-                        double depth = frm[np] + dir[np] * t;
-                        zmin = std::min(zmin, depth);
-                        zmax = std::max(zmax, depth);
+                        sx[hits] = frm[a0] - mid0; sy[hits] = frm[a1] - mid1; sd[hits] = frm[np] + dir[np] * t;
                         ++hits;
                     }
                 }
             }
-            if (hits == K * K) {
-                // ---- under the hull
-                zmin -= kDepthPad;
-                zmax += kDepthPad;
-                mc.dlo = zmin;
-                mc.dhi = zmax;
+            // plane fitted to the samples: depth ~ fa + fb (x0 - mid0) + fc (x1 - mid1)
+            bool region = false;
+            double fa = 0, fb = 0, fc = 0;
+            if (hits >= 4) {
+                double sxx = 0, sxy = 0, syy = 0, sx1 = 0, sy1 = 0, sxd = 0, syd = 0, sd1 = 0;
+                for (int q = 0; q < hits; ++q) {
+                    sxx += sx[q] * sx[q]; sxy += sx[q] * sy[q]; syy += sy[q] * sy[q];
+                    sx1 += sx[q]; sy1 += sy[q]; sxd += sx[q] * sd[q]; syd += sy[q] * sd[q]; sd1 += sd[q];
+                }
+                const double n = hits;
+                // normal equations [[n sx1 sy1] [sx1 sxx sxy] [sy1 sxy syy]] (fa fb fc) = (sd1 sxd syd)
+                const double det = n * (sxx * syy - sxy * sxy) - sx1 * (sx1 * syy - sxy * sy1) + sy1 * (sx1 * sxy - sxx * sy1);
+                if (std::fabs(det) > 1e-12 * n * (cs * cs) * (cs * cs)) {
+                    fa = (sd1 * (sxx * syy - sxy * sxy) - sx1 * (sxd * syy - sxy * syd) + sy1 * (sxd * sxy - sxx * syd)) / det;
+                    fb = (n * (sxd * syy - syd * sxy) - sd1 * (sx1 * syy - sxy * sy1) + sy1 * (sx1 * syd - sxd * sy1)) / det;
+                    fc = (n * (sxx * syd - sxy * sxd) - sx1 * (sx1 * syd - sxd * sy1) + sd1 * (sx1 * sxy - sxx * sy1)) / det;
+                    region = std::isfinite(fa) && std::isfinite(fb) && std::isfinite(fc);
+                }
+            }
+            if (region) {
+                // ---- the hull surface passes over the cell: region hugging it
+                double rmin = INFINITY, rmax = -INFINITY;
+                for (int q = 0; q < hits; ++q) {
+                    const double res = sd[q] - (fa + fb * sx[q] + fc * sy[q]);
+                    rmin = std::min(rmin, res); rmax = std::max(rmax, res);
+                }
+                // tool side is +side: above the surface = larger side * depth
+                const double rlo = rmin - (side > 0 ? kPadBelow : kPadAbove), rhi = rmax + (side > 0 ? kPadAbove : kPadBelow);
+                mc.a = fa - fb * mid0 - fc * mid1;
+                mc.b = fb;
+                mc.c = fc;
+                mc.rlo = rlo;
+                mc.rhi = rhi;
                 double corner[8][3];
+                double zmin = INFINITY, zmax = -INFINITY;
                 for (int c = 0; c < 8; ++c) {
                     corner[c][a0] = (c & 1) ? hi0 + kFootSlack : lo0 - kFootSlack;
                     corner[c][a1] = (c & 2) ? hi1 + kFootSlack : lo1 - kFootSlack;
-                    corner[c][np] = (c & 4) ? zmax : zmin;
+                    corner[c][np] = mc.a + mc.b * corner[c][a0] + mc.c * corner[c][a1] + ((c & 4) ? rhi : rlo);
+                    zmin = std::min(zmin, corner[c][np]); zmax = std::max(zmax, corner[c][np]);
                 }
+                zmin -= 1e-9; zmax += 1e-9;
                 for (int p = 0; p < pack->n_planes; ++p) {
                     const double *n = pack->plane_n + 3 * p;
                     double worst = -INFINITY;
@@ -188,7 +221,7 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
                     if (worst > pack->plane_off[p] - kMargin) pidx.push_back((uint16_t)p);
                 }
                 mc.n_planes = (int)pidx.size() - mc.plane_begin;
-                // candidates for the nearest front vertex of any point of the box
+                // candidates for the nearest front vertex of any point of the region (its bounding box)
                 double blo[3], bhi[3];
                 blo[a0] = lo0 - kFootSlack; bhi[a0] = hi0 + kFootSlack;
                 blo[a1] = lo1 - kFootSlack; bhi[a1] = hi1 + kFootSlack;
@@ -225,7 +258,6 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
             } else {
                 // ---- beside (or straddling the edge of) the hull: planes deciding a few sample rays
                 tmp.clear();
-                const double mid0 = 0.5 * (lo0 + hi0), mid1 = 0.5 * (lo1 + hi1);
                 const double tilt = 0.35;
                 const double sample[9][4] = {{mid0, mid1, 0, 0},    {mid0, mid1, tilt, 0}, {mid0, mid1, -tilt, 0},
                                              {mid0, mid1, 0, tilt}, {mid0, mid1, 0, -tilt}, {lo0, lo1, 0, 0},
@@ -258,7 +290,7 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
     e->move_cell_planes_mean = inside_cells ? (double)planes_total / inside_cells : 0.0;
     e->move_cell_verts_mean = inside_cells ? (double)verts_total / inside_cells : 0.0;
     if (getenv("PAINTRL_DEBUG"))
-        fprintf(stderr, "[paintrl] move cells %d x %d, %zu under the hull: %.2f planes, %.2f vertex candidates per cell; %zu plane refs\n",
+        fprintf(stderr, "[paintrl] move cells %d x %d, %zu with a surface region: %.2f planes, %.2f vertex candidates per cell; %zu plane refs\n",
                 nx, ny, inside_cells, e->move_cell_planes_mean, e->move_cell_verts_mean, pidx.size());
     return PAINTRL_OK;
 }
@@ -671,6 +703,11 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     err = cudaGetLastError();
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, cudaGetErrorString(err)); }
+    {
+        const char *ml = getenv("PAINTRL_MOVE_LANES");
+        int lanes = ml ? atoi(ml) : 8;
+        e->move_lanes = (lanes == 16 || lanes == 32) ? lanes : 8;
+    }
     *out = e;
     return PAINTRL_OK;
 }
@@ -724,7 +761,16 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     io.next_obs = h->cfg.auto_reset ? next_obs_dev : nullptr;
     io.reset_start_idx = reset_start_idx_dev;
     const int blocks = (h->num_envs + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    move_kernel<<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
+    {   // lanes per environment in the move phase: fewer when there are enough environments to fill the GPU
+        const int threads = kWarpsPerBlock * 32;
+        cudaStream_t ms = as_stream(stream);
+        if (h->move_lanes == 8)
+            move_kernel<8><<<(h->num_envs * 8 + threads - 1) / threads, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
+        else if (h->move_lanes == 16)
+            move_kernel<16><<<(h->num_envs * 16 + threads - 1) / threads, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
+        else
+            move_kernel<32><<<blocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
+    }
     int rc = launch_check(h, "move_kernel");
     if (rc != PAINTRL_OK) return rc;
     const bool staged = h->pk.n_words_pad <= kStageWords;

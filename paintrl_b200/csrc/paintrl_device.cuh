@@ -61,16 +61,19 @@ struct alignas(32) EnvStat {
 };
 
 // One cell of the move grid over (axis0, axis1) (see build_move_cells in paintrl_capi.cu).
-// Inside the hull's silhouette: the hull planes that are not satisfied with margin everywhere in
-// the cell's box (footprint x [dlo, dhi] along the non-principal axis) and the front vertices
-// that can be nearest to some point of that box.  Outside it: dlo > dhi (never accepted) and a
-// short list of planes that usually proves a miss.
-struct alignas(32) MoveCell {
+// Cells the hull's tool-side surface passes over carry a region hugging that surface: the cell's
+// footprint x { depth : rlo <= depth - (a + b x0 + c x1) <= rhi } (depth = non-principal coordinate,
+// the plane a + b x0 + c x1 is fitted to the surface over the cell), the hull planes that are not
+// satisfied with margin everywhere in the region, and the front vertices that can be nearest to
+// some point of it.  Other cells: rlo > rhi (never accepted) and a short list of planes that
+// usually proves a miss.
+struct alignas(64) MoveCell {
     int plane_begin, n_planes;    // into mc_pidx
     int vert_begin, n_verts;      // into mc_vc
-    double dlo, dhi;
+    double a, b, c, rlo, rhi;
+    double pad_;
 };
-static_assert(sizeof(MoveCell) == 32, "MoveCell is one 32-byte sector");
+static_assert(sizeof(MoveCell) == 64, "MoveCell is two 32-byte sectors");
 
 // Candidate nearest vertex: position, pack vertex index (tie-break), its incident-triangle
 // records [rec_begin, rec_begin + deg) in `trirec`.
@@ -206,7 +209,7 @@ __device__ __forceinline__ Vec3 tcp_orn_norm(const Vec3 &pose, const double q[4]
     return o;
 }
 
-// Warp max / min of doubles through two 32-bit REDUX steps on an order-preserving key.
+// Warp max of doubles through two 32-bit REDUX steps on an order-preserving key (paint kernel).
 __device__ __forceinline__ unsigned long long ordered_key(double v) {
     long long b = __double_as_longlong(v);
     return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
@@ -223,18 +226,49 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long k)
     return ((unsigned long long)mhi << 32) | mlo;
 }
 __device__ __forceinline__ double warp_max(double v) { return from_ordered_key(warp_max_u64(ordered_key(v))); }
-__device__ __forceinline__ double warp_min(double v) { return from_ordered_key(~warp_max_u64(~ordered_key(v))); }
+
+// ------------------------------------------------------------------------------------------
+// The move phase runs G lanes per environment (G = 8, 16 or 32; 32 / G environments per warp).
+// `Grp` is a lane's view of its group: index within the group, the group's lane mask, its first lane.
+struct Grp { int gl; unsigned mask; int base; };
+
+template <int G>
+__device__ __forceinline__ Grp make_grp(int lane) {
+    Grp g;
+    g.gl = lane & (G - 1);
+    g.base = lane & ~(G - 1);
+    g.mask = (G == 32) ? kFull : (((1u << G) - 1u) << g.base);
+    return g;
+}
+template <int G>
+__device__ __forceinline__ double grp_max(double v, const Grp &g) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(g.mask, v, o));
+    return v;
+}
+template <int G>
+__device__ __forceinline__ double grp_min(double v, const Grp &g) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(g.mask, v, o));
+    return v;
+}
+template <int G>
+__device__ __forceinline__ int grp_sum(int v, const Grp &g) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
+    return v;
+}
 
 // One pass of the slab test over a list of planes (all of them, or one cell's list), split
-// across the warp; max/min are order-independent so the result equals the serial one.
+// across the group; max/min are order-independent so the result equals the serial one.
 struct SlabResult { double t_in, t_out; bool outside; };
 
-template <bool INDEXED>
+template <int G, bool INDEXED>
 __device__ __forceinline__ SlabResult slab_pass(const DevPack &pk, const Vec3 &frm, double d0, double d1, double d2,
-                                                int begin, int end, int lane) {
+                                                int begin, int end, const Grp &g) {
     double t_in = -INFINITY, t_out = INFINITY;
     bool outside = false;
-    for (int i = begin + lane; i < end; i += 32) {
+    for (int i = begin + g.gl; i < end; i += G) {
         int pi = INDEXED ? (int)__ldg(&pk.mc_pidx[i]) : i;
         const double2 *p2 = reinterpret_cast<const double2 *>(pk.planes) + 2 * pi;
         double2 lo = __ldg(p2), hi2 = __ldg(p2 + 1);
@@ -249,30 +283,55 @@ __device__ __forceinline__ SlabResult slab_pass(const DevPack &pk, const Vec3 &f
         }
     }
     SlabResult r;
-    r.t_in = warp_max(t_in);
-    r.t_out = warp_min(t_out);
-    r.outside = __any_sync(kFull, outside);
+    r.t_in = grp_max<G>(t_in, g);
+    r.t_out = grp_min<G>(t_out, g);
+    r.outside = __any_sync(g.mask, outside);
     return r;
+}
+
+// Number of listed planes the point h does not satisfy with margin (n.h - off > -kVerifyMargin).
+// The value per plane does not depend on the list it is reached through, so equal counts over the
+// full plane table and over a sub-list mean that every plane outside the sub-list is satisfied
+// with margin.
+constexpr double kVerifyMargin = 1e-9;
+template <int G, bool INDEXED>
+__device__ __forceinline__ int near_violations(const DevPack &pk, const Vec3 &h, int begin, int end, const Grp &g) {
+    int c = 0;
+    for (int i = begin + g.gl; i < end; i += G) {
+        int pi = INDEXED ? (int)__ldg(&pk.mc_pidx[i]) : i;
+        const double2 *p2 = reinterpret_cast<const double2 *>(pk.planes) + 2 * pi;
+        double2 lo = __ldg(p2), hi2 = __ldg(p2 + 1);
+        double sd = fma(hi2.x, h.z, fma(lo.y, h.y, lo.x * h.x)) - hi2.y;
+        c += (sd > -kVerifyMargin) ? 1 : 0;
+    }
+    return grp_sum<G>(c, g);
 }
 
 // Exact slab test of the ray frm -> to against the hull half-spaces (shim S1).
 //
 // For any subset S of the planes t_in(S) <= t_in and t_out(S) >= t_out, so
 //   (1) a miss is proven by S alone when outside(S), t_in(S) > t_out(S), t_in(S) > 1 or t_out(S) < 0;
-//   (2) if the entry point h* = frm + d t_in(S) of a move cell's list lies in that cell's box, every
-//       unlisted plane j satisfies n_j.h* < off_j - margin, i.e. t_j < t* if it is an entering plane
-//       and t_j > t* if it is an exiting one: t* is the global t_in bit for bit and the hit / miss
-//       decision over S equals the one over all planes.
+//   (2) if every plane outside S is satisfied with margin at the entry point h* = frm + d t_in(S),
+//       i.e. n_j.h* < off_j - margin, then t_j < t* for an entering plane j and t_j > t* for an
+//       exiting one: t* is the global t_in bit for bit and the hit / miss decision over S equals the
+//       one over all planes.  This holds by construction when S is a move cell's list and h* lies in
+//       that cell's region (2a), and otherwise it is checked directly with one division-free pass
+//       over the plane table (2b).
 // Otherwise the full plane list is scanned.  Either way the result is the serial slab test's.
-// On an accepted hit `cell` is the move cell holding the hit point (for the vertex candidates), else -1.
-__device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, const Vec3 &to, int lane, Vec3 &hit,
+// On a hit accepted through (2a) `cell` is the move cell holding the hit point (for the vertex
+// candidates), else -1.
+template <int G>
+__device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, const Vec3 &to, const Grp &grp, Vec3 &hit,
                                          int &cell_out, int &full_scans) {
     double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
     SlabResult r;
-    bool accepted = false;
+    bool accepted = false, candidate = false;
+    int sb = 0, se = 0;
     cell_out = -1;
+    const int npax = 3 - pk.axis0 - pk.axis1;
     // the TCP hovers kHookDistance above the surface: first guess = the point that far along the ray
     Vec3 g = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
+    Vec3 h = g;
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
         int cx = (int)floor((comp(g, pk.axis0) - pk.mc_o0) * pk.mc_inv);
@@ -281,23 +340,33 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, con
         const int cell = cy * pk.mc_nx + cx;
         const int4 hdr = __ldg(reinterpret_cast<const int4 *>(&pk.mc[cell]));
         if (hdr.y <= 0) break;
-        r = slab_pass<true>(pk, frm, d0, d1, d2, hdr.x, hdr.x + hdr.y, lane);
+        r = slab_pass<G, true>(pk, frm, d0, d1, d2, hdr.x, hdr.x + hdr.y, grp);
         if (r.outside || r.t_in > r.t_out || r.t_in > 1.0 || r.t_out < 0.0) return false;   // (1)
+        candidate = false;
         if (!(r.t_in > -INFINITY)) break;
-        Vec3 h = {frm.x + d0 * r.t_in, frm.y + d1 * r.t_in, frm.z + d2 * r.t_in};
-        int hx = (int)floor((comp(h, pk.axis0) - pk.mc_o0) * pk.mc_inv);
-        int hy = (int)floor((comp(h, pk.axis1) - pk.mc_o1) * pk.mc_inv);
-        double depth = comp(h, 3 - pk.axis0 - pk.axis1);
-        const double2 dr = __ldg(reinterpret_cast<const double2 *>(&pk.mc[cell]) + 1);
-        if (hx == cx && hy == cy && depth >= dr.x && depth <= dr.y) {                       // (2)
+        candidate = true;
+        sb = hdr.x; se = hdr.x + hdr.y;
+        h.x = frm.x + d0 * r.t_in; h.y = frm.y + d1 * r.t_in; h.z = frm.z + d2 * r.t_in;
+        const double h0 = comp(h, pk.axis0), h1 = comp(h, pk.axis1);
+        int hx = (int)floor((h0 - pk.mc_o0) * pk.mc_inv);
+        int hy = (int)floor((h1 - pk.mc_o1) * pk.mc_inv);
+        const double2 *cd = reinterpret_cast<const double2 *>(&pk.mc[cell]);
+        const double2 ab = __ldg(cd + 1), cl = __ldg(cd + 2), hp = __ldg(cd + 3);   // (a, b) (c, rlo) (rhi, -)
+        const double resid = comp(h, npax) - (ab.x + ab.y * h0 + cl.x * h1);
+        if (hx == cx && hy == cy && resid >= cl.y && resid <= hp.x) {                      // (2a)
             accepted = true;
             cell_out = cell;
             break;
         }
         g = h;
     }
+    if (!accepted && candidate) {                                                           // (2b)
+        const int c_all = near_violations<G, false>(pk, h, 0, pk.n_planes, grp);
+        const int c_sub = near_violations<G, true>(pk, h, sb, se, grp);
+        accepted = (c_all == c_sub);
+    }
     if (!accepted) {
-        r = slab_pass<false>(pk, frm, d0, d1, d2, 0, pk.n_planes, lane);
+        r = slab_pass<G, false>(pk, frm, d0, d1, d2, 0, pk.n_planes, grp);
         full_scans += 1;
     }
     if (r.outside || !(r.t_in <= r.t_out && 0.0 <= r.t_in && r.t_in <= 1.0)) return false;
@@ -307,62 +376,67 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, con
     return true;
 }
 
+// Lexicographic arg-min of (squared distance, vertex id) over the group; `rec` travels with it.
+template <int G>
+__device__ __forceinline__ void grp_argmin(double &d, unsigned &id, unsigned &rec, const Grp &g) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(g.mask, d, o);
+        const unsigned oi = __shfl_xor_sync(g.mask, id, o), orc = __shfl_xor_sync(g.mask, rec, o);
+        if (od < d || (od == d && oi < id)) { d = od; id = oi; rec = orc; }
+    }
+}
+
 // cKDTree.query(point, k=1) over the side-masked vertices (bullet_paint_wrapper.py:526): exact
 // FP64 squared distances, lowest pack index on ties.  Returns the vertex's record word
 // (rec_begin << 8 | deg), or 0xFFFFFFFF if there is none.
 //
 // Fast path: the move cell that holds the point lists every vertex that can be nearest to a
-// point of its box, so the arg-min over that list is the arg-min over all vertices.
-__device__ __forceinline__ unsigned nearest_vertex_cell(const DevPack &pk, const Vec3 &p, int cell, int lane) {
+// point of its region, so the arg-min over that list is the arg-min over all vertices.
+template <int G>
+__device__ __forceinline__ unsigned nearest_vertex_cell(const DevPack &pk, const Vec3 &p, int cell, const Grp &g) {
     const int4 hdr = __ldg(reinterpret_cast<const int4 *>(&pk.mc[cell]));
-    unsigned long long best = ~0ull;   // ordered (d2 bits) -- d2 >= 0 so the raw bits order correctly
+    double best = INFINITY;
     unsigned bid = 0xFFFFFFFFu, brec = 0xFFFFFFFFu;
-    for (int i = lane; i < hdr.w; i += 32) {
+    for (int i = g.gl; i < hdr.w; i += G) {
         const double2 *c = reinterpret_cast<const double2 *>(&pk.mc_vc[hdr.z + i]);
         double2 xy = __ldg(c), zr = __ldg(c + 1);
         double dx = xy.x - p.x, dy = xy.y - p.y, dz = zr.x - p.z;
         double d = dx * dx + dy * dy + dz * dz;
-        unsigned long long key = (unsigned long long)__double_as_longlong(d);
         unsigned long long meta = (unsigned long long)__double_as_longlong(zr.y);
         unsigned id = (unsigned)meta, rec = (unsigned)(meta >> 32);
-        if (key < best || (key == best && id < bid)) { best = key; bid = id; brec = rec; }
+        if (d < best || (d == best && id < bid)) { best = d; bid = id; brec = rec; }
     }
-    unsigned long long m = ~warp_max_u64(~best);
-    unsigned wid = __reduce_min_sync(kFull, best == m ? bid : 0xFFFFFFFFu);
-    unsigned src = __ffs(__ballot_sync(kFull, best == m && bid == wid)) - 1;
-    return __shfl_sync(kFull, brec, src);
+    grp_argmin<G>(best, bid, brec, g);
+    return brec;
 }
 
-// Slow path (point outside every accepted cell box): grid search over (axis0, axis1) with ring expansion.
-__device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const Vec3 &p, int lane) {
+// Slow path (point outside every accepted cell region): grid search over (axis0, axis1) with ring expansion.
+template <int G>
+__device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const Vec3 &p, const Grp &g) {
     double q0 = comp(p, pk.axis0), q1 = comp(p, pk.axis1);
     int cx = (int)floor((q0 - pk.vg_o0) * pk.vg_inv);
     int cy = (int)floor((q1 - pk.vg_o1) * pk.vg_inv);
     cx = min(max(cx, 0), pk.vg_nx - 1);
     cy = min(max(cy, 0), pk.vg_ny - 1);
     double best_d = INFINITY;
-    int best_i = 0x7fffffff;
+    unsigned best_i = 0xFFFFFFFFu;
     for (int k = 1;; ++k) {
         int x0 = max(cx - k, 0), x1 = min(cx + k, pk.vg_nx - 1);
         int y0 = max(cy - k, 0), y1 = min(cy + k, pk.vg_ny - 1);
         double bd = INFINITY;
-        int bi = 0x7fffffff;
+        unsigned bi = 0xFFFFFFFFu, dummy = 0;
         for (int row = y0; row <= y1; ++row) {
             int begin = __ldg(&pk.vg_start[row * pk.vg_nx + x0]);
             int end = __ldg(&pk.vg_start[row * pk.vg_nx + x1 + 1]);
-            for (int j = begin + lane; j < end; j += 32) {
+            for (int j = begin + g.gl; j < end; j += G) {
                 double dx = __ldg(&pk.vx[j]) - p.x, dy = __ldg(&pk.vy[j]) - p.y, dz = __ldg(&pk.vz[j]) - p.z;
                 double d = dx * dx + dy * dy + dz * dz;
-                int id = __ldg(&pk.vid[j]);
+                unsigned id = (unsigned)__ldg(&pk.vid[j]);
                 if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double od = __shfl_xor_sync(kFull, bd, o);
-            int oi = __shfl_xor_sync(kFull, bi, o);
-            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-        }
+        grp_argmin<G>(bd, bi, dummy, g);
         best_d = bd;
         best_i = bi;
         bool whole = (x0 == 0 && y0 == 0 && x1 == pk.vg_nx - 1 && y1 == pk.vg_ny - 1);
@@ -376,24 +450,25 @@ __device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const
         m -= 1e-9;
         if (m > 0.0 && best_d < m * m) break;
     }
-    if (best_i == 0x7fffffff) return 0xFFFFFFFFu;
+    if (best_i == 0xFFFFFFFFu) return 0xFFFFFFFFu;
     return __ldg(&pk.vrec[best_i]);
 }
 
 // Part._get_hook_point + _get_closest_bary (bullet_paint_wrapper.py:525-534, 508-523, 154-185):
-// incident front triangles of the nearest vertex, one per lane.  Returns the picked triangle's
-// record (whose tail holds n, quat_from_normal(-n) and the shot-centre offset), or nullptr.
-__device__ __forceinline__ const double *hook_triangle(const DevPack &pk, const Vec3 &point, int cell, int lane) {
-    unsigned rec = cell >= 0 ? nearest_vertex_cell(pk, point, cell, lane) : nearest_vertex_grid(pk, point, lane);
+// incident front triangles of the nearest vertex, one per lane of the group.  Returns the picked
+// triangle's record (whose tail holds n, quat_from_normal(-n) and the shot-centre offset), or nullptr.
+template <int G>
+__device__ __forceinline__ const double *hook_triangle(const DevPack &pk, const Vec3 &point, int cell, const Grp &g) {
+    unsigned rec = cell >= 0 ? nearest_vertex_cell<G>(pk, point, cell, g) : nearest_vertex_grid<G>(pk, point, g);
     if (rec == 0xFFFFFFFFu) return nullptr;
     const int deg = (int)(rec & 0xffu);
     const double *base = pk.trirec + (size_t)(rec >> 8) * kTriRec;
     if (deg <= 0) return nullptr;
     int pick = -1;
-    double run_max = -INFINITY;   // max of min_uvw over the lanes scanned so far
+    double run_max = -INFINITY;   // max of min_uvw over the triangles scanned so far
     int run_arg = -1;             // last list position attaining it
-    for (int b0 = 0; b0 < deg; b0 += 32) {
-        int k = b0 + lane;
+    for (int b0 = 0; b0 < deg; b0 += G) {
+        int k = b0 + g.gl;
         bool inside = false;
         double m = -INFINITY;
         if (k < deg) {
@@ -412,11 +487,11 @@ __device__ __forceinline__ const double *hook_triangle(const DevPack &pk, const 
             inside = (0.0 <= bu && bu <= 1.0 && 0.0 <= bv && bv <= 1.0 && 0.0 <= bw && bw <= 1.0);
             m = fmin(fmin(bu, bv), bw);
         }
-        unsigned in_mask = __ballot_sync(kFull, inside);
+        unsigned in_mask = (__ballot_sync(g.mask, inside) & g.mask) >> g.base;
         if (in_mask) { pick = b0 + __ffs(in_mask) - 1; break; }
-        double cm = warp_max(m);
+        double cm = grp_max<G>(m, g);
         if (cm >= run_max) {   // `>=`: a later triangle wins ties (bullet_paint_wrapper.py:520)
-            unsigned eq = __ballot_sync(kFull, k < deg && m == cm);
+            unsigned eq = (__ballot_sync(g.mask, k < deg && m == cm) & g.mask) >> g.base;
             run_max = cm;
             run_arg = b0 + 31 - __clz(eq);
         }

@@ -554,11 +554,14 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16
 
 // ------------------------------------------------------------------------------ kernels
 // Robot._get_actions (robot.py:302-329): action -> direction, five guided sub-steps.
+// G lanes per environment (the plane / vertex / triangle lists of a sub-step are short).
+template <int G>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *actions) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int env = blockIdx.x * kWarpsPerBlock + warp;
+    const int lane = threadIdx.x & 31;
+    const int env = (blockIdx.x * (kWarpsPerBlock * 32) + threadIdx.x) / G;
     if (env >= num_envs) return;
+    const Grp grp = make_grp<G>(lane);
     EnvState st;
     load_state(&ea.states[env], st);
 
@@ -612,7 +615,7 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
         Vec3 hit, pos, center;
         int cell;
         const double *rec = nullptr;
-        if (ray_test(pk, p, end, lane, hit, cell, full_scans)) rec = hook_triangle(pk, hit, cell, lane);
+        if (ray_test<G>(pk, p, end, grp, hit, cell, full_scans)) rec = hook_triangle<G>(pk, hit, cell, grp);
         if (rec) {
             // pose = hit + 0.1 n, orn = -n (bullet_paint_wrapper.py:529-530); quaternion and shot-centre
             // offset of -n come from the record (computed by the host with these same operations)
@@ -639,16 +642,16 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
                 if (st.term_counter > kNotOnPartTerminateSteps) st.flags |= kFlagTerminate;
             }
         }
-        if (lane == 0) { centers[3 * s] = center.x; centers[3 * s + 1] = center.y; centers[3 * s + 2] = center.z; }
+        if (grp.gl == 0) { centers[3 * s] = center.x; centers[3 * s + 1] = center.y; centers[3 * s + 2] = center.z; }
         cur_p = pos;
     }
     st.pose[0] = cur_p.x; st.pose[1] = cur_p.y; st.pose[2] = cur_p.z;
     st.quat[0] = quat[0]; st.quat[1] = quat[1]; st.quat[2] = quat[2]; st.quat[3] = quat[3];
-    if (lane == 0) {
+    if (grp.gl == 0) {
         ea.moves[env].offpart_added = st.term_counter - counter_before;
         ea.moves[env].full_scans = full_scans;
     }
-    store_state(&ea.states[env], st, lane);
+    store_state(&ea.states[env], st, grp.gl);
 }
 
 // Everything after the move: stamp, score, observe, auto-reset.  The environment's record, the
