@@ -40,7 +40,8 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + SOURCES + ['-o', LIB]
+    extra = ['-DPAINTRL_PROFILE'] if os.environ.get('PAINTRL_PROFILE') else []   # phase timing build (profiles/)
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + SOURCES + ['-o', LIB]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)

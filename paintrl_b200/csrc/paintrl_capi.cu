@@ -79,6 +79,7 @@ struct PaintrlEngine {
     unsigned long long launches = 0;
     double move_cell_planes_mean = 0.0, move_cell_verts_mean = 0.0;
     int move_lanes = 32;             // lanes per environment in move_kernel (8, 16 or 32)
+    int move_minb = 7;               // its __launch_bounds__ min blocks per SM (7: 72 registers, 4: 128)
 };
 
 namespace {
@@ -125,11 +126,13 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
     const double cs = kPaintRadius / 4, pad = 0.15;
     const double o0 = pack->range0_min - pad, o1 = pack->range1_min - pad;
     int nx = (int)std::ceil((pack->range0_max + pad - o0) / cs), ny = (int)std::ceil((pack->range1_max + pad - o1) / cs);
-    std::vector<MoveCell> cells;
-    std::vector<uint16_t> pidx;
-    std::vector<VertCand> vcs;
-    if (pack->n_planes >= 65535 || nx <= 0 || ny <= 0 || (long long)nx * ny > (1 << 21)) nx = ny = 0;   // fast path off
-    cells.resize((size_t)nx * ny);
+    std::vector<uint2> entries;
+    std::vector<double> blob;         // 4 doubles per 32-byte sector
+    if (nx <= 0 || ny <= 0 || (long long)nx * ny > (1 << 21)) nx = ny = 0;   // fast path off
+    entries.resize((size_t)nx * ny);
+    std::vector<int> pidx;            // the current cell's plane indices
+    std::vector<VertCand> vcs;        // the current cell's vertex candidates
+    size_t plane_refs = 0;
     const double kPadBelow = 5e-4, kPadAbove = 1e-4, kFootSlack = 1e-6, kMargin = 1e-9, kVertSlack = 1e-9;
     const int K = 5;
     // the tool hovers on the side the start normals point away from and looks along them
@@ -146,13 +149,9 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
     std::vector<int> tmp;
     for (int cy = 0; cy < ny; ++cy) {
         for (int cx = 0; cx < nx; ++cx) {
-            MoveCell &mc = cells[(size_t)cy * nx + cx];
-            mc.plane_begin = (int)pidx.size();
-            mc.vert_begin = (int)vcs.size();
-            mc.n_planes = mc.n_verts = 0;
-            mc.a = mc.b = mc.c = 0.0;
-            mc.rlo = 1.0; mc.rhi = -1.0;
-            mc.pad_ = 0.0;
+            struct { double a, b, c, rlo, rhi; int n_planes, n_verts; } mc = {0.0, 0.0, 0.0, 1.0, -1.0, 0, 0};
+            pidx.clear();
+            vcs.clear();
             const double lo0 = o0 + cx * cs, hi0 = o0 + (cx + 1) * cs, lo1 = o1 + cy * cs, hi1 = o1 + (cy + 1) * cs;
             const double mid0 = 0.5 * (lo0 + hi0), mid1 = 0.5 * (lo1 + hi1);
             // sample the hull's tool-side surface over the footprint
@@ -218,9 +217,9 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
                     double worst = -INFINITY;
                     for (int c = 0; c < 8; ++c)
                         worst = std::max(worst, n[0] * corner[c][0] + n[1] * corner[c][1] + n[2] * corner[c][2]);
-                    if (worst > pack->plane_off[p] - kMargin) pidx.push_back((uint16_t)p);
+                    if (worst > pack->plane_off[p] - kMargin) pidx.push_back(p);
                 }
-                mc.n_planes = (int)pidx.size() - mc.plane_begin;
+                mc.n_planes = (int)pidx.size();
                 // candidates for the nearest front vertex of any point of the region (its bounding box)
                 double blo[3], bhi[3];
                 blo[a0] = lo0 - kFootSlack; bhi[a0] = hi0 + kFootSlack;
@@ -251,7 +250,7 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
                         vcs.push_back(vc);
                     }
                 }
-                mc.n_verts = (int)vcs.size() - mc.vert_begin;
+                mc.n_verts = (int)vcs.size();
                 planes_total += mc.n_planes;
                 verts_total += mc.n_verts;
                 ++inside_cells;
@@ -277,21 +276,44 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
                 }
                 std::sort(tmp.begin(), tmp.end());
                 tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-                for (int p : tmp) pidx.push_back((uint16_t)p);
+                for (int p : tmp) pidx.push_back(p);
                 mc.n_planes = (int)tmp.size();
             }
+            // ---- the cell's blob: region, copies of its planes, its vertex candidates
+            if (mc.n_planes > 0xffff || mc.n_verts > 0xffff || blob.size() / 4 > 0xfffffff0u)
+                return fail(PAINTRL_E_INVALID, "move cell list too long");
+            uint2 &en = entries[(size_t)cy * nx + cx];
+            en.x = (unsigned)(blob.size() / 4);
+            en.y = (unsigned)mc.n_planes | ((unsigned)mc.n_verts << 16);
+            const double hdr[8] = {mc.a, mc.b, mc.c, mc.rlo, mc.rhi, 0.0, 0.0, 0.0};
+            blob.insert(blob.end(), hdr, hdr + 8);
+            for (int p : pidx) {
+                const double pl[4] = {pack->plane_n[3 * p], pack->plane_n[3 * p + 1], pack->plane_n[3 * p + 2], pack->plane_off[p]};
+                blob.insert(blob.end(), pl, pl + 4);
+            }
+            for (const VertCand &vc : vcs) {
+                double v[4] = {vc.x, vc.y, vc.z, 0.0};
+                const unsigned long long meta = (unsigned long long)vc.id | ((unsigned long long)vc.rec << 32);
+                std::memcpy(&v[3], &meta, 8);
+                blob.insert(blob.end(), v, v + 4);
+            }
+            plane_refs += pidx.size();
         }
     }
+    blob.resize(blob.size() + 4 * 64, 0.0);   // lanes may read one round of sectors past a short list
     pk.mc_nx = nx; pk.mc_ny = ny;
     pk.mc_o0 = o0; pk.mc_o1 = o1; pk.mc_inv = 1.0 / cs;
-    CUDA_TRY(e->arena.upload(cells, &pk.mc));
-    CUDA_TRY(e->arena.upload(pidx, &pk.mc_pidx));
-    CUDA_TRY(e->arena.upload(vcs, &pk.mc_vc));
+    CUDA_TRY(e->arena.upload(entries, &pk.mc_entry));
+    {
+        const double *dev = nullptr;
+        CUDA_TRY(e->arena.upload(blob, &dev));
+        pk.mc_blob = reinterpret_cast<const double2 *>(dev);
+    }
     e->move_cell_planes_mean = inside_cells ? (double)planes_total / inside_cells : 0.0;
     e->move_cell_verts_mean = inside_cells ? (double)verts_total / inside_cells : 0.0;
     if (getenv("PAINTRL_DEBUG"))
-        fprintf(stderr, "[paintrl] move cells %d x %d, %zu with a surface region: %.2f planes, %.2f vertex candidates per cell; %zu plane refs\n",
-                nx, ny, inside_cells, e->move_cell_planes_mean, e->move_cell_verts_mean, pidx.size());
+        fprintf(stderr, "[paintrl] move cells %d x %d, %zu with a surface region: %.2f planes, %.2f vertex candidates per cell; %zu plane refs, blobs %.1f MB\n",
+                nx, ny, inside_cells, e->move_cell_planes_mean, e->move_cell_verts_mean, plane_refs, blob.size() * 8 / 1e6);
     return PAINTRL_OK;
 }
 
@@ -612,6 +634,22 @@ extern "C" {
 int32_t paintrl_abi_version(void) { return PAINTRL_ABI_VERSION; }
 const char *paintrl_last_error(void) { return g_error.c_str(); }
 
+/* Debug only (not in paintrl.h): phase cycle counters of a -DPAINTRL_PROFILE build; returns 0 slots otherwise. */
+int paintrl_debug_profile(unsigned long long *out64, int reset) {
+#ifdef PAINTRL_PROFILE
+    cudaDeviceSynchronize();
+    if (out64) cudaMemcpyFromSymbol(out64, g_prof, 64 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[64] = {0};
+        cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+    }
+    return 64;
+#else
+    (void)out64; (void)reset;
+    return 0;
+#endif
+}
+
 int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_t num_envs, int32_t device,
                    PaintrlHandle *out) {
     if (!pack || !cfg || !out) return fail(PAINTRL_E_INVALID, "null argument");
@@ -707,6 +745,8 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
         const char *ml = getenv("PAINTRL_MOVE_LANES");
         int lanes = ml ? atoi(ml) : 8;
         e->move_lanes = (lanes == 16 || lanes == 32) ? lanes : 8;
+        const char *mb = getenv("PAINTRL_MOVE_MINB");
+        e->move_minb = (mb && atoi(mb) == 4) ? 4 : 7;
     }
     *out = e;
     return PAINTRL_OK;
@@ -764,12 +804,15 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     {   // lanes per environment in the move phase: fewer when there are enough environments to fill the GPU
         const int threads = kWarpsPerBlock * 32;
         cudaStream_t ms = as_stream(stream);
-        if (h->move_lanes == 8)
-            move_kernel<8><<<(h->num_envs * 8 + threads - 1) / threads, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
-        else if (h->move_lanes == 16)
-            move_kernel<16><<<(h->num_envs * 16 + threads - 1) / threads, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
-        else
-            move_kernel<32><<<blocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
+        const int L = h->move_lanes;
+        const int mblocks = (int)(((long long)h->num_envs * L + threads - 1) / threads);
+#define PAINTRL_MOVE(G, MINB) move_kernel<G, MINB><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev)
+        if (h->move_minb == 7) {
+            if (L == 8) PAINTRL_MOVE(8, 7); else if (L == 16) PAINTRL_MOVE(16, 7); else PAINTRL_MOVE(32, 7);
+        } else {
+            if (L == 8) PAINTRL_MOVE(8, 4); else if (L == 16) PAINTRL_MOVE(16, 4); else PAINTRL_MOVE(32, 4);
+        }
+#undef PAINTRL_MOVE
     }
     int rc = launch_check(h, "move_kernel");
     if (rc != PAINTRL_OK) return rc;

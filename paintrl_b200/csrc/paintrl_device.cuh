@@ -12,6 +12,26 @@
 
 namespace paintrl {
 
+// Optional phase timing (build with -DPAINTRL_PROFILE; see profiles/README): cycles between
+// PAINTRL_PROF marks, summed over environments into a 64-slot device array.
+#ifdef PAINTRL_PROFILE
+__device__ unsigned long long g_prof[64];
+#define PAINTRL_PROF_BEGIN long long prof_t = clock64();
+#define PAINTRL_PROF(slot, leader)                                                        \
+    do {                                                                                  \
+        long long prof_now = clock64();                                                   \
+        if (leader) atomicAdd(&g_prof[slot], (unsigned long long)(prof_now - prof_t));    \
+        prof_t = prof_now;                                                                \
+    } while (0)
+#define PAINTRL_PROF_PARAM , long long &prof_t
+#define PAINTRL_PROF_PASS , prof_t
+#else
+#define PAINTRL_PROF_BEGIN
+#define PAINTRL_PROF(slot, leader) do {} while (0)
+#define PAINTRL_PROF_PARAM
+#define PAINTRL_PROF_PASS
+#endif
+
 constexpr double kPaintRadius = 0.051;        // bullet_paint_wrapper.py:42
 constexpr double kStepSize = kPaintRadius;    // bullet_paint_wrapper.py:43
 constexpr int kPaintPerAction = 5;            // robot.py:165
@@ -60,20 +80,22 @@ struct alignas(32) EnvStat {
     unsigned long long episodes_ended, footprint_texels, full_scans, env_steps;
 };
 
-// One cell of the move grid over (axis0, axis1) (see build_move_cells in paintrl_capi.cu).
+// Move grid over (axis0, axis1) (see build_move_cells in paintrl_capi.cu).  Every cell has an 8-byte
+// entry (blob offset in 32-byte sectors, list lengths) and a contiguous blob
+//   sector 0: a, b, c, rlo      sector 1: rhi, -, -, -
+//   sectors 2 .. 2 + n_planes:  hull planes (nx, ny, nz, off), copied from the plane table
+//   then n_verts sectors:       candidate nearest vertices (x, y, z, id | rec << 32)
+// so that one table lookup is followed by one round of independent loads.
 // Cells the hull's tool-side surface passes over carry a region hugging that surface: the cell's
 // footprint x { depth : rlo <= depth - (a + b x0 + c x1) <= rhi } (depth = non-principal coordinate,
 // the plane a + b x0 + c x1 is fitted to the surface over the cell), the hull planes that are not
 // satisfied with margin everywhere in the region, and the front vertices that can be nearest to
-// some point of it.  Other cells: rlo > rhi (never accepted) and a short list of planes that
-// usually proves a miss.
-struct alignas(64) MoveCell {
-    int plane_begin, n_planes;    // into mc_pidx
-    int vert_begin, n_verts;      // into mc_vc
-    double a, b, c, rlo, rhi;
-    double pad_;
+// some point of it.  Other cells: rlo > rhi (never accepted), a short list of planes that usually
+// proves a miss, no vertices.
+struct CellRef {
+    const double2 *blob;   // nullptr: none
+    int n_planes, n_verts;
 };
-static_assert(sizeof(MoveCell) == 64, "MoveCell is two 32-byte sectors");
 
 // Candidate nearest vertex: position, pack vertex index (tie-break), its incident-triangle
 // records [rec_begin, rec_begin + deg) in `trirec`.
@@ -99,9 +121,8 @@ struct DevPack {
     // move grid
     int mc_nx, mc_ny;
     double mc_o0, mc_o1, mc_inv;
-    const MoveCell *mc;
-    const uint16_t *mc_pidx;
-    const VertCand *mc_vc;
+    const uint2 *mc_entry;        // [mc_nx * mc_ny] x = blob sector offset, y = n_planes | n_verts << 16
+    const double2 *mc_blob;       // 32-byte sectors (two double2 each)
     const double *trirec;         // [n_rec][kTriRec]
     // slow-path nearest-vertex grid over (axis0, axis1): front vertices sorted by cell
     int vg_nx, vg_ny;
@@ -259,19 +280,18 @@ __device__ __forceinline__ int grp_sum(int v, const Grp &g) {
     return v;
 }
 
-// One pass of the slab test over a list of planes (all of them, or one cell's list), split
-// across the group; max/min are order-independent so the result equals the serial one.
+// One pass of the slab test over a list of planes (`planes` = two double2 per plane: the plane table
+// or a cell blob's copy of some of its entries), split across the group; max/min are
+// order-independent so the result equals the serial one.
 struct SlabResult { double t_in, t_out; bool outside; };
 
-template <int G, bool INDEXED>
-__device__ __forceinline__ SlabResult slab_pass(const DevPack &pk, const Vec3 &frm, double d0, double d1, double d2,
-                                                int begin, int end, const Grp &g) {
+template <int G>
+__device__ __forceinline__ SlabResult slab_pass(const double2 *planes, int n, const Vec3 &frm, double d0, double d1, double d2,
+                                                const Grp &g) {
     double t_in = -INFINITY, t_out = INFINITY;
     bool outside = false;
-    for (int i = begin + g.gl; i < end; i += G) {
-        int pi = INDEXED ? (int)__ldg(&pk.mc_pidx[i]) : i;
-        const double2 *p2 = reinterpret_cast<const double2 *>(pk.planes) + 2 * pi;
-        double2 lo = __ldg(p2), hi2 = __ldg(p2 + 1);
+    for (int i = g.gl; i < n; i += G) {
+        const double2 lo = __ldg(planes + 2 * i), hi2 = __ldg(planes + 2 * i + 1);
         double den = (lo.x * d0 + lo.y * d1) + hi2.x * d2;
         double num = hi2.y - ((lo.x * frm.x + lo.y * frm.y) + hi2.x * frm.z);
         if (den == 0.0) {
@@ -290,22 +310,22 @@ __device__ __forceinline__ SlabResult slab_pass(const DevPack &pk, const Vec3 &f
 }
 
 // Number of listed planes the point h does not satisfy with margin (n.h - off > -kVerifyMargin).
-// The value per plane does not depend on the list it is reached through, so equal counts over the
-// full plane table and over a sub-list mean that every plane outside the sub-list is satisfied
-// with margin.
+// The value per plane depends only on the plane's four doubles, so equal counts over the full
+// plane table and over a list of copies of some of its entries mean that every plane outside the
+// list is satisfied with margin.
 constexpr double kVerifyMargin = 1e-9;
-template <int G, bool INDEXED>
-__device__ __forceinline__ int near_violations(const DevPack &pk, const Vec3 &h, int begin, int end, const Grp &g) {
+template <int G>
+__device__ __forceinline__ int near_violations(const double2 *planes, int n, const Vec3 &h, const Grp &g) {
     int c = 0;
-    for (int i = begin + g.gl; i < end; i += G) {
-        int pi = INDEXED ? (int)__ldg(&pk.mc_pidx[i]) : i;
-        const double2 *p2 = reinterpret_cast<const double2 *>(pk.planes) + 2 * pi;
-        double2 lo = __ldg(p2), hi2 = __ldg(p2 + 1);
+    for (int i = g.gl; i < n; i += G) {
+        const double2 lo = __ldg(planes + 2 * i), hi2 = __ldg(planes + 2 * i + 1);
         double sd = fma(hi2.x, h.z, fma(lo.y, h.y, lo.x * h.x)) - hi2.y;
         c += (sd > -kVerifyMargin) ? 1 : 0;
     }
     return grp_sum<G>(c, g);
 }
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Exact slab test of the ray frm -> to against the hull half-spaces (shim S1).
 //
@@ -318,61 +338,85 @@ __device__ __forceinline__ int near_violations(const DevPack &pk, const Vec3 &h,
 //       that cell's region (2a), and otherwise it is checked directly with one division-free pass
 //       over the plane table (2b).
 // Otherwise the full plane list is scanned.  Either way the result is the serial slab test's.
-// On a hit accepted through (2a) `cell` is the move cell holding the hit point (for the vertex
-// candidates), else -1.
+// On a hit accepted through (2a) `ref` is the move cell holding the hit point (for the vertex
+// candidates; `vc0` / `vc1` hold this lane's first candidate), else ref.blob == nullptr.
+// (pf0, pf1): expected displacement of the next ray along the principal axes -- its cell's blob is
+// prefetched into L1 while this ray is being tested (do_prefetch).
 template <int G>
 __device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, const Vec3 &to, const Grp &grp, Vec3 &hit,
-                                         int &cell_out, int &full_scans) {
+                                         CellRef &ref, double2 &vc0, double2 &vc1, int &full_scans, double pf0, double pf1,
+                                         bool do_prefetch PAINTRL_PROF_PARAM) {
     double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
     SlabResult r;
     bool accepted = false, candidate = false;
-    int sb = 0, se = 0;
-    cell_out = -1;
+    const double2 *sub = nullptr;
+    int n_sub = 0;
+    ref.blob = nullptr;
     const int npax = 3 - pk.axis0 - pk.axis1;
     // the TCP hovers kHookDistance above the surface: first guess = the point that far along the ray
     Vec3 g = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
     Vec3 h = g;
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; ++attempt) {
-        int cx = (int)floor((comp(g, pk.axis0) - pk.mc_o0) * pk.mc_inv);
-        int cy = (int)floor((comp(g, pk.axis1) - pk.mc_o1) * pk.mc_inv);
+        const double g0 = comp(g, pk.axis0), g1 = comp(g, pk.axis1);
+        int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
+        int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
         if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) break;
-        const int cell = cy * pk.mc_nx + cx;
-        const int4 hdr = __ldg(reinterpret_cast<const int4 *>(&pk.mc[cell]));
-        if (hdr.y <= 0) break;
-        r = slab_pass<G, true>(pk, frm, d0, d1, d2, hdr.x, hdr.x + hdr.y, grp);
+        const uint2 entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+        const int n_planes = (int)(entry.y & 0xffffu), n_verts = (int)(entry.y >> 16);
+        if (n_planes <= 0) break;
+        const double2 *blob = pk.mc_blob + (size_t)entry.x * 2;
+        // one round of independent loads: region, this lane's plane(s) (in slab_pass), first vertex candidate
+        const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);   // (a, b) (c, rlo) (rhi, -)
+        if (grp.gl < n_verts) {
+            vc0 = __ldg(blob + 2 * (2 + n_planes + grp.gl));
+            vc1 = __ldg(blob + 2 * (2 + n_planes + grp.gl) + 1);
+        }
+        if (do_prefetch && attempt == 0) {
+            int px = (int)floor((g0 + pf0 - pk.mc_o0) * pk.mc_inv);
+            int py = (int)floor((g1 + pf1 - pk.mc_o1) * pk.mc_inv);
+            if (px >= 0 && py >= 0 && px < pk.mc_nx && py < pk.mc_ny && (px != cx || py != cy)) {
+                const uint2 pe = __ldg(&pk.mc_entry[py * pk.mc_nx + px]);
+                const int sectors = 2 + (int)(pe.y & 0xffffu) + (int)(pe.y >> 16);
+                const char *pb = reinterpret_cast<const char *>(pk.mc_blob + (size_t)pe.x * 2);
+                for (int o = grp.gl * 128; o < sectors * 32; o += G * 128) prefetch_l1(pb + o);
+            }
+        }
+        PAINTRL_PROF(6, grp.gl == 0);
+        r = slab_pass<G>(blob + 4, n_planes, frm, d0, d1, d2, grp);
+        PAINTRL_PROF(7, grp.gl == 0);
         if (r.outside || r.t_in > r.t_out || r.t_in > 1.0 || r.t_out < 0.0) return false;   // (1)
         candidate = false;
         if (!(r.t_in > -INFINITY)) break;
         candidate = true;
-        sb = hdr.x; se = hdr.x + hdr.y;
+        sub = blob + 4; n_sub = n_planes;
         h.x = frm.x + d0 * r.t_in; h.y = frm.y + d1 * r.t_in; h.z = frm.z + d2 * r.t_in;
         const double h0 = comp(h, pk.axis0), h1 = comp(h, pk.axis1);
         int hx = (int)floor((h0 - pk.mc_o0) * pk.mc_inv);
         int hy = (int)floor((h1 - pk.mc_o1) * pk.mc_inv);
-        const double2 *cd = reinterpret_cast<const double2 *>(&pk.mc[cell]);
-        const double2 ab = __ldg(cd + 1), cl = __ldg(cd + 2), hp = __ldg(cd + 3);   // (a, b) (c, rlo) (rhi, -)
-        const double resid = comp(h, npax) - (ab.x + ab.y * h0 + cl.x * h1);
-        if (hx == cx && hy == cy && resid >= cl.y && resid <= hp.x) {                      // (2a)
+        const double resid = comp(h, npax) - (abv.x + abv.y * h0 + clv.x * h1);
+        if (hx == cx && hy == cy && resid >= clv.y && resid <= hpv.x) {                     // (2a)
             accepted = true;
-            cell_out = cell;
+            ref.blob = blob; ref.n_planes = n_planes; ref.n_verts = n_verts;
             break;
         }
         g = h;
     }
+    PAINTRL_PROF(8, grp.gl == 0);
     if (!accepted && candidate) {                                                           // (2b)
-        const int c_all = near_violations<G, false>(pk, h, 0, pk.n_planes, grp);
-        const int c_sub = near_violations<G, true>(pk, h, sb, se, grp);
+        const int c_all = near_violations<G>(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, h, grp);
+        const int c_sub = near_violations<G>(sub, n_sub, h, grp);
         accepted = (c_all == c_sub);
     }
     if (!accepted) {
-        r = slab_pass<G, false>(pk, frm, d0, d1, d2, 0, pk.n_planes, grp);
+        r = slab_pass<G>(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, frm, d0, d1, d2, grp);
         full_scans += 1;
     }
     if (r.outside || !(r.t_in <= r.t_out && 0.0 <= r.t_in && r.t_in <= 1.0)) return false;
     hit.x = frm.x + d0 * r.t_in;
     hit.y = frm.y + d1 * r.t_in;
     hit.z = frm.z + d2 * r.t_in;
+    PAINTRL_PROF(9, grp.gl == 0);
     return true;
 }
 
@@ -393,17 +437,17 @@ __device__ __forceinline__ void grp_argmin(double &d, unsigned &id, unsigned &re
 //
 // Fast path: the move cell that holds the point lists every vertex that can be nearest to a
 // point of its region, so the arg-min over that list is the arg-min over all vertices.
+// (vc0, vc1) = this lane's first candidate, loaded by ray_test.
 template <int G>
-__device__ __forceinline__ unsigned nearest_vertex_cell(const DevPack &pk, const Vec3 &p, int cell, const Grp &g) {
-    const int4 hdr = __ldg(reinterpret_cast<const int4 *>(&pk.mc[cell]));
+__device__ __forceinline__ unsigned nearest_vertex_cell(const Vec3 &p, const CellRef &ref, double2 vc0, double2 vc1, const Grp &g) {
     double best = INFINITY;
     unsigned bid = 0xFFFFFFFFu, brec = 0xFFFFFFFFu;
-    for (int i = g.gl; i < hdr.w; i += G) {
-        const double2 *c = reinterpret_cast<const double2 *>(&pk.mc_vc[hdr.z + i]);
-        double2 xy = __ldg(c), zr = __ldg(c + 1);
-        double dx = xy.x - p.x, dy = xy.y - p.y, dz = zr.x - p.z;
+    const double2 *vc = ref.blob + 2 * (2 + ref.n_planes);
+    for (int i = g.gl; i < ref.n_verts; i += G) {
+        if (i >= G) { vc0 = __ldg(vc + 2 * i); vc1 = __ldg(vc + 2 * i + 1); }
+        double dx = vc0.x - p.x, dy = vc0.y - p.y, dz = vc1.x - p.z;
         double d = dx * dx + dy * dy + dz * dz;
-        unsigned long long meta = (unsigned long long)__double_as_longlong(zr.y);
+        unsigned long long meta = (unsigned long long)__double_as_longlong(vc1.y);
         unsigned id = (unsigned)meta, rec = (unsigned)(meta >> 32);
         if (d < best || (d == best && id < bid)) { best = d; bid = id; brec = rec; }
     }
@@ -458,8 +502,10 @@ __device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const
 // incident front triangles of the nearest vertex, one per lane of the group.  Returns the picked
 // triangle's record (whose tail holds n, quat_from_normal(-n) and the shot-centre offset), or nullptr.
 template <int G>
-__device__ __forceinline__ const double *hook_triangle(const DevPack &pk, const Vec3 &point, int cell, const Grp &g) {
-    unsigned rec = cell >= 0 ? nearest_vertex_cell<G>(pk, point, cell, g) : nearest_vertex_grid<G>(pk, point, g);
+__device__ __forceinline__ const double *hook_triangle(const DevPack &pk, const Vec3 &point, const CellRef &ref, double2 vc0,
+                                                       double2 vc1, const Grp &g PAINTRL_PROF_PARAM) {
+    unsigned rec = ref.blob ? nearest_vertex_cell<G>(point, ref, vc0, vc1, g) : nearest_vertex_grid<G>(pk, point, g);
+    PAINTRL_PROF(10, g.gl == 0);
     if (rec == 0xFFFFFFFFu) return nullptr;
     const int deg = (int)(rec & 0xffu);
     const double *base = pk.trirec + (size_t)(rec >> 8) * kTriRec;

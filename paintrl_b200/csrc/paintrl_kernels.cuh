@@ -162,9 +162,11 @@ __device__ __forceinline__ void row_ranks(const DevPack &pk, double p0, int lane
 // 1 if rx<0,ry>0, 2 if rx<0,ry<0, else 3; obs[s] = #(status != 255) / #texels of the sector.
 template <typename WS, typename BITS>
 __device__ __forceinline__ void section4_counts(const DevPack &pk, const BITS &bits, const Vec3 &pose, int lane, WS &ws,
-                                                int tot[4], int open[4]) {
+                                                int tot[4], int open[4] PAINTRL_PROF_PARAM) {
     const double p0 = comp(pose, pk.axis0), p1 = comp(pose, pk.axis1);
+    PAINTRL_PROF(21, lane == 0);
     row_ranks(pk, p0, lane, ws);
+    PAINTRL_PROF(22, lane == 0);
     const double f1 = floor((p1 - pk.row_o1) * pk.row_inv);
     const int prow = !(f1 >= 0.0) ? -1 : (f1 >= (double)pk.n_rows ? pk.n_rows : (int)f1);
     const bool init_painted = (pk.status_init == kPainted);
@@ -196,6 +198,7 @@ __device__ __forceinline__ void section4_counts(const DevPack &pk, const BITS &b
             o3 += __popc(o & ~mL);
         }
     }
+    PAINTRL_PROF(23, lane == 0);
     // ---- the TCP's own row, texel by texel along axis1 (lane = slot)
     if (prow >= 0 && prow < pk.n_rows) {
         const int w0 = __ldg(&pk.row_word0[prow]), w1 = __ldg(&pk.row_word0[prow + 1]);
@@ -215,6 +218,7 @@ __device__ __forceinline__ void section4_counts(const DevPack &pk, const BITS &b
             }
         }
     }
+    PAINTRL_PROF(24, lane == 0);
     tot[0] = __reduce_add_sync(kFull, t0); tot[1] = __reduce_add_sync(kFull, t1);
     tot[2] = __reduce_add_sync(kFull, t2); tot[3] = __reduce_add_sync(kFull, t3);
     open[0] = __reduce_add_sync(kFull, o0); open[1] = __reduce_add_sync(kFull, o1);
@@ -251,7 +255,7 @@ __device__ __forceinline__ void sectionk_counts(const DevPack &pk, const BITS &b
 template <typename WS, typename BITS>
 __device__ __forceinline__ void write_observation(const DevPack &pk, const DevConfig &cfg, const BITS &bits,
                                                   const unsigned *grid_cnt, const Vec3 &pose, int lane, WS &ws,
-                                                  double *obs_a, double *obs_b) {
+                                                  double *obs_a, double *obs_b PAINTRL_PROF_PARAM) {
     double a1, a2;
     normalized_pose(pk, pose, a1, a2);
     const int grad = cfg.obs_grad;
@@ -279,7 +283,7 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const DevCo
     // section / discrete
     if (grad == 4) {
         int tot[4], open[4];
-        section4_counts(pk, bits, pose, lane, ws, tot, open);
+        section4_counts(pk, bits, pose, lane, ws, tot, open PAINTRL_PROF_PASS);
         if (lane < 4) {
             int t = lane == 0 ? tot[0] : (lane == 1 ? tot[1] : (lane == 2 ? tot[2] : tot[3]));
             int o = lane == 0 ? open[0] : (lane == 1 ? open[1] : (lane == 2 ? open[2] : open[3]));
@@ -462,7 +466,7 @@ __device__ __forceinline__ void for_each_stamp_word(const DevPack &pk, int lane,
 // |union of valid pixels| of robot.py:425 and whether any flip bit changed.
 template <int COLOR, typename WS, typename BITS>
 __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16_t *thick, unsigned *grid_cnt, bool has_last,
-                                      int lane, WS &ws, int &n_new_out, int &n_possible_out, bool &dirty_out) {
+                                      int lane, WS &ws, int &n_new_out, int &n_possible_out, bool &dirty_out PAINTRL_PROF_PARAM) {
     ShotsF c;
 #pragma unroll
     for (int s = 0; s <= NS; ++s) {
@@ -478,7 +482,9 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16
         lo0 = fminf(lo0, c0); hi0 = fmaxf(hi0, c0);
         lo1 = fminf(lo1, c1); hi1 = fmaxf(hi1, c1);
     }
+    PAINTRL_PROF(17, lane == 0);
     stamp_ranges(pk, lo0, hi0, lo1, hi1, lane, ws);
+    PAINTRL_PROF(18, lane == 0);
 
     double rmax[NS];
     if (COLOR == 1) {   // HSI: r = distances.max() per shot (bullet_paint_wrapper.py:423-424)
@@ -555,15 +561,20 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16
 // ------------------------------------------------------------------------------ kernels
 // Robot._get_actions (robot.py:302-329): action -> direction, five guided sub-steps.
 // G lanes per environment (the plane / vertex / triangle lists of a sub-step are short).
-template <int G>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int G, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *actions) {
     const int lane = threadIdx.x & 31;
     const int env = (blockIdx.x * (kWarpsPerBlock * 32) + threadIdx.x) / G;
     if (env >= num_envs) return;
     const Grp grp = make_grp<G>(lane);
-    EnvState st;
-    load_state(&ea.states[env], st);
+    PAINTRL_PROF_BEGIN
+    // the fields of the record this phase reads: pose, quaternion, turning angle, off-part state
+    EnvState *gst = &ea.states[env];
+    const double2 s0 = reinterpret_cast<const double2 *>(gst)[0], s1 = reinterpret_cast<const double2 *>(gst)[1],
+                  s2 = reinterpret_cast<const double2 *>(gst)[2];
+    const double quat_w = gst->quat[3], last_angle = gst->last_angle;
+    int term_counter = gst->term_counter, flags = gst->flags;
 
     // ---- action -> direction (robot_gym_env.py:342-347, robot.py:390-398, 352-358)
     double u1, u2, new_angle;
@@ -593,17 +604,16 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
         new_angle = (da1 != 0.0) ? atan(fabs(da2 / da1)) : kPi / 2;
     }
     const double delta_axis1 = u1 * kStepSize, delta_axis2 = u2 * kStepSize;
-    st.angle_diff = fabs(new_angle - st.last_angle);
-    st.last_angle = new_angle;
-    const int counter_before = st.term_counter;
+    const double angle_diff = fabs(new_angle - last_angle);
+    const int counter_before = term_counter;
 
     // ---- Robot._get_actions: 5 guided sub-steps (robot.py:302-329, bullet_paint_wrapper.py:865-880)
-    Vec3 cur_p = {st.pose[0], st.pose[1], st.pose[2]};
-    Vec3 cur_n = tcp_orn_norm(cur_p, st.quat);
+    Vec3 cur_p = {s0.x, s0.y, s1.x};
+    double quat[4] = {s1.y, s2.x, s2.y, quat_w};
+    Vec3 cur_n = tcp_orn_norm(cur_p, quat);
     const double delta1 = delta_axis1 / kPaintPerAction, delta2 = delta_axis2 / kPaintPerAction;
     const double delta2_scaled = delta2 * pk.lwr;
     int full_scans = 0;
-    double quat[4] = {st.quat[0], st.quat[1], st.quat[2], st.quat[3]};
     bool miss_quat_valid = false;   // quat == quat_from_normal(cur_n) from an earlier miss of this step
     double *centers = &ea.moves[env].centers[0][0];
 #pragma unroll 1
@@ -613,9 +623,14 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
         add_comp(p, pk.axis1, delta2_scaled);
         Vec3 end = {p.x + cur_n.x, p.y + cur_n.y, p.z + cur_n.z};
         Vec3 hit, pos, center;
-        int cell;
+        CellRef ref;
+        double2 vc0 = make_double2(0.0, 0.0), vc1 = vc0;
         const double *rec = nullptr;
-        if (ray_test<G>(pk, p, end, grp, hit, cell, full_scans)) rec = hook_triangle<G>(pk, hit, cell, grp);
+        PAINTRL_PROF(s == 0 ? 0 : 1, grp.gl == 0);
+        if (ray_test<G>(pk, p, end, grp, hit, ref, vc0, vc1, full_scans, delta1, delta2_scaled,
+                        s + 1 < kPaintPerAction PAINTRL_PROF_PASS))
+            rec = hook_triangle<G>(pk, hit, ref, vc0, vc1, grp PAINTRL_PROF_PASS);
+        PAINTRL_PROF(11, grp.gl == 0);
         if (rec) {
             // pose = hit + 0.1 n, orn = -n (bullet_paint_wrapper.py:529-530); quaternion and shot-centre
             // offset of -n come from the record (computed by the host with these same operations)
@@ -629,29 +644,35 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
             quat[0] = t2.x; quat[1] = t2.y; quat[2] = t3.x; quat[3] = t3.y;
             center.x = t4.x + pos.x; center.y = t4.y + pos.y; center.z = t5.x + pos.z;   // robot.py:277-278
             cur_n.x = -nx; cur_n.y = -ny; cur_n.z = -nz;
-            st.flags |= kFlagLastOnPart;
+            flags |= kFlagLastOnPart;
             miss_quat_valid = false;
         } else {
             if (!miss_quat_valid) { quat_from_normal(cur_n, quat); miss_quat_valid = true; }
             pos = transform_point(cur_p, quat, delta2, delta1, 0.0);   // robot.py:317 (sic)
             center = transform_point(pos, quat, 0.0, 0.0, 0.1);        // robot.py:277-278
-            if (st.flags & kFlagLastOnPart) {                           // robot.py:292-300
-                st.flags &= ~kFlagLastOnPart;
+            if (flags & kFlagLastOnPart) {                              // robot.py:292-300
+                flags &= ~kFlagLastOnPart;
             } else {
-                st.term_counter += 1;
-                if (st.term_counter > kNotOnPartTerminateSteps) st.flags |= kFlagTerminate;
+                term_counter += 1;
+                if (term_counter > kNotOnPartTerminateSteps) flags |= kFlagTerminate;
             }
         }
         if (grp.gl == 0) { centers[3 * s] = center.x; centers[3 * s + 1] = center.y; centers[3 * s + 2] = center.z; }
         cur_p = pos;
+        PAINTRL_PROF(12, grp.gl == 0);
     }
-    st.pose[0] = cur_p.x; st.pose[1] = cur_p.y; st.pose[2] = cur_p.z;
-    st.quat[0] = quat[0]; st.quat[1] = quat[1]; st.quat[2] = quat[2]; st.quat[3] = quat[3];
     if (grp.gl == 0) {
-        ea.moves[env].offpart_added = st.term_counter - counter_before;
+        reinterpret_cast<double2 *>(gst)[0] = make_double2(cur_p.x, cur_p.y);
+        reinterpret_cast<double2 *>(gst)[1] = make_double2(cur_p.z, quat[0]);
+        reinterpret_cast<double2 *>(gst)[2] = make_double2(quat[1], quat[2]);
+        gst->quat[3] = quat[3];
+        reinterpret_cast<double2 *>(&gst->last_angle)[0] = make_double2(new_angle, angle_diff);
+        gst->term_counter = term_counter;
+        gst->flags = flags;
+        ea.moves[env].offpart_added = term_counter - counter_before;
         ea.moves[env].full_scans = full_scans;
     }
-    store_state(&ea.states[env], st, grp.gl);
+    PAINTRL_PROF(13, grp.gl == 0);
 }
 
 // Everything after the move: stamp, score, observe, auto-reset.  The environment's record, the
@@ -666,6 +687,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     const int env = blockIdx.x * kWarpsPerBlock + warp;
     if (env >= num_envs) return;
     WS &ws = scratch[warp];
+    PAINTRL_PROF_BEGIN
     unsigned *gbits = bits_of(pk, ea, env), *grid_cnt = grid_cnt_of(pk, ea, env);
     int16_t *thick = thick_of(pk, ea, env);
     const unsigned plane_bytes = (unsigned)pk.n_words_pad * 4u;
@@ -678,6 +700,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     }
     __syncwarp();
     mbar_wait(&ws.bar, 0);
+    PAINTRL_PROF(16, lane == 0);
     const Bits<STAGED> bits = {gbits, ws.sbits};
     EnvState &st = ws.st;
 
@@ -685,7 +708,8 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     const bool has_last = (st.flags & kFlagHasLast) != 0;
     int n_new, n_possible;
     bool dirty;
-    stamp<COLOR>(pk, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible, dirty);
+    stamp<COLOR>(pk, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible, dirty PAINTRL_PROF_PASS);
+    PAINTRL_PROF(19, lane == 0);
 
     // ---- robot.py:425-433, robot_gym_env.py:321-340 (every lane computes the same scalars)
     int flags = st.flags | kFlagHasLast;
@@ -716,8 +740,10 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     double *obs = io.obs + (size_t)env * cfg.obs_dim;
     double *next_obs = io.next_obs ? io.next_obs + (size_t)env * cfg.obs_dim : nullptr;
     const Vec3 cur_p = {st.pose[0], st.pose[1], st.pose[2]};
-    write_observation(pk, cfg, bits, grid_cnt, cur_p, lane, ws, obs, resetting ? nullptr : next_obs);
+    PAINTRL_PROF(20, lane == 0);
+    write_observation(pk, cfg, bits, grid_cnt, cur_p, lane, ws, obs, resetting ? nullptr : next_obs PAINTRL_PROF_PASS);
     __syncwarp();
+    PAINTRL_PROF(25, lane == 0);
     if (lane == 0) {
         io.reward[env] = reward;
         io.penalty[env] = penalty;
@@ -758,6 +784,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     __syncwarp();
     if (lane < 8) reinterpret_cast<double2 *>(&ea.states[env])[lane] = reinterpret_cast<const double2 *>(&st)[lane];
     if (STAGED && lane == 0) bulk_wait_read();
+    PAINTRL_PROF(26, lane == 0);
 }
 
 // PaintGymEnv.reset / Robot.reset(pose) for the listed environments, with their first observation.
@@ -784,8 +811,9 @@ reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, const int32_t *env_ids, in
     __syncwarp();
     const Bits<false> bits = {gbits, nullptr};
     Vec3 pose = {st.pose[0], st.pose[1], st.pose[2]};
+    PAINTRL_PROF_BEGIN
     write_observation(pk, cfg, bits, grid_cnt, pose, lane, scratch[warp], obs_out ? obs_out + (size_t)k * cfg.obs_dim : nullptr,
-                      nullptr);
+                      nullptr PAINTRL_PROF_PASS);
     store_state(&ea.states[env], st, lane);
 }
 
@@ -799,7 +827,8 @@ reset_obs_kernel(DevPack pk, DevConfig cfg, unsigned *zero_bits, const unsigned 
     if (k >= pk.n_starts) return;
     const Bits<false> bits = {zero_bits, nullptr};
     Vec3 pose = {pk.start_pos[3 * k], pk.start_pos[3 * k + 1], pk.start_pos[3 * k + 2]};
-    write_observation(pk, cfg, bits, grid_cnt, pose, lane, scratch[warp], table + (size_t)k * cfg.obs_dim, nullptr);
+    PAINTRL_PROF_BEGIN
+    write_observation(pk, cfg, bits, grid_cnt, pose, lane, scratch[warp], table + (size_t)k * cfg.obs_dim, nullptr PAINTRL_PROF_PASS);
 }
 
 // ------------------------------------------------------------------------------ state access
