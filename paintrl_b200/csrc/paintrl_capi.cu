@@ -546,7 +546,7 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
 
     // ---- slot tables: exact FP64 positions, and FP32 origin-relative positions (ball pre-test)
     {
-        std::vector<double> tx(pk.n_slots, 1e30), ty(pk.n_slots, 1e30), tz(pk.n_slots, 1e30);
+        std::vector<double> tx(pk.n_slots + 32, 1e30), ty(pk.n_slots + 32, 1e30), tz(pk.n_slots + 32, 1e30);   // padded: row_ranks reads 4 keys at a time
         std::vector<float> fx(pk.n_slots, 1e30f), fy(pk.n_slots, 1e30f), fz(pk.n_slots, 1e30f);
         pk.org0 = 0.5 * (tmin[0] + tmax[0]); pk.org1 = 0.5 * (tmin[1] + tmax[1]); pk.org2 = 0.5 * (tmin[2] + tmax[2]);
         float max_abs = 0.f;

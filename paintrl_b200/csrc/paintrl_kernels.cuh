@@ -57,6 +57,7 @@ struct alignas(128) WarpScratch {
     int rowL[kMaxRows], rowU[kMaxRows];           // texels of the row with axis0 coordinate <  / <= the TCP's
     int rowWa[kMaxRows], rowWn[kMaxRows];         // stamp candidates of the row: first word, word count
                                                   // (reused as the K != 4 section histogram)
+    uint16_t cand[STAGED ? kStageWords : 2];      // flat list of the step's candidate words (STAGED only)
     unsigned long long bar;                       // mbarrier of the bulk copies
 };
 static_assert(2 * kMaxRows >= 2 * kMaxObs, "the section histogram aliases rowWa / rowWn");
@@ -106,10 +107,12 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned by
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ unsigned lowmask(int n) {   // n in [0, 32]
-    return n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+__device__ __forceinline__ unsigned lowmask(int n) {   // the n lowest bits; n >= 0, clamped to 32 (one BMSK)
+    unsigned m;
+    asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(m) : "r"(n));
+    return m;
 }
-__device__ __forceinline__ int clamp32(int v) { return min(max(v, 0), 32); }
+__device__ __forceinline__ int clamp32(int v) { return max(v, 0); }   // lowmask() clamps at 32 itself
 
 __device__ __forceinline__ unsigned *bits_of(const DevPack &pk, const EnvArrays &ea, int env) {
     return ea.bits + (size_t)env * pk.n_words_pad;
@@ -143,9 +146,15 @@ __device__ __forceinline__ void row_ranks(const DevPack &pk, double p0, int lane
         } else {
             const int *cs = pk.cell_start + (size_t)r * (pk.ncx + 1) + (int)f;
             const int i0 = __ldg(cs), i1 = __ldg(cs + 1);
-            const double *k = kx + (size_t)__ldg(&pk.row_word0[r]) * 32;
-            L = U = i0;
-            for (int i = i0; i < i1; ++i) {
+            const double *k = kx + (size_t)__ldg(&pk.row_word0[r]) * 32 + i0;
+            // the first four keys of the cell in one round of loads (the tables are padded), the rest in a loop
+            const double k0 = __ldg(k), k1 = __ldg(k + 1), k2 = __ldg(k + 2), k3 = __ldg(k + 3);
+            const int c = i1 - i0;
+            L = i0 + ((c > 0 && k0 < p0) ? 1 : 0) + ((c > 1 && k1 < p0) ? 1 : 0) + ((c > 2 && k2 < p0) ? 1 : 0) +
+                ((c > 3 && k3 < p0) ? 1 : 0);
+            U = i0 + ((c > 0 && k0 <= p0) ? 1 : 0) + ((c > 1 && k1 <= p0) ? 1 : 0) + ((c > 2 && k2 <= p0) ? 1 : 0) +
+                ((c > 3 && k3 <= p0) ? 1 : 0);
+            for (int i = 4; i < c; ++i) {
                 const double x = __ldg(&k[i]);
                 L += (x < p0) ? 1 : 0;
                 U += (x <= p0) ? 1 : 0;
@@ -157,66 +166,73 @@ __device__ __forceinline__ void row_ranks(const DevPack &pk, double p0, int lane
     __syncwarp();
 }
 
+// The TCP's row of the texel layout (-1 / n_rows when it lies below / above all rows).
+__device__ __forceinline__ int pose_row(const DevPack &pk, double p1) {
+    const double f1 = floor((p1 - pk.row_o1) * pk.row_inv);
+    return !(f1 >= 0.0) ? -1 : (f1 >= (double)pk.n_rows ? pk.n_rows : (int)f1);
+}
+
 // 4-sector observation (bullet_paint_wrapper.py:1033-1061): for every front texel, rx / ry = texel
 // position - TCP position along the principal axes; skipped if both are 0; sector 0 if rx>0,ry>0,
 // 1 if rx<0,ry>0, 2 if rx<0,ry<0, else 3; obs[s] = #(status != 255) / #texels of the sector.
 template <typename WS, typename BITS>
 __device__ __forceinline__ void section4_counts(const DevPack &pk, const BITS &bits, const Vec3 &pose, int lane, WS &ws,
-                                                int tot[4], int open[4] PAINTRL_PROF_PARAM) {
+                                                int tot[4], int open[4], bool ranks_ready PAINTRL_PROF_PARAM) {
     const double p0 = comp(pose, pk.axis0), p1 = comp(pose, pk.axis1);
     PAINTRL_PROF(21, lane == 0);
-    row_ranks(pk, p0, lane, ws);
+    if (!ranks_ready) row_ranks(pk, p0, lane, ws);
     PAINTRL_PROF(22, lane == 0);
-    const double f1 = floor((p1 - pk.row_o1) * pk.row_inv);
-    const int prow = !(f1 >= 0.0) ? -1 : (f1 >= (double)pk.n_rows ? pk.n_rows : (int)f1);
+    const int prow = pose_row(pk, p1);
     const bool init_painted = (pk.status_init == kPainted);
     const unsigned flip = init_painted ? 0u : 0xffffffffu;   // open = bits ^ flip
 
-    // ---- rows above / below the TCP's row: totals are static
+    // ---- rows above / below the TCP's row, one row per lane: texels left of the TCP are the first L
+    // slots of the row, texels right of it the slots from U on, so the sector counts are popcounts of
+    // prefix masks of the row's words (totals are static: L, U - L, n - U)
     int t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-    for (int r = lane; r < pk.n_rows; r += 32) {
-        const int n = __ldg(&pk.row_count[r]), L = ws.rowL[r], U = ws.rowU[r];
-        if (r > prow) { t1 += L; t0 += n - U; t3 += U - L; }
-        else if (r < prow) { t2 += L; t3 += n - L; }
-    }
-    // ---- their open texels: prefix / suffix masks of each word
     int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-    for (int w = lane; w < pk.n_words; w += 32) {
-        const unsigned info = __ldg(&pk.word_info[w]);   // row | valid slots << 8 | word index in the row << 14
-        const int r = (int)(info & 0xffu);
+    for (int r = lane; r < pk.n_rows; r += 32) {
         if (r == prow) continue;
-        const int s = (int)(info >> 14) << 5;
-        const unsigned o = (bits.ld(w) ^ flip) & lowmask((int)((info >> 8) & 0x3fu));
-        const unsigned mL = lowmask(clamp32(ws.rowL[r] - s));
-        if (r > prow) {
-            const unsigned mU = lowmask(clamp32(ws.rowU[r] - s));
-            o1 += __popc(o & mL);
-            o0 += __popc(o & ~mU);
-            o3 += __popc(o & mU & ~mL);
-        } else {
-            o2 += __popc(o & mL);
-            o3 += __popc(o & ~mL);
+        const int n = __ldg(&pk.row_count[r]), L = ws.rowL[r], U = ws.rowU[r];
+        const int w0 = __ldg(&pk.row_word0[r]), nw = (n + 31) >> 5;
+        const int kL = L >> 5, kU = U >> 5;
+        const unsigned last = lowmask(n - ((nw - 1) << 5));
+        int cL = 0, cU = 0, cA = 0;   // open texels among the first L / first U / all n slots
+        for (int wi = 0; wi < nw; ++wi) {   // whole words
+            unsigned o = bits.ld(w0 + wi) ^ flip;
+            if (wi == nw - 1) o &= last;
+            const int c = __popc(o);
+            cA += c;
+            cL += wi < kL ? c : 0;
+            cU += wi < kU ? c : 0;
         }
+        if (kL < nw) cL += __popc((bits.ld(w0 + kL) ^ flip) & lowmask(L & 31) & (kL == nw - 1 ? last : 0xffffffffu));
+        if (kU < nw) cU += __popc((bits.ld(w0 + kU) ^ flip) & lowmask(U & 31) & (kU == nw - 1 ? last : 0xffffffffu));
+        if (r > prow) { t1 += L; t0 += n - U; t3 += U - L; o1 += cL; o0 += cA - cU; o3 += cU - cL; }
+        else { t2 += L; t3 += n - L; o2 += cL; o3 += cA - cL; }
     }
     PAINTRL_PROF(23, lane == 0);
-    // ---- the TCP's own row, texel by texel along axis1 (lane = slot)
+    // ---- the TCP's own row, texel by texel along axis1 (lane = slot): ballots of y > p1 / y < p1
+    // against the row's prefix masks; every lane holds the same counts, lane 0 contributes them
     if (prow >= 0 && prow < pk.n_rows) {
         const int w0 = __ldg(&pk.row_word0[prow]), w1 = __ldg(&pk.row_word0[prow + 1]);
         const int n = __ldg(&pk.row_count[prow]), L = ws.rowL[prow], U = ws.rowU[prow];
-        const double *ky = axis_table(pk, pk.axis1);
-        for (int w = w0; w < w1; ++w) {
-            const int idx = ((w - w0) << 5) + lane;
-            const double y = __ldg(&ky[(size_t)w * 32 + lane]);
-            const int op = (int)(((bits.ld(w) ^ flip) >> lane) & 1u);
-            const bool gx = idx >= U, lx = idx < L, gy = y > p1, ly = y < p1;
-            if (idx < n && (gx || lx || gy || ly)) {
-                const int q = (gx && gy) ? 0 : ((lx && gy) ? 1 : ((lx && ly) ? 2 : 3));
-                if (q == 0) { t0 += 1; o0 += op; }
-                else if (q == 1) { t1 += 1; o1 += op; }
-                else if (q == 2) { t2 += 1; o2 += op; }
-                else { t3 += 1; o3 += op; }
-            }
+        const double *ky = axis_table(pk, pk.axis1) + (size_t)w0 * 32 + lane;
+        int u0 = 0, u1 = 0, u2 = 0, u3 = 0, v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+#pragma unroll 2
+        for (int wi = 0; wi < w1 - w0; ++wi) {
+            const double y = __ldg(ky + (size_t)wi * 32);
+            const unsigned mV = lowmask(clamp32(n - (wi << 5)));
+            const unsigned gy = __ballot_sync(kFull, y > p1) & mV, ly = __ballot_sync(kFull, y < p1) & mV;
+            const unsigned mL = lowmask(clamp32(L - (wi << 5))), mU = lowmask(clamp32(U - (wi << 5)));
+            const unsigned o = bits.ld(w0 + wi) ^ flip;
+            const unsigned q0 = gy & ~mU, q1 = gy & mL, q2 = ly & mL;
+            const unsigned skip = mV & ~gy & ~ly & mU & ~mL;              // rx == 0 and ry == 0
+            const unsigned q3 = mV & ~(q0 | q1 | q2 | skip);
+            u0 += __popc(q0); u1 += __popc(q1); u2 += __popc(q2); u3 += __popc(q3);
+            v0 += __popc(q0 & o); v1 += __popc(q1 & o); v2 += __popc(q2 & o); v3 += __popc(q3 & o);
         }
+        if (lane == 0) { t0 += u0; t1 += u1; t2 += u2; t3 += u3; o0 += v0; o1 += v1; o2 += v2; o3 += v3; }
     }
     PAINTRL_PROF(24, lane == 0);
     tot[0] = __reduce_add_sync(kFull, t0); tot[1] = __reduce_add_sync(kFull, t1);
@@ -283,7 +299,7 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const DevCo
     // section / discrete
     if (grad == 4) {
         int tot[4], open[4];
-        section4_counts(pk, bits, pose, lane, ws, tot, open PAINTRL_PROF_PASS);
+        section4_counts(pk, bits, pose, lane, ws, tot, open, false PAINTRL_PROF_PASS);
         if (lane < 4) {
             int t = lane == 0 ? tot[0] : (lane == 1 ? tot[1] : (lane == 2 ? tot[2] : tot[3]));
             int o = lane == 0 ? open[0] : (lane == 1 ? open[1] : (lane == 2 ? open[2] : open[3]));
@@ -387,68 +403,129 @@ __device__ __forceinline__ double cen(const WS &ws, int s, int k) {
     return s < NS ? ws.mv.centers[s][k] : ws.st.last_center[k];
 }
 
-// which shots (bits 0..4) and the previous step's last shot (bit 5) contain slot j
-template <typename WS>
-__device__ __forceinline__ unsigned ball_mask(const DevPack &pk, const ShotsF &c, const WS &ws, int j, bool has_last) {
-    const float r2f = (float)(kPaintRadius * kPaintRadius);
+// FP32 pre-test of slot j against the six balls: e[s] = |t - c_s|^2 - r^2 (negative inside);
+// returns true when some |e[s]| <= kBallEps, i.e. FP32 cannot decide and the FP64 test must.
+__device__ __forceinline__ bool ball_pretest(const DevPack &pk, const ShotsF &c, int j, float e[NS + 1]) {
+    const float nr2f = -(float)(kPaintRadius * kPaintRadius);
     const float tx = __ldg(&pk.fx[j]), ty = __ldg(&pk.fy[j]), tz = __ldg(&pk.fz[j]);
-    unsigned in = 0, amb = 0;
+    float m = INFINITY;
 #pragma unroll
     for (int s = 0; s <= NS; ++s) {
         const float dx = tx - c.x[s], dy = ty - c.y[s], dz = tz - c.z[s];
-        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        in |= (d2 <= r2f ? 1u : 0u) << s;
-        amb |= (fabsf(d2 - r2f) <= kBallEps ? 1u : 0u) << s;
+        e[s] = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, nr2f)));
+        m = fminf(m, fabsf(e[s]));
     }
-    if (amb) {
-        const double r2 = kPaintRadius * kPaintRadius;
+    return m <= kBallEps;
+}
+
+// the exact test `dx*dx + dy*dy + dz*dz <= r*r` of slot j against ball s (bullet_paint_wrapper.py:569)
+template <typename WS>
+__device__ __forceinline__ bool ball_exact(const WS &ws, double x, double y, double z, int s) {
+    const double r2 = kPaintRadius * kPaintRadius;
+    const double dx = x - cen(ws, s, 0), dy = y - cen(ws, s, 1), dz = z - cen(ws, s, 2);
+    return (dx * dx + dy * dy + dz * dz) <= r2;
+}
+
+// which shots (bits 0..4) and the previous step's last shot (bit 5) contain slot j
+template <typename WS>
+__device__ __forceinline__ unsigned ball_mask(const DevPack &pk, const ShotsF &c, const WS &ws, int j, bool has_last) {
+    float e[NS + 1];
+    unsigned in = 0;
+    if (ball_pretest(pk, c, j, e)) {
         const double x = __ldg(&pk.tx[j]), y = __ldg(&pk.ty[j]), z = __ldg(&pk.tz[j]);
-        in = 0;
 #pragma unroll
-        for (int s = 0; s <= NS; ++s) {
-            const double dx = x - cen(ws, s, 0), dy = y - cen(ws, s, 1), dz = z - cen(ws, s, 2);
-            in |= ((dx * dx + dy * dy + dz * dz) <= r2 ? 1u : 0u) << s;
-        }
+        for (int s = 0; s <= NS; ++s) in |= (ball_exact(ws, x, y, z, s) ? 1u : 0u) << s;
+    } else {
+#pragma unroll
+        for (int s = 0; s <= NS; ++s) in |= (e[s] <= 0.f ? 1u : 0u) << s;
     }
     if (!has_last) in &= (1u << NS) - 1u;
     return in;
+}
+
+// RGB stamp: is slot j inside some shot, and is it a "valid pixel" of some shot -- inside shot s but
+// not inside the shot before it (bullet_paint_wrapper.py:575; the shot before shot 0 is the previous
+// step's last one).  Predicate logic only, no per-shot bit mask.
+template <typename WS>
+__device__ __forceinline__ void ball_flags(const DevPack &pk, const ShotsF &c, const WS &ws, int j, bool has_last, bool &any_shot,
+                                           bool &possible) {
+    float e[NS + 1];
+    bool in[NS + 1];
+    if (ball_pretest(pk, c, j, e)) {
+        const double x = __ldg(&pk.tx[j]), y = __ldg(&pk.ty[j]), z = __ldg(&pk.tz[j]);
+#pragma unroll
+        for (int s = 0; s <= NS; ++s) in[s] = ball_exact(ws, x, y, z, s);
+    } else {
+#pragma unroll
+        for (int s = 0; s <= NS; ++s) in[s] = e[s] <= 0.f;
+    }
+    bool prev = has_last && in[NS];
+    any_shot = false;
+    possible = false;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        any_shot = any_shot || in[s];
+        possible = possible || (in[s] && !prev);
+        prev = in[s];
+    }
 }
 
 // Per row, the words whose texels can lie inside one of the step's shots: the row's axis1 interval
 // against the shots' axis1 extent gives a half-width along axis0 (the ball projects to a disc of
 // the same radius), the static cell table turns the axis0 interval into a slot range.  FP32 on
 // origin-relative coordinates with margins: it only has to be conservative, every slot of a
-// candidate word is tested exactly.
-template <typename WS>
-__device__ __forceinline__ void stamp_ranges(const DevPack &pk, float lo0, float hi0, float lo1, float hi1, int lane, WS &ws) {
+// candidate word is tested exactly.  STAGED: the words are also flattened into ws.cand (returns
+// their number).
+template <bool STAGED, int COLOR, typename WS>
+__device__ __forceinline__ int stamp_ranges(const DevPack &pk, float lo0, float hi0, float lo1, float hi1, int lane, WS &ws) {
     const float rr = (float)kPaintRadius + 4e-5f;
-    for (int r = lane; r < pk.n_rows; r += 32) {
+    int base = 0;
+    for (int r0 = 0; r0 < pk.n_rows; r0 += 32) {
+        const int r = r0 + lane;
         int wa = 0, wn = 0;
-        const float ylo = fmaf((float)r, pk.rel_row_h, pk.rel_row_o1) - 2e-5f, yhi = ylo + pk.rel_row_h + 4e-5f;
-        const float dy = fmaxf(0.f, fmaxf(ylo - hi1, lo1 - yhi));
-        if (dy <= rr) {
-            const float hw = sqrtf(rr * rr - dy * dy) + 4e-5f;
-            const float fa = floorf((lo0 - hw - pk.rel_cx_o0) * pk.rel_cx_inv) - 1.f;
-            const float fb = floorf((hi0 + hw - pk.rel_cx_o0) * pk.rel_cx_inv) + 1.f;
-            if (fb >= 0.f && fa < (float)pk.ncx) {
-                const int ca = (int)fmaxf(fa, 0.f), cb = (int)fminf(fb, (float)(pk.ncx - 1));
-                const int *cs = pk.cell_start + (size_t)r * (pk.ncx + 1);
-                const int i0 = __ldg(cs + ca), i1 = __ldg(cs + cb + 1);
-                if (i1 > i0) {
-                    wa = __ldg(&pk.row_word0[r]) + (i0 >> 5);
-                    wn = ((i1 - 1) >> 5) - (i0 >> 5) + 1;
+        if (r < pk.n_rows) {
+            const float ylo = fmaf((float)r, pk.rel_row_h, pk.rel_row_o1) - 2e-5f, yhi = ylo + pk.rel_row_h + 4e-5f;
+            const float dy = fmaxf(0.f, fmaxf(ylo - hi1, lo1 - yhi));
+            if (dy <= rr) {
+                const float hw = sqrtf(rr * rr - dy * dy) + 4e-5f;
+                const float fa = floorf((lo0 - hw - pk.rel_cx_o0) * pk.rel_cx_inv) - 1.f;
+                const float fb = floorf((hi0 + hw - pk.rel_cx_o0) * pk.rel_cx_inv) + 1.f;
+                if (fb >= 0.f && fa < (float)pk.ncx) {
+                    const int ca = (int)fmaxf(fa, 0.f), cb = (int)fminf(fb, (float)(pk.ncx - 1));
+                    const int *cs = pk.cell_start + (size_t)r * (pk.ncx + 1);
+                    const int i0 = __ldg(cs + ca), i1 = __ldg(cs + cb + 1);
+                    if (i1 > i0) {
+                        wa = __ldg(&pk.row_word0[r]) + (i0 >> 5);
+                        wn = ((i1 - 1) >> 5) - (i0 >> 5) + 1;
+                    }
                 }
             }
+            ws.rowWa[r] = wa;
+            ws.rowWn[r] = wn;
         }
-        ws.rowWa[r] = wa;
-        ws.rowWn[r] = wn;
+        if (STAGED) {
+            int incl = wn;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const int at = base + incl - wn;
+            for (int t = 0; t < wn; ++t) ws.cand[at + t] = (uint16_t)(wa + t);
+            base += __shfl_sync(kFull, incl, 31);
+        }
     }
     __syncwarp();
+    return base;
 }
 
 // Calls body(w) warp-uniformly for every candidate word.
-template <typename WS, typename BodyFn>
-__device__ __forceinline__ void for_each_stamp_word(const DevPack &pk, int lane, const WS &ws, BodyFn body) {
+template <bool STAGED, typename WS, typename BodyFn>
+__device__ __forceinline__ void for_each_stamp_word(const DevPack &pk, int lane, const WS &ws, int n_cand, BodyFn body) {
+    if (STAGED) {
+        for (int k = 0; k < n_cand; ++k) body((int)ws.cand[k]);
+        return;
+    }
     for (int r0 = 0; r0 < pk.n_rows; r0 += 32) {
         const int r = r0 + lane;
         const int wa = r < pk.n_rows ? ws.rowWa[r] : 0, wn = r < pk.n_rows ? ws.rowWn[r] : 0;
@@ -464,7 +541,7 @@ __device__ __forceinline__ void for_each_stamp_word(const DevPack &pk, int lane,
 
 // Returns (warp-uniform) the newly painted count (RGB) / removed thickness units (HSI), the
 // |union of valid pixels| of robot.py:425 and whether any flip bit changed.
-template <int COLOR, typename WS, typename BITS>
+template <int COLOR, bool STAGED, typename WS, typename BITS>
 __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16_t *thick, unsigned *grid_cnt, bool has_last,
                                       int lane, WS &ws, int &n_new_out, int &n_possible_out, bool &dirty_out PAINTRL_PROF_PARAM) {
     ShotsF c;
@@ -483,14 +560,14 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16
         lo1 = fminf(lo1, c1); hi1 = fmaxf(hi1, c1);
     }
     PAINTRL_PROF(17, lane == 0);
-    stamp_ranges(pk, lo0, hi0, lo1, hi1, lane, ws);
+    const int n_cand = stamp_ranges<STAGED, COLOR>(pk, lo0, hi0, lo1, hi1, lane, ws);
     PAINTRL_PROF(18, lane == 0);
 
     double rmax[NS];
     if (COLOR == 1) {   // HSI: r = distances.max() per shot (bullet_paint_wrapper.py:423-424)
 #pragma unroll
         for (int s = 0; s < NS; ++s) rmax[s] = -1.0;
-        for_each_stamp_word(pk, lane, ws, [&](int w) {
+        for_each_stamp_word<STAGED>(pk, lane, ws, n_cand, [&](int w) {
             const int j = w * 32 + lane;
             const unsigned in = ball_mask(pk, c, ws, j, false);
             if (in) {
@@ -510,22 +587,33 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16
 
     int n_new = 0, n_possible = 0;   // RGB: warp-uniform; HSI n_new: per-lane partial
     unsigned any = 0;
-    for_each_stamp_word(pk, lane, ws, [&](int w) {
-        const int j = w * 32 + lane;
-        const unsigned in = ball_mask(pk, c, ws, j, has_last);
-        const unsigned shots = in & ((1u << NS) - 1u);
-        const unsigned uni = __ballot_sync(kFull, shots != 0u);
-        if (uni == 0u) return;
-        // affected \ last_affected, shot by shot (:575): shot s counts if the previous shot missed the texel
-        const unsigned prev = ((shots << 1) | (in >> NS)) & ((1u << NS) - 1u);
-        n_possible += __popc(__ballot_sync(kFull, (shots & ~prev) != 0u));
-        unsigned flipped;                                  // slots whose painted predicate changes
-        if (COLOR == 0) {                                  // :358-365
+    if (COLOR == 0) {                                      // :358-365
+        for_each_stamp_word<STAGED>(pk, lane, ws, n_cand, [&](int w) {
+            const int j = w * 32 + lane;
+            bool any_shot, possible;
+            ball_flags(pk, c, ws, j, has_last, any_shot, possible);
+            const unsigned uni = __ballot_sync(kFull, any_shot);
+            if (uni == 0u) return;
+            n_possible += __popc(__ballot_sync(kFull, possible));
             const unsigned old = bits.ld(w);
-            flipped = uni & ~old;
-            n_new += __popc(flipped);
-            if (flipped && lane == 0) bits.st(w, old | uni);
-        } else {                                           // :411-434
+            const unsigned flipped = uni & ~old;           // slots whose painted predicate changes
+            if (flipped) {
+                n_new += __popc(flipped);
+                if (lane == 0) bits.st(w, old | uni);
+                any |= flipped;
+                if (grid_cnt && ((flipped >> lane) & 1u)) atomicAdd(grid_cnt + __ldg(&pk.gcell[j]), 1u);
+            }
+        });
+    } else {                                               // :411-434
+        for_each_stamp_word<STAGED>(pk, lane, ws, n_cand, [&](int w) {
+            const int j = w * 32 + lane;
+            const unsigned in = ball_mask(pk, c, ws, j, has_last);
+            const unsigned shots = in & ((1u << NS) - 1u);
+            const unsigned uni = __ballot_sync(kFull, shots != 0u);
+            if (uni == 0u) return;
+            // affected \ last_affected, shot by shot (:575): shot s counts if the previous shot missed the texel
+            const unsigned prev = ((shots << 1) | (in >> NS)) & ((1u << NS) - 1u);
+            n_possible += __popc(__ballot_sync(kFull, (shots & ~prev) != 0u));
             bool fl = false;
             if (shots) {
                 const int sv0 = (int)__ldcg(&thick[j]);
@@ -546,12 +634,14 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16
                     fl = (sv0 == kPainted);                // values only decrease: 255 is left once
                 }
             }
-            flipped = __ballot_sync(kFull, fl);
-            if (flipped && lane == 0) bits.st(w, bits.ld(w) | flipped);
-        }
-        any |= flipped;
-        if (grid_cnt && ((flipped >> lane) & 1u)) atomicAdd(grid_cnt + __ldg(&pk.gcell[j]), 1u);
-    });
+            const unsigned flipped = __ballot_sync(kFull, fl);
+            if (flipped) {
+                if (lane == 0) bits.st(w, bits.ld(w) | flipped);
+                any |= flipped;
+                if (grid_cnt && ((flipped >> lane) & 1u)) atomicAdd(grid_cnt + __ldg(&pk.gcell[j]), 1u);
+            }
+        });
+    }
     n_new_out = (COLOR == 0) ? n_new : __reduce_add_sync(kFull, n_new);
     n_possible_out = n_possible;
     dirty_out = any != 0u;
@@ -679,7 +769,7 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
 // move kernel's output and (STAGED) its flip bits come in through one TMA bulk-copy group per warp
 // and the bits go back the same way.
 template <int COLOR, bool STAGED>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, STAGED ? 8 : 4)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, STAGED ? 7 : 4)
 paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     typedef WarpScratch<STAGED> WS;
     __shared__ WS scratch[kWarpsPerBlock];
@@ -703,31 +793,90 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     PAINTRL_PROF(16, lane == 0);
     const Bits<STAGED> bits = {gbits, ws.sbits};
     EnvState &st = ws.st;
+    const Vec3 cur_p = {st.pose[0], st.pose[1], st.pose[2]};
+    // 4-sector section / discrete observation: its per-row ranks only depend on the pose, so they are
+    // looked up before the stamp and the TCP row's axis1 keys are prefetched into L1 meanwhile
+    const bool fast4 = (cfg.obs_mode == 0 || cfg.obs_mode == 3) && cfg.obs_grad == 4;
+    if (fast4) {
+        row_ranks(pk, comp(cur_p, pk.axis0), lane, ws);
+        const int prow = pose_row(pk, comp(cur_p, pk.axis1));
+        if (prow >= 0 && prow < pk.n_rows) {
+            const int w0 = __ldg(&pk.row_word0[prow]), w1 = __ldg(&pk.row_word0[prow + 1]);
+            const char *ky = reinterpret_cast<const char *>(axis_table(pk, pk.axis1) + (size_t)w0 * 32);
+            for (int k = lane; k < 2 * (w1 - w0); k += 32) prefetch_l1(ky + (size_t)k * 128);
+        }
+    }
+    PAINTRL_PROF(15, lane == 0);
 
     // ---- stamp the 5 shots (bullet_paint_wrapper.py:568-577)
     const bool has_last = (st.flags & kFlagHasLast) != 0;
     int n_new, n_possible;
     bool dirty;
-    stamp<COLOR>(pk, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible, dirty PAINTRL_PROF_PASS);
+    stamp<COLOR, STAGED>(pk, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible, dirty PAINTRL_PROF_PASS);
     PAINTRL_PROF(19, lane == 0);
 
-    // ---- robot.py:425-433, robot_gym_env.py:321-340 (every lane computes the same scalars)
+    // ---- robot.py:425-433, robot_gym_env.py:321-340 (every lane ends up with the same scalars).
+    // The FP64 divisions of this block and of the normalised pose are independent of each other:
+    // each is evaluated by one lane, all in the same instruction, and broadcast.
     int flags = st.flags | kFlagHasLast;
     const double succeeded = (COLOR == 0) ? (double)n_new : (double)n_new / 255.0;
-    const double rate = n_possible ? succeeded / (double)n_possible : 0.0;
     if (ws.mv.offpart_added >= kPaintPerAction && n_possible == 0) flags |= kFlagTerminate;
-    const double reward = succeeded / 100;
+    const double radius = kPaintRadius;
+    const double axis1_real = comp(cur_p, pk.axis0), axis2_real = comp(cur_p, pk.axis1);
+    double rate, reward, turn, axis2_in, rel;
+    {
+        double num = succeeded, den = (double)n_possible;                       // lane 0: rate (robot.py:426)
+        if (lane == 1) den = 100.0;                                             // reward (robot_gym_env.py:322)
+        if (lane == 2) { num = st.angle_diff; den = kPi; }                      // turning penalty (:338)
+        if (lane == 3) { num = axis2_real - pk.range1_min + radius; den = pk.range1_max - pk.range1_min + 2 * radius; }   // bullet_paint_wrapper.py:969
+        if (lane == 4) { num = axis2_real - pk.range1_min; den = pk.range1_max - pk.range1_min; }                         // :845
+        const double q = num / den;
+        rate = n_possible ? __shfl_sync(kFull, q, 0) : 0.0;
+        reward = __shfl_sync(kFull, q, 1);
+        turn = __shfl_sync(kFull, q, 2);
+        axis2_in = __shfl_sync(kFull, q, 3);
+        rel = __shfl_sync(kFull, q, 4);
+    }
     const double total_reward = st.total_reward + reward;
     double penalty = 0.2;
     if (cfg.overlap_penalty) penalty += 0.1 * (1 - rate);
-    if (cfg.turning_penalty) penalty += 0.1 * (st.angle_diff / kPi);
+    if (cfg.turning_penalty) penalty += 0.1 * turn;
     const double actual = reward - penalty;
+    const int step_counter = st.step_counter + 1;
+    // normalised pose, bullet_paint_wrapper.py:844-851, 965-978
+    int gi;
+    {
+        const double scaled = rel * pk.grid_granularity;
+        gi = !(scaled > -1.0) ? 0 : (scaled >= (double)pk.grid_granularity ? pk.grid_granularity - 1 : (int)scaled);
+    }
+    const double glo = __ldg(&pk.grid_lo[gi]), ghi = __ldg(&pk.grid_hi[gi]);
+    PAINTRL_PROF(20, lane == 0);
+
+    // ---- observation counts (robot_gym_env.py:358: computed even when done)
+    int tot[4] = {0, 0, 0, 0}, open[4] = {0, 0, 0, 0};
+    if (fast4) section4_counts(pk, bits, cur_p, lane, ws, tot, open, true PAINTRL_PROF_PASS);
+
+    // ---- second round of divisions: average reward (robot_gym_env.py:295), axis1 of the normalised pose, sector ratios
+    double avg_reward, axis1_in, ratio;
+    {
+        double num = total_reward, den = (double)step_counter;
+        if (lane == 1) { num = axis1_real - glo + radius; den = ghi - glo + 2 * radius; }
+        int t = 1, o = 0;
+        if (lane >= 2 && lane < 6) {
+            t = lane == 2 ? tot[0] : (lane == 3 ? tot[1] : (lane == 4 ? tot[2] : tot[3]));
+            o = lane == 2 ? open[0] : (lane == 3 ? open[1] : (lane == 4 ? open[2] : open[3]));
+            num = (double)o; den = (double)t;
+        }
+        const double q = num / den;
+        ratio = t == 0 ? 0.0 : q;                        // lanes 2..5: sector s = lane - 2 (bullet_paint_wrapper.py:1057-1060)
+        avg_reward = __shfl_sync(kFull, q, 0);
+        axis1_in = (ghi - glo == 0.0) ? 0.0 : __shfl_sync(kFull, q, 1);
+    }
+    const double a1 = clip01(axis1_in), a2 = clip01(axis2_in);
 
     // ---- robot_gym_env.py:289-304 _termination
-    const int step_counter = st.step_counter + 1;
     const double max_pts = cfg.max_possible_point;
     const bool finished = !(max_pts > total_reward * 100);
-    const double avg_reward = total_reward / step_counter;
     bool done, decided = false;
     if (avg_reward < cfg.expected_avg_reward && cfg.termination_mode != 0) {
         if (cfg.termination_mode == 1) { done = true; decided = true; }
@@ -735,13 +884,31 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     }
     if (!decided) done = finished || (flags & kFlagTerminate) || step_counter > cfg.episode_max_length - 1;
 
-    // ---- observation (computed even when done, robot_gym_env.py:358)
+    // ---- write the observation (robot_gym_env.py:306-319)
     const bool resetting = done && cfg.auto_reset;
     double *obs = io.obs + (size_t)env * cfg.obs_dim;
     double *next_obs = io.next_obs ? io.next_obs + (size_t)env * cfg.obs_dim : nullptr;
-    const Vec3 cur_p = {st.pose[0], st.pose[1], st.pose[2]};
-    PAINTRL_PROF(20, lane == 0);
-    write_observation(pk, cfg, bits, grid_cnt, cur_p, lane, ws, obs, resetting ? nullptr : next_obs PAINTRL_PROF_PASS);
+    if (resetting) next_obs = nullptr;
+    if (fast4) {
+        if (lane >= 2 && lane < 6) {
+            obs[lane - 2] = ratio;
+            if (next_obs) next_obs[lane - 2] = ratio;
+        }
+        if (lane == 0) {
+            if (cfg.obs_mode == 3) {   // discrete: robot_gym_env.py:101-103, 314-318
+                const int position = (handle_pos(a1) + 1) * 22 + handle_pos(a2);
+                const double v = 1.0 / position;
+                obs[4] = v;
+                if (next_obs) next_obs[4] = v;
+            } else {
+                obs[4] = a1; obs[5] = a2;
+                if (next_obs) { next_obs[4] = a1; next_obs[5] = a2; }
+            }
+        }
+    } else {
+        write_observation(pk, cfg, bits, grid_cnt, cur_p, lane, ws, obs, next_obs PAINTRL_PROF_PASS);
+    }
+    if (io.next_obs) next_obs = io.next_obs + (size_t)env * cfg.obs_dim;
     __syncwarp();
     PAINTRL_PROF(25, lane == 0);
     if (lane == 0) {

@@ -18,7 +18,7 @@ from paintrl_b200.config import EnvConfig
 NAMES = {0: 'move: load + action + first p', 1: 'move: p / end of later sub-steps', 6: 'ray: guess cell, entry, issue blob loads',
          7: 'ray: slab pass (div, reductions)', 8: 'ray: region check / accept', 9: 'ray: verify / full scan / hit',
          10: 'hook: nearest vertex', 11: 'hook: triangles + pick', 12: 'move: pose, quat, centre', 13: 'move: stores',
-         16: 'paint: TMA loads + mbarrier wait', 17: 'stamp: shot floats, bbox', 18: 'stamp: row ranges', 19: 'stamp: words (ball tests, bits)',
+         15: 'paint: early row ranks + TCP-row prefetch', 16: 'paint: TMA loads + mbarrier wait', 17: 'stamp: shot floats, bbox', 18: 'stamp: row ranges', 19: 'stamp: words (ball tests, bits)',
          20: 'score + termination', 21: 'obs: normalised pose', 22: 'obs: row ranks', 23: 'obs: rows + words (popc)',
          24: 'obs: TCP row', 25: 'obs: reductions + write', 26: 'paint: outputs, reset, stores'}
 
