@@ -650,6 +650,25 @@ int paintrl_debug_profile(unsigned long long *out64, int reset) {
 #endif
 }
 
+/* Debug only: rays that left the fast path (instrumented build); returns the number copied (<= max_rays). */
+int paintrl_debug_rays(double *out, int max_rays, int reset) {
+#ifdef PAINTRL_PROFILE
+    cudaDeviceSynchronize();
+    unsigned long long counts[4];
+    cudaMemcpyFromSymbol(counts, g_dbg_counts, sizeof(counts));
+    int n = (int)std::min<unsigned long long>(std::min<unsigned long long>(counts[1], 4096), (unsigned long long)max_rays);
+    if (out && n > 0) cudaMemcpyFromSymbol(out, g_dbg_rays, (size_t)n * 8 * sizeof(double));
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_dbg_counts, z, sizeof(z));
+    }
+    return n;
+#else
+    (void)out; (void)max_rays; (void)reset;
+    return 0;
+#endif
+}
+
 int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_t num_envs, int32_t device,
                    PaintrlHandle *out) {
     if (!pack || !cfg || !out) return fail(PAINTRL_E_INVALID, "null argument");
@@ -728,7 +747,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
               e->arena.alloc((void **)&e->stage_done, (size_t)num_envs) == cudaSuccess;
     if (!ok) { delete e; return fail(PAINTRL_E_CUDA, "device allocation failed (state / status planes)"); }
     cudaMemset(e->states, 0, sizeof(EnvState) * (size_t)num_envs);
-    cudaMemset(e->moves, 0, sizeof(MoveOut) * (size_t)num_envs);
+    cudaMemset(e->moves, 0xff, sizeof(MoveOut) * (size_t)num_envs);   // miss_cache = none
     cudaMemset(e->env_stats, 0, sizeof(EnvStat) * (size_t)num_envs);
     cudaMemset(e->bits, 0, bits_bytes);
     if (e->thick) cudaMemset(e->thick, 0, thick_bytes);
@@ -746,7 +765,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
         int lanes = ml ? atoi(ml) : 8;
         e->move_lanes = (lanes == 16 || lanes == 32) ? lanes : 8;
         const char *mb = getenv("PAINTRL_MOVE_MINB");
-        e->move_minb = (mb && atoi(mb) == 4) ? 4 : 7;
+        e->move_minb = mb ? std::min(7, std::max(4, atoi(mb))) : 4;
     }
     *out = e;
     return PAINTRL_OK;
@@ -806,9 +825,18 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
         cudaStream_t ms = as_stream(stream);
         const int L = h->move_lanes;
         const int mblocks = (int)(((long long)h->num_envs * L + threads - 1) / threads);
-#define PAINTRL_MOVE(G, MINB) move_kernel<G, MINB><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev)
+        const bool ax12m = h->pk.axis0 == 1 && h->pk.axis1 == 2;
+#define PAINTRL_MOVE(G, MINB)                                                                                              \
+    do {                                                                                                                   \
+        if (ax12m) move_kernel<G, MINB, true><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);  \
+        else move_kernel<G, MINB, false><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);       \
+    } while (0)
         if (h->move_minb == 7) {
             if (L == 8) PAINTRL_MOVE(8, 7); else if (L == 16) PAINTRL_MOVE(16, 7); else PAINTRL_MOVE(32, 7);
+        } else if (h->move_minb == 6) {
+            if (L == 8) PAINTRL_MOVE(8, 6); else if (L == 16) PAINTRL_MOVE(16, 6); else PAINTRL_MOVE(32, 6);
+        } else if (h->move_minb == 5) {
+            if (L == 8) PAINTRL_MOVE(8, 5); else if (L == 16) PAINTRL_MOVE(16, 5); else PAINTRL_MOVE(32, 5);
         } else {
             if (L == 8) PAINTRL_MOVE(8, 4); else if (L == 16) PAINTRL_MOVE(16, 4); else PAINTRL_MOVE(32, 4);
         }
@@ -819,13 +847,18 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     const bool staged = h->pk.n_words_pad <= kStageWords;
     const dim3 grid(blocks), block(kWarpsPerBlock * 32);
     cudaStream_t s = as_stream(stream);
+    const bool ax12 = h->pk.axis0 == 1 && h->pk.axis1 == 2;
+#define PAINTRL_PAINT(C, ST)                                                                                       \
+    do {                                                                                                           \
+        if (ax12) paint_kernel<C, ST, true><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);   \
+        else paint_kernel<C, ST, false><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);       \
+    } while (0)
     if (h->color == 0) {
-        if (staged) paint_kernel<0, true><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
-        else paint_kernel<0, false><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
+        if (staged) PAINTRL_PAINT(0, true); else PAINTRL_PAINT(0, false);
     } else {
-        if (staged) paint_kernel<1, true><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
-        else paint_kernel<1, false><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);
+        if (staged) PAINTRL_PAINT(1, true); else PAINTRL_PAINT(1, false);
     }
+#undef PAINTRL_PAINT
     return launch_check(h, "paint_kernel");
 }
 
@@ -900,7 +933,10 @@ int paintrl_stats(PaintrlHandle h, PaintrlStats *out) {
     CUDA_TRY(cudaMemcpy(host, h->stats, sizeof(host), cudaMemcpyDeviceToHost));
     out->episodes_ended = host[0];
     out->footprint_texels = host[1];
-    out->ray_full_scans = host[2];
+    out->ray_full_scans = host[2] & 0xffffffffull;
+    if (getenv("PAINTRL_DEBUG"))
+        fprintf(stderr, "[paintrl] rays: %llu full plane scans, %llu verify passes over %llu env-steps\n",
+                host[2] & 0xffffffffull, host[2] >> 32, host[3]);
     out->env_steps = host[3];
     out->kernel_launches = h->launches;
     return PAINTRL_OK;

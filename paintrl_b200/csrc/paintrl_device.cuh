@@ -70,8 +70,9 @@ static_assert(sizeof(EnvState) == 128, "EnvState must be one 128-byte line");
 // (robot.py:277-278) and how many off-part sub-steps it counted (robot.py:427-430).
 struct alignas(128) MoveOut {
     double centers[kPaintPerAction][3];
-    int32_t offpart_added;
-    int32_t full_scans;
+    int32_t counts;        // bits 0..3 off-part sub-steps added, 8..15 full plane scans, 16..23 verify passes
+    uint32_t miss_cache;   // the entering | exiting << 16 hull planes that decided the env's last full plane scan
+                           // (0xffff: none); kept from step to step, only ever used to prove misses
 };
 static_assert(sizeof(MoveOut) == 128, "MoveOut must be one 128-byte line");
 
@@ -186,6 +187,17 @@ __host__ __device__ __forceinline__ double npdot3(double x0, double x1, double x
 
 struct Vec3 { double x, y, z; };
 
+// Principal axes of the part.  Both reference parts use (1, 2): kernels instantiated with AX12 carry
+// them as compile-time constants, so component selections fold away.
+struct Ax { int a0, a1; };
+template <bool AX12>
+__device__ __forceinline__ Ax make_ax(int axis0, int axis1) {
+    Ax ax;
+    ax.a0 = AX12 ? 1 : axis0;
+    ax.a1 = AX12 ? 2 : axis1;
+    return ax;
+}
+
 __device__ __forceinline__ double comp(const Vec3 &v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
 __device__ __forceinline__ void add_comp(Vec3 &v, int a, double d) {
     if (a == 0) v.x += d; else if (a == 1) v.y += d; else v.z += d;
@@ -261,23 +273,47 @@ __device__ __forceinline__ Grp make_grp(int lane) {
     g.mask = (G == 32) ? kFull : (((1u << G) - 1u) << g.base);
     return g;
 }
+// max / min / sum over the group.  A full warp uses the REDUX unit on an order-preserving integer
+// key (two 32-bit steps per double); smaller groups use xor-shuffles.
+__device__ __forceinline__ double warp_min(double v) { return from_ordered_key(~warp_max_u64(~ordered_key(v))); }
+
 template <int G>
 __device__ __forceinline__ double grp_max(double v, const Grp &g) {
+    if constexpr (G == 32) {
+        return warp_max(v);
+    } else {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(g.mask, v, o));
-    return v;
+        for (int o = G / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(g.mask, v, o));
+        return v;
+    }
 }
 template <int G>
 __device__ __forceinline__ double grp_min(double v, const Grp &g) {
+    if constexpr (G == 32) {
+        return warp_min(v);
+    } else {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(g.mask, v, o));
-    return v;
+        for (int o = G / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(g.mask, v, o));
+        return v;
+    }
 }
 template <int G>
 __device__ __forceinline__ int grp_sum(int v, const Grp &g) {
+    if constexpr (G == 32) {
+        return __reduce_add_sync(kFull, v);
+    } else {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
-    return v;
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
+        return v;
+    }
+}
+template <int G>
+__device__ __forceinline__ bool grp_any(bool p, const Grp &g) {
+    return G == 32 ? __any_sync(kFull, p) : __any_sync(g.mask, p);
+}
+template <int G>
+__device__ __forceinline__ unsigned grp_ballot(bool p, const Grp &g) {   // bit i = lane i of the group
+    return G == 32 ? __ballot_sync(kFull, p) : ((__ballot_sync(g.mask, p) & g.mask) >> g.base);
 }
 
 // One pass of the slab test over a list of planes (`planes` = two double2 per plane: the plane table
@@ -285,13 +321,49 @@ __device__ __forceinline__ int grp_sum(int v, const Grp &g) {
 // order-independent so the result equals the serial one.
 struct SlabResult { double t_in, t_out; bool outside; };
 
-template <int G>
+template <int G, bool TRACK = false>
 __device__ __forceinline__ SlabResult slab_pass(const double2 *planes, int n, const Vec3 &frm, double d0, double d1, double d2,
-                                                const Grp &g) {
+                                                const Grp &g, unsigned *args = nullptr) {
     double t_in = -INFINITY, t_out = INFINITY;
     bool outside = false;
+    int a_in = 0xffff, a_out = 0xffff;   // TRACK: list positions attaining this lane's t_in / t_out
     for (int i = g.gl; i < n; i += G) {
         const double2 lo = __ldg(planes + 2 * i), hi2 = __ldg(planes + 2 * i + 1);
+        double den = (lo.x * d0 + lo.y * d1) + hi2.x * d2;
+        double num = hi2.y - ((lo.x * frm.x + lo.y * frm.y) + hi2.x * frm.z);
+        if (den == 0.0) {
+            if (num < 0.0) outside = true;
+        } else {
+            double t = num / den;
+            if (den < 0.0) { if (TRACK && t > t_in) a_in = i; t_in = fmax(t_in, t); }
+            else { if (TRACK && t < t_out) a_out = i; t_out = fmin(t_out, t); }
+        }
+    }
+    SlabResult r;
+    r.t_in = grp_max<G>(t_in, g);
+    r.t_out = grp_min<G>(t_out, g);
+    r.outside = grp_any<G>(outside, g);
+    if (TRACK) {
+        const unsigned m_in = grp_ballot<G>(t_in == r.t_in && a_in != 0xffff, g), m_out = grp_ballot<G>(t_out == r.t_out && a_out != 0xffff, g);
+        const int w_in = m_in ? __shfl_sync(g.mask, a_in, g.base + __ffs(m_in) - 1) : 0xffff;
+        const int w_out = m_out ? __shfl_sync(g.mask, a_out, g.base + __ffs(m_out) - 1) : 0xffff;
+        *args = (unsigned)min(w_in, 0xffff) | ((unsigned)min(w_out, 0xffff) << 16);
+    }
+    return r;
+}
+
+// Does the pair of hull planes `cache` (entering | exiting << 16), together with the bounds of a
+// subset already scanned, prove that the ray misses the hull?  (Any subset may be used for that.)
+__device__ __forceinline__ bool pair_proves_miss(const DevPack &pk, unsigned cache, const SlabResult &r0, bool have_r0, const Vec3 &frm,
+                                                 double d0, double d1, double d2) {
+    double t_in = have_r0 ? r0.t_in : -INFINITY, t_out = have_r0 ? r0.t_out : INFINITY;
+    bool outside = false;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int pi = (int)((cache >> (16 * k)) & 0xffffu);
+        if (pi >= pk.n_planes) continue;
+        const double2 *p2 = reinterpret_cast<const double2 *>(pk.planes) + 2 * pi;
+        const double2 lo = __ldg(p2), hi2 = __ldg(p2 + 1);
         double den = (lo.x * d0 + lo.y * d1) + hi2.x * d2;
         double num = hi2.y - ((lo.x * frm.x + lo.y * frm.y) + hi2.x * frm.z);
         if (den == 0.0) {
@@ -302,11 +374,7 @@ __device__ __forceinline__ SlabResult slab_pass(const double2 *planes, int n, co
             else t_out = fmin(t_out, t);
         }
     }
-    SlabResult r;
-    r.t_in = grp_max<G>(t_in, g);
-    r.t_out = grp_min<G>(t_out, g);
-    r.outside = __any_sync(g.mask, outside);
-    return r;
+    return outside || t_in > t_out || t_in > 1.0 || t_out < 0.0;
 }
 
 // Number of listed planes the point h does not satisfy with margin (n.h - off > -kVerifyMargin).
@@ -327,6 +395,28 @@ __device__ __forceinline__ int near_violations(const double2 *planes, int n, con
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// debug (instrumented build only): rays that left the fast path, for offline analysis of the move cells
+#ifdef PAINTRL_PROFILE
+__device__ unsigned long long g_dbg_counts[4];   // [0] grid searches  [1] rays logged
+__device__ double g_dbg_rays[4096][8];           // frm.xyz, d.xyz, kind (1 verify ok, 2 full scan), hit flag
+#endif
+__device__ __forceinline__ void g_dbg_grid_searches_inc() {
+#ifdef PAINTRL_PROFILE
+    atomicAdd(&g_dbg_counts[0], 1ull);
+#endif
+}
+__device__ __forceinline__ void g_dbg_log_ray(const Vec3 &frm, double d0, double d1, double d2, int kind, bool hit, bool leader) {
+#ifdef PAINTRL_PROFILE
+    if (leader) {
+        unsigned long long i = atomicAdd(&g_dbg_counts[1], 1ull);
+        if (i < 4096) {
+            double *o = g_dbg_rays[i];
+            o[0] = frm.x; o[1] = frm.y; o[2] = frm.z; o[3] = d0; o[4] = d1; o[5] = d2; o[6] = kind; o[7] = hit ? 1.0 : 0.0;
+        }
+    }
+#endif
+}
+
 // Exact slab test of the ray frm -> to against the hull half-spaces (shim S1).
 //
 // For any subset S of the planes t_in(S) <= t_in and t_out(S) >= t_out, so
@@ -342,23 +432,35 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 // candidates; `vc0` / `vc1` hold this lane's first candidate), else ref.blob == nullptr.
 // (pf0, pf1): expected displacement of the next ray along the principal axes -- its cell's blob is
 // prefetched into L1 while this ray is being tested (do_prefetch).
+constexpr int kRayAttempts = 3;
+
+// Region test of a move cell: does the point h (principal coordinates h0, h1) lie in the cell
+// (cx, cy) and within the slab around its fitted surface plane?
+__device__ __forceinline__ bool in_cell_region(const DevPack &pk, const Vec3 &h, double h0, double h1, double depth, int cx, int cy,
+                                               const double2 &abv, const double2 &clv, const double2 &hpv) {
+    const int hx = (int)floor((h0 - pk.mc_o0) * pk.mc_inv);
+    const int hy = (int)floor((h1 - pk.mc_o1) * pk.mc_inv);
+    const double resid = depth - (abv.x + abv.y * h0 + clv.x * h1);
+    return hx == cx && hy == cy && resid >= clv.y && resid <= hpv.x;
+}
+
 template <int G>
-__device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, const Vec3 &to, const Grp &grp, Vec3 &hit,
-                                         CellRef &ref, double2 &vc0, double2 &vc1, int &full_scans, double pf0, double pf1,
-                                         bool do_prefetch PAINTRL_PROF_PARAM) {
+__device__ __forceinline__ bool ray_test(const DevPack &pk, const Ax &ax, const Vec3 &frm, const Vec3 &to, const Grp &grp, Vec3 &hit,
+                                         CellRef &ref, double2 &vc0, double2 &vc1, int &counts, unsigned &miss_cache, double pf0,
+                                         double pf1, bool do_prefetch PAINTRL_PROF_PARAM) {
     double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
     SlabResult r;
     bool accepted = false, candidate = false;
     const double2 *sub = nullptr;
     int n_sub = 0;
     ref.blob = nullptr;
-    const int npax = 3 - pk.axis0 - pk.axis1;
-    // the TCP hovers kHookDistance above the surface: first guess = the point that far along the ray
-    Vec3 g = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
-    Vec3 h = g;
+    const int npax = 3 - ax.a0 - ax.a1;
+    // the TCP hovers kHookDistance above the surface: first guess = the point that far along the ray;
+    // later guesses = the entry point of the previous cell's list
+    Vec3 h = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
 #pragma unroll 1
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        const double g0 = comp(g, pk.axis0), g1 = comp(g, pk.axis1);
+    for (int attempt = 0; attempt < kRayAttempts; ++attempt) {
+        const double g0 = comp(h, ax.a0), g1 = comp(h, ax.a1);
         int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
         int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
         if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) break;
@@ -379,7 +481,8 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, con
                 const uint2 pe = __ldg(&pk.mc_entry[py * pk.mc_nx + px]);
                 const int sectors = 2 + (int)(pe.y & 0xffffu) + (int)(pe.y >> 16);
                 const char *pb = reinterpret_cast<const char *>(pk.mc_blob + (size_t)pe.x * 2);
-                for (int o = grp.gl * 128; o < sectors * 32; o += G * 128) prefetch_l1(pb + o);
+                if (G == 32) { if (grp.gl * 128 < sectors * 32) prefetch_l1(pb + grp.gl * 128); }
+                else for (int o = grp.gl * 128; o < sectors * 32; o += G * 128) prefetch_l1(pb + o);
             }
         }
         PAINTRL_PROF(6, grp.gl == 0);
@@ -391,28 +494,50 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, con
         candidate = true;
         sub = blob + 4; n_sub = n_planes;
         h.x = frm.x + d0 * r.t_in; h.y = frm.y + d1 * r.t_in; h.z = frm.z + d2 * r.t_in;
-        const double h0 = comp(h, pk.axis0), h1 = comp(h, pk.axis1);
-        int hx = (int)floor((h0 - pk.mc_o0) * pk.mc_inv);
-        int hy = (int)floor((h1 - pk.mc_o1) * pk.mc_inv);
-        const double resid = comp(h, npax) - (abv.x + abv.y * h0 + clv.x * h1);
-        if (hx == cx && hy == cy && resid >= clv.y && resid <= hpv.x) {                     // (2a)
+        if (in_cell_region(pk, h, comp(h, ax.a0), comp(h, ax.a1), comp(h, npax), cx, cy, abv, clv, hpv)) {   // (2a)
             accepted = true;
             ref.blob = blob; ref.n_planes = n_planes; ref.n_verts = n_verts;
             break;
         }
-        g = h;
     }
     PAINTRL_PROF(8, grp.gl == 0);
+    if (!accepted) {
+        // (1) again with the pair of planes that decided this environment's last full scan
+        if (pair_proves_miss(pk, miss_cache, r, candidate, frm, d0, d1, d2)) return false;
+    }
     if (!accepted && candidate) {                                                           // (2b)
+        counts += 1 << 16;
         const int c_all = near_violations<G>(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, h, grp);
         const int c_sub = near_violations<G>(sub, n_sub, h, grp);
         accepted = (c_all == c_sub);
+        if (accepted && r.t_in <= r.t_out && 0.0 <= r.t_in && r.t_in <= 1.0) {
+            // a hit: if it lies in the region of its own cell, that cell's vertex candidates apply
+            const double h0 = comp(h, ax.a0), h1 = comp(h, ax.a1);
+            const int cx = (int)floor((h0 - pk.mc_o0) * pk.mc_inv), cy = (int)floor((h1 - pk.mc_o1) * pk.mc_inv);
+            if (cx >= 0 && cy >= 0 && cx < pk.mc_nx && cy < pk.mc_ny) {
+                const uint2 entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+                const int n_planes = (int)(entry.y & 0xffffu), n_verts = (int)(entry.y >> 16);
+                const double2 *blob = pk.mc_blob + (size_t)entry.x * 2;
+                const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);
+                if (n_verts > 0 && in_cell_region(pk, h, h0, h1, comp(h, npax), cx, cy, abv, clv, hpv)) {
+                    ref.blob = blob; ref.n_planes = n_planes; ref.n_verts = n_verts;
+                    if (grp.gl < n_verts) {
+                        vc0 = __ldg(blob + 2 * (2 + n_planes + grp.gl));
+                        vc1 = __ldg(blob + 2 * (2 + n_planes + grp.gl) + 1);
+                    }
+                }
+            }
+        }
     }
     if (!accepted) {
-        r = slab_pass<G>(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, frm, d0, d1, d2, grp);
-        full_scans += 1;
+        unsigned args = 0xffffffffu;
+        r = slab_pass<G, true>(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, frm, d0, d1, d2, grp, &args);
+        miss_cache = args;
+        counts += 1 << 8;
     }
-    if (r.outside || !(r.t_in <= r.t_out && 0.0 <= r.t_in && r.t_in <= 1.0)) return false;
+    const bool is_hit = !(r.outside || !(r.t_in <= r.t_out && 0.0 <= r.t_in && r.t_in <= 1.0));
+    if (!ref.blob) g_dbg_log_ray(frm, d0, d1, d2, accepted ? 1 : 2, is_hit, grp.gl == 0);
+    if (!is_hit) return false;
     hit.x = frm.x + d0 * r.t_in;
     hit.y = frm.y + d1 * r.t_in;
     hit.z = frm.z + d2 * r.t_in;
@@ -421,13 +546,27 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Vec3 &frm, con
 }
 
 // Lexicographic arg-min of (squared distance, vertex id) over the group; `rec` travels with it.
+// d >= 0, so its raw bits order like its value.
 template <int G>
 __device__ __forceinline__ void grp_argmin(double &d, unsigned &id, unsigned &rec, const Grp &g) {
+    if constexpr (G == 32) {
+        const unsigned long long k = (unsigned long long)__double_as_longlong(d);
+        const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+        const unsigned mhi = __reduce_min_sync(kFull, hi);
+        const unsigned mlo = __reduce_min_sync(kFull, hi == mhi ? lo : 0xffffffffu);
+        const bool best = (hi == mhi && lo == mlo);
+        const unsigned mid = __reduce_min_sync(kFull, best ? id : 0xffffffffu);
+        const int src = __ffs(__ballot_sync(kFull, best && id == mid)) - 1;
+        rec = __shfl_sync(kFull, rec, src);
+        id = mid;
+        d = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+    } else {
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(g.mask, d, o);
-        const unsigned oi = __shfl_xor_sync(g.mask, id, o), orc = __shfl_xor_sync(g.mask, rec, o);
-        if (od < d || (od == d && oi < id)) { d = od; id = oi; rec = orc; }
+        for (int o = G / 2; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(g.mask, d, o);
+            const unsigned oi = __shfl_xor_sync(g.mask, id, o), orc = __shfl_xor_sync(g.mask, rec, o);
+            if (od < d || (od == d && oi < id)) { d = od; id = oi; rec = orc; }
+        }
     }
 }
 
@@ -457,8 +596,8 @@ __device__ __forceinline__ unsigned nearest_vertex_cell(const Vec3 &p, const Cel
 
 // Slow path (point outside every accepted cell region): grid search over (axis0, axis1) with ring expansion.
 template <int G>
-__device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const Vec3 &p, const Grp &g) {
-    double q0 = comp(p, pk.axis0), q1 = comp(p, pk.axis1);
+__device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const Ax &ax, const Vec3 &p, const Grp &g) {
+    double q0 = comp(p, ax.a0), q1 = comp(p, ax.a1);
     int cx = (int)floor((q0 - pk.vg_o0) * pk.vg_inv);
     int cy = (int)floor((q1 - pk.vg_o1) * pk.vg_inv);
     cx = min(max(cx, 0), pk.vg_nx - 1);
@@ -502,9 +641,10 @@ __device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const
 // incident front triangles of the nearest vertex, one per lane of the group.  Returns the picked
 // triangle's record (whose tail holds n, quat_from_normal(-n) and the shot-centre offset), or nullptr.
 template <int G>
-__device__ __forceinline__ const double *hook_triangle(const DevPack &pk, const Vec3 &point, const CellRef &ref, double2 vc0,
+__device__ __forceinline__ const double *hook_triangle(const DevPack &pk, const Ax &ax, const Vec3 &point, const CellRef &ref, double2 vc0,
                                                        double2 vc1, const Grp &g PAINTRL_PROF_PARAM) {
-    unsigned rec = ref.blob ? nearest_vertex_cell<G>(point, ref, vc0, vc1, g) : nearest_vertex_grid<G>(pk, point, g);
+    unsigned rec = ref.blob ? nearest_vertex_cell<G>(point, ref, vc0, vc1, g) : nearest_vertex_grid<G>(pk, ax, point, g);
+    if (!ref.blob) g_dbg_grid_searches_inc();
     PAINTRL_PROF(10, g.gl == 0);
     if (rec == 0xFFFFFFFFu) return nullptr;
     const int deg = (int)(rec & 0xffu);
@@ -533,11 +673,11 @@ __device__ __forceinline__ const double *hook_triangle(const DevPack &pk, const 
             inside = (0.0 <= bu && bu <= 1.0 && 0.0 <= bv && bv <= 1.0 && 0.0 <= bw && bw <= 1.0);
             m = fmin(fmin(bu, bv), bw);
         }
-        unsigned in_mask = (__ballot_sync(g.mask, inside) & g.mask) >> g.base;
+        unsigned in_mask = grp_ballot<G>(inside, g);
         if (in_mask) { pick = b0 + __ffs(in_mask) - 1; break; }
         double cm = grp_max<G>(m, g);
         if (cm >= run_max) {   // `>=`: a later triangle wins ties (bullet_paint_wrapper.py:520)
-            unsigned eq = (__ballot_sync(g.mask, k < deg && m == cm) & g.mask) >> g.base;
+            unsigned eq = grp_ballot<G>(k < deg && m == cm, g);
             run_max = cm;
             run_arg = b0 + 31 - __clz(eq);
         }
@@ -558,9 +698,9 @@ __device__ __forceinline__ int grid_index_2(const DevPack &pk, double v) {
 __device__ __forceinline__ double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
 
 // bullet_paint_wrapper.py:965-978
-__device__ __forceinline__ void normalized_pose(const DevPack &pk, const Vec3 &pose, double &a1, double &a2) {
+__device__ __forceinline__ void normalized_pose(const DevPack &pk, const Ax &ax, const Vec3 &pose, double &a1, double &a2) {
     const double radius = kPaintRadius;
-    double axis1_real = comp(pose, pk.axis0), axis2_real = comp(pose, pk.axis1);
+    double axis1_real = comp(pose, ax.a0), axis2_real = comp(pose, ax.a1);
     double axis2_in = (axis2_real - pk.range1_min + radius) / (pk.range1_max - pk.range1_min + 2 * radius);
     int gi = grid_index_2(pk, axis2_real);
     double lo = __ldg(&pk.grid_lo[gi]), hi = __ldg(&pk.grid_hi[gi]);

@@ -133,9 +133,9 @@ __device__ __forceinline__ const double *axis_table(const DevPack &pk, int a) {
 // and the TCP (here), so texels of lower cells are < p0, those of higher cells are > p0, and only
 // the TCP's own cell of each row is compared value by value.
 template <typename WS>
-__device__ __forceinline__ void row_ranks(const DevPack &pk, double p0, int lane, WS &ws) {
+__device__ __forceinline__ void row_ranks(const DevPack &pk, const Ax &ax, double p0, int lane, WS &ws) {
     const double f = floor((p0 - pk.cx_o0) * pk.cx_inv);
-    const double *kx = axis_table(pk, pk.axis0);
+    const double *kx = axis_table(pk, ax.a0);
     for (int r = lane; r < pk.n_rows; r += 32) {
         const int n = __ldg(&pk.row_count[r]);
         int L, U;
@@ -176,11 +176,11 @@ __device__ __forceinline__ int pose_row(const DevPack &pk, double p1) {
 // position - TCP position along the principal axes; skipped if both are 0; sector 0 if rx>0,ry>0,
 // 1 if rx<0,ry>0, 2 if rx<0,ry<0, else 3; obs[s] = #(status != 255) / #texels of the sector.
 template <typename WS, typename BITS>
-__device__ __forceinline__ void section4_counts(const DevPack &pk, const BITS &bits, const Vec3 &pose, int lane, WS &ws,
+__device__ __forceinline__ void section4_counts(const DevPack &pk, const Ax &ax, const BITS &bits, const Vec3 &pose, int lane, WS &ws,
                                                 int tot[4], int open[4], bool ranks_ready PAINTRL_PROF_PARAM) {
-    const double p0 = comp(pose, pk.axis0), p1 = comp(pose, pk.axis1);
+    const double p0 = comp(pose, ax.a0), p1 = comp(pose, ax.a1);
     PAINTRL_PROF(21, lane == 0);
-    if (!ranks_ready) row_ranks(pk, p0, lane, ws);
+    if (!ranks_ready) row_ranks(pk, ax, p0, lane, ws);
     PAINTRL_PROF(22, lane == 0);
     const int prow = pose_row(pk, p1);
     const bool init_painted = (pk.status_init == kPainted);
@@ -217,7 +217,7 @@ __device__ __forceinline__ void section4_counts(const DevPack &pk, const BITS &b
     if (prow >= 0 && prow < pk.n_rows) {
         const int w0 = __ldg(&pk.row_word0[prow]), w1 = __ldg(&pk.row_word0[prow + 1]);
         const int n = __ldg(&pk.row_count[prow]), L = ws.rowL[prow], U = ws.rowU[prow];
-        const double *ky = axis_table(pk, pk.axis1) + (size_t)w0 * 32 + lane;
+        const double *ky = axis_table(pk, ax.a1) + (size_t)w0 * 32 + lane;
         int u0 = 0, u1 = 0, u2 = 0, u3 = 0, v0 = 0, v1 = 0, v2 = 0, v3 = 0;
 #pragma unroll 2
         for (int wi = 0; wi < w1 - w0; ++wi) {
@@ -243,12 +243,12 @@ __device__ __forceinline__ void section4_counts(const DevPack &pk, const BITS &b
 
 // Section observation with K != 4 sectors (atan2 path, bullet_paint_wrapper.py:1026-1031): full scan.
 template <typename BITS>
-__device__ __forceinline__ void sectionk_counts(const DevPack &pk, const BITS &bits, const Vec3 &pose, int section,
+__device__ __forceinline__ void sectionk_counts(const DevPack &pk, const Ax &ax, const BITS &bits, const Vec3 &pose, int section,
                                                 int lane, int *hist /*[2*kMaxObs] smem*/) {
     for (int i = lane; i < 2 * kMaxObs; i += 32) hist[i] = 0;
     __syncwarp();
-    const double p0 = comp(pose, pk.axis0), p1 = comp(pose, pk.axis1);
-    const double *c0 = axis_table(pk, pk.axis0), *c1 = axis_table(pk, pk.axis1);
+    const double p0 = comp(pose, ax.a0), p1 = comp(pose, ax.a1);
+    const double *c0 = axis_table(pk, ax.a0), *c1 = axis_table(pk, ax.a1);
     const double basis = 2 * kPi / section;
     const bool init_painted = (pk.status_init == kPainted);
     for (int w = 0; w < pk.n_words; ++w) {
@@ -269,11 +269,11 @@ __device__ __forceinline__ void sectionk_counts(const DevPack &pk, const BITS &b
 
 // robot_gym_env.py:306-319 _augmented_observation; every lane returns, lanes < obs_dim write.
 template <typename WS, typename BITS>
-__device__ __forceinline__ void write_observation(const DevPack &pk, const DevConfig &cfg, const BITS &bits,
+__device__ __forceinline__ void write_observation(const DevPack &pk, const Ax &ax, const DevConfig &cfg, const BITS &bits,
                                                   const unsigned *grid_cnt, const Vec3 &pose, int lane, WS &ws,
                                                   double *obs_a, double *obs_b PAINTRL_PROF_PARAM) {
     double a1, a2;
-    normalized_pose(pk, pose, a1, a2);
+    normalized_pose(pk, ax, pose, a1, a2);
     const int grad = cfg.obs_grad;
     if (cfg.obs_mode == 2) {   // simple
         if (lane < 2) {
@@ -299,7 +299,7 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const DevCo
     // section / discrete
     if (grad == 4) {
         int tot[4], open[4];
-        section4_counts(pk, bits, pose, lane, ws, tot, open, false PAINTRL_PROF_PASS);
+        section4_counts(pk, ax, bits, pose, lane, ws, tot, open, false PAINTRL_PROF_PASS);
         if (lane < 4) {
             int t = lane == 0 ? tot[0] : (lane == 1 ? tot[1] : (lane == 2 ? tot[2] : tot[3]));
             int o = lane == 0 ? open[0] : (lane == 1 ? open[1] : (lane == 2 ? open[2] : open[3]));
@@ -309,7 +309,7 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const DevCo
         }
     } else {
         int *hist = ws.rowWa;   // rowWa / rowWn are contiguous and free once the stamp is done
-        sectionk_counts(pk, bits, pose, grad, lane, hist);
+        sectionk_counts(pk, ax, bits, pose, grad, lane, hist);
         for (int s = lane; s < grad; s += 32) {
             int t = hist[s], o = hist[kMaxObs + s];
             double v = t == 0 ? 0.0 : (double)o / (double)t;
@@ -522,19 +522,19 @@ __device__ __forceinline__ int stamp_ranges(const DevPack &pk, float lo0, float 
 // Calls body(w) warp-uniformly for every candidate word.
 template <bool STAGED, typename WS, typename BodyFn>
 __device__ __forceinline__ void for_each_stamp_word(const DevPack &pk, int lane, const WS &ws, int n_cand, BodyFn body) {
-    if (STAGED) {
+    if constexpr (STAGED) {
         for (int k = 0; k < n_cand; ++k) body((int)ws.cand[k]);
-        return;
-    }
-    for (int r0 = 0; r0 < pk.n_rows; r0 += 32) {
-        const int r = r0 + lane;
-        const int wa = r < pk.n_rows ? ws.rowWa[r] : 0, wn = r < pk.n_rows ? ws.rowWn[r] : 0;
-        unsigned m = __ballot_sync(kFull, wn > 0);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const int a = __shfl_sync(kFull, wa, src), n = __shfl_sync(kFull, wn, src);
-            for (int w = a; w < a + n; ++w) body(w);
+    } else {
+        for (int r0 = 0; r0 < pk.n_rows; r0 += 32) {
+            const int r = r0 + lane;
+            const int wa = r < pk.n_rows ? ws.rowWa[r] : 0, wn = r < pk.n_rows ? ws.rowWn[r] : 0;
+            unsigned m = __ballot_sync(kFull, wn > 0);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int a = __shfl_sync(kFull, wa, src), n = __shfl_sync(kFull, wn, src);
+                for (int w = a; w < a + n; ++w) body(w);
+            }
         }
     }
 }
@@ -542,7 +542,7 @@ __device__ __forceinline__ void for_each_stamp_word(const DevPack &pk, int lane,
 // Returns (warp-uniform) the newly painted count (RGB) / removed thickness units (HSI), the
 // |union of valid pixels| of robot.py:425 and whether any flip bit changed.
 template <int COLOR, bool STAGED, typename WS, typename BITS>
-__device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16_t *thick, unsigned *grid_cnt, bool has_last,
+__device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BITS &bits, int16_t *thick, unsigned *grid_cnt, bool has_last,
                                       int lane, WS &ws, int &n_new_out, int &n_possible_out, bool &dirty_out PAINTRL_PROF_PARAM) {
     ShotsF c;
 #pragma unroll
@@ -554,8 +554,8 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16
     float lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        const float c0 = pk.axis0 == 0 ? c.x[s] : (pk.axis0 == 1 ? c.y[s] : c.z[s]);
-        const float c1 = pk.axis1 == 0 ? c.x[s] : (pk.axis1 == 1 ? c.y[s] : c.z[s]);
+        const float c0 = ax.a0 == 0 ? c.x[s] : (ax.a0 == 1 ? c.y[s] : c.z[s]);
+        const float c1 = ax.a1 == 0 ? c.x[s] : (ax.a1 == 1 ? c.y[s] : c.z[s]);
         lo0 = fminf(lo0, c0); hi0 = fmaxf(hi0, c0);
         lo1 = fminf(lo1, c1); hi1 = fmaxf(hi1, c1);
     }
@@ -651,9 +651,10 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const BITS &bits, int16
 // ------------------------------------------------------------------------------ kernels
 // Robot._get_actions (robot.py:302-329): action -> direction, five guided sub-steps.
 // G lanes per environment (the plane / vertex / triangle lists of a sub-step are short).
-template <int G, int MINB>
+template <int G, int MINB, bool AX12>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *actions) {
+    const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
     const int lane = threadIdx.x & 31;
     const int env = (blockIdx.x * (kWarpsPerBlock * 32) + threadIdx.x) / G;
     if (env >= num_envs) return;
@@ -703,23 +704,24 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
     Vec3 cur_n = tcp_orn_norm(cur_p, quat);
     const double delta1 = delta_axis1 / kPaintPerAction, delta2 = delta_axis2 / kPaintPerAction;
     const double delta2_scaled = delta2 * pk.lwr;
-    int full_scans = 0;
+    int counts = 0;                                  // bits 8..15 full plane scans, 16..23 verify passes
+    unsigned miss_cache = ea.moves[env].miss_cache;
     bool miss_quat_valid = false;   // quat == quat_from_normal(cur_n) from an earlier miss of this step
     double *centers = &ea.moves[env].centers[0][0];
 #pragma unroll 1
     for (int s = 0; s < kPaintPerAction; ++s) {
         Vec3 p = cur_p;
-        add_comp(p, pk.axis0, delta1);
-        add_comp(p, pk.axis1, delta2_scaled);
+        add_comp(p, ax.a0, delta1);
+        add_comp(p, ax.a1, delta2_scaled);
         Vec3 end = {p.x + cur_n.x, p.y + cur_n.y, p.z + cur_n.z};
         Vec3 hit, pos, center;
         CellRef ref;
         double2 vc0 = make_double2(0.0, 0.0), vc1 = vc0;
         const double *rec = nullptr;
         PAINTRL_PROF(s == 0 ? 0 : 1, grp.gl == 0);
-        if (ray_test<G>(pk, p, end, grp, hit, ref, vc0, vc1, full_scans, delta1, delta2_scaled,
+        if (ray_test<G>(pk, ax, p, end, grp, hit, ref, vc0, vc1, counts, miss_cache, delta1, delta2_scaled,
                         s + 1 < kPaintPerAction PAINTRL_PROF_PASS))
-            rec = hook_triangle<G>(pk, hit, ref, vc0, vc1, grp PAINTRL_PROF_PASS);
+            rec = hook_triangle<G>(pk, ax, hit, ref, vc0, vc1, grp PAINTRL_PROF_PASS);
         PAINTRL_PROF(11, grp.gl == 0);
         if (rec) {
             // pose = hit + 0.1 n, orn = -n (bullet_paint_wrapper.py:529-530); quaternion and shot-centre
@@ -759,8 +761,8 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
         reinterpret_cast<double2 *>(&gst->last_angle)[0] = make_double2(new_angle, angle_diff);
         gst->term_counter = term_counter;
         gst->flags = flags;
-        ea.moves[env].offpart_added = term_counter - counter_before;
-        ea.moves[env].full_scans = full_scans;
+        ea.moves[env].counts = counts | (term_counter - counter_before);
+        ea.moves[env].miss_cache = miss_cache;
     }
     PAINTRL_PROF(13, grp.gl == 0);
 }
@@ -768,9 +770,10 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
 // Everything after the move: stamp, score, observe, auto-reset.  The environment's record, the
 // move kernel's output and (STAGED) its flip bits come in through one TMA bulk-copy group per warp
 // and the bits go back the same way.
-template <int COLOR, bool STAGED>
+template <int COLOR, bool STAGED, bool AX12>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, STAGED ? 7 : 4)
 paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
+    const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
     typedef WarpScratch<STAGED> WS;
     __shared__ WS scratch[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -798,11 +801,11 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     // looked up before the stamp and the TCP row's axis1 keys are prefetched into L1 meanwhile
     const bool fast4 = (cfg.obs_mode == 0 || cfg.obs_mode == 3) && cfg.obs_grad == 4;
     if (fast4) {
-        row_ranks(pk, comp(cur_p, pk.axis0), lane, ws);
-        const int prow = pose_row(pk, comp(cur_p, pk.axis1));
+        row_ranks(pk, ax, comp(cur_p, ax.a0), lane, ws);
+        const int prow = pose_row(pk, comp(cur_p, ax.a1));
         if (prow >= 0 && prow < pk.n_rows) {
             const int w0 = __ldg(&pk.row_word0[prow]), w1 = __ldg(&pk.row_word0[prow + 1]);
-            const char *ky = reinterpret_cast<const char *>(axis_table(pk, pk.axis1) + (size_t)w0 * 32);
+            const char *ky = reinterpret_cast<const char *>(axis_table(pk, ax.a1) + (size_t)w0 * 32);
             for (int k = lane; k < 2 * (w1 - w0); k += 32) prefetch_l1(ky + (size_t)k * 128);
         }
     }
@@ -812,7 +815,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     const bool has_last = (st.flags & kFlagHasLast) != 0;
     int n_new, n_possible;
     bool dirty;
-    stamp<COLOR, STAGED>(pk, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible, dirty PAINTRL_PROF_PASS);
+    stamp<COLOR, STAGED>(pk, ax, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible, dirty PAINTRL_PROF_PASS);
     PAINTRL_PROF(19, lane == 0);
 
     // ---- robot.py:425-433, robot_gym_env.py:321-340 (every lane ends up with the same scalars).
@@ -820,12 +823,12 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     // each is evaluated by one lane, all in the same instruction, and broadcast.
     int flags = st.flags | kFlagHasLast;
     const double succeeded = (COLOR == 0) ? (double)n_new : (double)n_new / 255.0;
-    if (ws.mv.offpart_added >= kPaintPerAction && n_possible == 0) flags |= kFlagTerminate;
+    if ((ws.mv.counts & 0xf) >= kPaintPerAction && n_possible == 0) flags |= kFlagTerminate;
     const double radius = kPaintRadius;
-    const double axis1_real = comp(cur_p, pk.axis0), axis2_real = comp(cur_p, pk.axis1);
+    const double axis1_real = comp(cur_p, ax.a0), axis2_real = comp(cur_p, ax.a1);
     double rate, reward, turn, axis2_in, rel;
     {
-        double num = succeeded, den = (double)n_possible;                       // lane 0: rate (robot.py:426)
+        double num = succeeded, den = n_possible ? (double)n_possible : 1.0;    // lane 0: rate (robot.py:426)
         if (lane == 1) den = 100.0;                                             // reward (robot_gym_env.py:322)
         if (lane == 2) { num = st.angle_diff; den = kPi; }                      // turning penalty (:338)
         if (lane == 3) { num = axis2_real - pk.range1_min + radius; den = pk.range1_max - pk.range1_min + 2 * radius; }   // bullet_paint_wrapper.py:969
@@ -854,7 +857,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
 
     // ---- observation counts (robot_gym_env.py:358: computed even when done)
     int tot[4] = {0, 0, 0, 0}, open[4] = {0, 0, 0, 0};
-    if (fast4) section4_counts(pk, bits, cur_p, lane, ws, tot, open, true PAINTRL_PROF_PASS);
+    if (fast4) section4_counts(pk, ax, bits, cur_p, lane, ws, tot, open, true PAINTRL_PROF_PASS);
 
     // ---- second round of divisions: average reward (robot_gym_env.py:295), axis1 of the normalised pose, sector ratios
     double avg_reward, axis1_in, ratio;
@@ -865,7 +868,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
         if (lane >= 2 && lane < 6) {
             t = lane == 2 ? tot[0] : (lane == 3 ? tot[1] : (lane == 4 ? tot[2] : tot[3]));
             o = lane == 2 ? open[0] : (lane == 3 ? open[1] : (lane == 4 ? open[2] : open[3]));
-            num = (double)o; den = (double)t;
+            num = (double)o; den = t ? (double)t : 1.0;
         }
         const double q = num / den;
         ratio = t == 0 ? 0.0 : q;                        // lanes 2..5: sector s = lane - 2 (bullet_paint_wrapper.py:1057-1060)
@@ -906,7 +909,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
             }
         }
     } else {
-        write_observation(pk, cfg, bits, grid_cnt, cur_p, lane, ws, obs, next_obs PAINTRL_PROF_PASS);
+        write_observation(pk, ax, cfg, bits, grid_cnt, cur_p, lane, ws, obs, next_obs PAINTRL_PROF_PASS);
     }
     if (io.next_obs) next_obs = io.next_obs + (size_t)env * cfg.obs_dim;
     __syncwarp();
@@ -920,7 +923,8 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
         EnvStat *es = &ea.env_stats[env];       // no other thread touches this record: plain reductions, no return value
         if (done) atomicAdd(&es->episodes_ended, 1ull);
         if (n_possible) atomicAdd(&es->footprint_texels, (unsigned long long)n_possible);
-        if (ws.mv.full_scans) atomicAdd(&es->full_scans, (unsigned long long)ws.mv.full_scans);
+        if (ws.mv.counts >> 8)   // full plane scans in the low half of the counter, verify passes in the high half
+            atomicAdd(&es->full_scans, (unsigned long long)((ws.mv.counts >> 8) & 0xff) | ((unsigned long long)((ws.mv.counts >> 16) & 0xff) << 32));
         atomicAdd(&es->env_steps, 1ull);
         // the record
         st.last_center[0] = ws.mv.centers[NS - 1][0];
@@ -958,6 +962,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, const int32_t *env_ids, int n, const int32_t *start_idx,
              const double *set_pos, const double *set_normal, double *obs_out, int mode /*0 reset, 1 set_pose*/) {
+    const Ax ax = make_ax<false>(pk.axis0, pk.axis1);
     __shared__ WarpScratch<false> scratch[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = blockIdx.x * kWarpsPerBlock + warp;
@@ -979,7 +984,7 @@ reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, const int32_t *env_ids, in
     const Bits<false> bits = {gbits, nullptr};
     Vec3 pose = {st.pose[0], st.pose[1], st.pose[2]};
     PAINTRL_PROF_BEGIN
-    write_observation(pk, cfg, bits, grid_cnt, pose, lane, scratch[warp], obs_out ? obs_out + (size_t)k * cfg.obs_dim : nullptr,
+    write_observation(pk, ax, cfg, bits, grid_cnt, pose, lane, scratch[warp], obs_out ? obs_out + (size_t)k * cfg.obs_dim : nullptr,
                       nullptr PAINTRL_PROF_PASS);
     store_state(&ea.states[env], st, lane);
 }
@@ -988,6 +993,7 @@ reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, const int32_t *env_ids, in
 // copies it instead of scanning the cleared planes again).  `zero_bits` / `grid_cnt` are all-zero planes.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 reset_obs_kernel(DevPack pk, DevConfig cfg, unsigned *zero_bits, const unsigned *grid_cnt, double *table) {
+    const Ax ax = make_ax<false>(pk.axis0, pk.axis1);
     __shared__ WarpScratch<false> scratch[kWarpsPerBlock];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int k = blockIdx.x * kWarpsPerBlock + warp;
@@ -995,7 +1001,7 @@ reset_obs_kernel(DevPack pk, DevConfig cfg, unsigned *zero_bits, const unsigned 
     const Bits<false> bits = {zero_bits, nullptr};
     Vec3 pose = {pk.start_pos[3 * k], pk.start_pos[3 * k + 1], pk.start_pos[3 * k + 2]};
     PAINTRL_PROF_BEGIN
-    write_observation(pk, cfg, bits, grid_cnt, pose, lane, scratch[warp], table + (size_t)k * cfg.obs_dim, nullptr PAINTRL_PROF_PASS);
+    write_observation(pk, ax, cfg, bits, grid_cnt, pose, lane, scratch[warp], table + (size_t)k * cfg.obs_dim, nullptr PAINTRL_PROF_PASS);
 }
 
 // ------------------------------------------------------------------------------ state access

@@ -27,6 +27,7 @@ ap.add_argument('--envs', type=int, default=4096)
 ap.add_argument('--workload', default='c2')
 ap.add_argument('--steps', type=int, default=50)
 ap.add_argument('--no-flush', action='store_true')
+ap.add_argument('--dump-rays', default=None, help='write the rays that left the fast path to this .npy file')
 args = ap.parse_args()
 w = bench.WORKLOADS[args.workload]
 cfg = EnvConfig(w['extra'], auto_reset=True, seed=1234, **w['kw'])
@@ -49,6 +50,14 @@ for i in range(args.steps):
         flush.fill_(i & 255)
     env.step(acts[10 + i])
 lib.paintrl_debug_profile(buf, 0)
+if args.dump_rays:
+    import numpy as np
+    rays = np.zeros((4096, 8))
+    lib.paintrl_debug_rays.restype = ctypes.c_int
+    lib.paintrl_debug_rays.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    n_r = lib.paintrl_debug_rays(rays.ctypes.data, 4096, 0)
+    np.save(args.dump_rays, rays[:n_r])
+    print('dumped %d slow-path rays to %s' % (n_r, args.dump_rays))
 n = args.steps * args.envs
 tot_m = sum(buf[i] for i in range(0, 16)); tot_p = sum(buf[i] for i in range(16, 32))
 print('%s, %d envs, %d steps: cycles per environment-step (leader lane, L2 %s between steps)' % (args.workload, args.envs, args.steps, 'warm' if args.no_flush else 'flushed'))
