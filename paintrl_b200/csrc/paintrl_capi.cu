@@ -848,10 +848,18 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     const dim3 grid(blocks), block(kWarpsPerBlock * 32);
     cudaStream_t s = as_stream(stream);
     const bool ax12 = h->pk.axis0 == 1 && h->pk.axis1 == 2;
-#define PAINTRL_PAINT(C, ST)                                                                                       \
-    do {                                                                                                           \
-        if (ax12) paint_kernel<C, ST, true><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);   \
-        else paint_kernel<C, ST, false><<<grid, block, 0, s>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io);       \
+    // programmatic dependent launch after move_kernel (see griddepcontrol.* in the kernels)
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = 0; lc.stream = s;
+    cudaLaunchAttribute lattr[1];
+    lattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    lattr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = lattr; lc.numAttrs = 1;
+    const EnvArrays pea = env_arrays(h);
+#define PAINTRL_PAINT(C, ST)                                                                              \
+    do {                                                                                                  \
+        if (ax12) cudaLaunchKernelEx(&lc, paint_kernel<C, ST, true>, h->pk, h->cfg, pea, h->num_envs, io);  \
+        else cudaLaunchKernelEx(&lc, paint_kernel<C, ST, false>, h->pk, h->cfg, pea, h->num_envs, io);      \
     } while (0)
     if (h->color == 0) {
         if (staged) PAINTRL_PAINT(0, true); else PAINTRL_PAINT(0, false);

@@ -654,6 +654,8 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BIT
 template <int G, int MINB, bool AX12>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
 move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *actions) {
+    // programmatic dependent launch: let the paint kernel's CTAs be scheduled as this grid drains
+    asm volatile("griddepcontrol.launch_dependents;");
     const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
     const int lane = threadIdx.x & 31;
     const int env = (blockIdx.x * (kWarpsPerBlock * 32) + threadIdx.x) / G;
@@ -787,9 +789,14 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     if (lane == 0) {
         mbar_init(&ws.bar, 1);
         mbar_expect_tx(&ws.bar, (unsigned)(sizeof(EnvState) + sizeof(MoveOut)) + (STAGED ? plane_bytes : 0u));
+        if (STAGED) bulk_g2s(ws.sbits, gbits, plane_bytes, &ws.bar);   // not written by the move kernel
+    }
+    // launched with programmatic stream serialization: everything above overlaps the move kernel's tail,
+    // its outputs (record, shot centres) are read only after it has completed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (lane == 0) {
         bulk_g2s(&ws.st, &ea.states[env], (unsigned)sizeof(EnvState), &ws.bar);
         bulk_g2s(&ws.mv, &ea.moves[env], (unsigned)sizeof(MoveOut), &ws.bar);
-        if (STAGED) bulk_g2s(ws.sbits, gbits, plane_bytes, &ws.bar);
     }
     __syncwarp();
     mbar_wait(&ws.bar, 0);
