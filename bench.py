@@ -56,6 +56,18 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
 
 
+def captured_traffic(workload_key):
+    """DRAM bytes (read + write) per step from the committed `ncu --set full` capture of this workload
+    (profiles/r01_v4_dram_traffic.json, both kernels of the step summed), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r01_v4_dram_traffic.json')
+    try:
+        with open(path) as f:
+            t = json.load(f).get(workload_key)
+        return float(sum(t.values())) if t else None
+    except (OSError, ValueError):
+        return None
+
+
 def algorithmic_bytes(status_bytes, n_front, obs_dim, act_dim, scan, u_mean, p_reset):
     """B_alg per env-step."""
     return (status_bytes * n_front * (1 if scan else 0) + 2 * status_bytes * u_mean + 8 * obs_dim + 8 * act_dim
@@ -304,7 +316,8 @@ def main():
                     'd2h_bytes_per_step': d2h_bytes, 'steps': e2e_steps, 'api': 'BatchedPaintEnv.step_host -> paintrl_step_host'},
             'gpu_launches': s1['kernel_launches'] - s0['kernel_launches'],
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src, 'kernel': 'paintrl::move_kernel + paintrl::paint_kernel (one step = two launches)',
+                         'traffic': captured_traffic(args.workload), 'traffic_unit': 'bytes per step (ncu capture, profiles/)',
+                         'peak_source': peak_src, 'kernel': 'paintrl::move_kernel + paintrl::paint_kernel (one step = two launches)',
                          'kernel_ms': kernel_ms, 'algorithmic_bytes_per_env_step': b_alg,
                          'footprint_union_texels_mean': u_mean, 'p_reset': p_reset,
                          'ray_full_scans_per_env_step': (s1['ray_full_scans'] - s0['ray_full_scans']) / max(1, steps_done)},

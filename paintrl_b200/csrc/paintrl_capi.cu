@@ -79,7 +79,8 @@ struct PaintrlEngine {
     unsigned long long launches = 0;
     double move_cell_planes_mean = 0.0, move_cell_verts_mean = 0.0;
     int move_lanes = 32;             // lanes per environment in move_kernel (8, 16 or 32)
-    int move_minb = 7;               // its __launch_bounds__ min blocks per SM (7: 72 registers, 4: 128)
+    int move_minb = 4;               // its __launch_bounds__ min blocks per SM (4: 128 registers ... 7: 72)
+    bool force_unstaged = false;     // PAINTRL_FORCE_UNSTAGED: run the global-memory bit-plane path (tests)
 };
 
 namespace {
@@ -761,9 +762,12 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, cudaGetErrorString(err)); }
     {
+        // lanes per environment in the move phase: a full warp while the batch alone cannot fill the GPU
+        // (the phase is latency-bound there), 8 lanes once it can (then instruction issue is the limit)
         const char *ml = getenv("PAINTRL_MOVE_LANES");
-        int lanes = ml ? atoi(ml) : 8;
-        e->move_lanes = (lanes == 16 || lanes == 32) ? lanes : 8;
+        int lanes = ml ? atoi(ml) : (num_envs <= 16384 ? 32 : 8);
+        e->move_lanes = (lanes == 16 || lanes == 8) ? lanes : 32;
+        e->force_unstaged = getenv("PAINTRL_FORCE_UNSTAGED") != nullptr;
         const char *mb = getenv("PAINTRL_MOVE_MINB");
         e->move_minb = mb ? std::min(7, std::max(4, atoi(mb))) : 4;
     }
@@ -844,7 +848,7 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     }
     int rc = launch_check(h, "move_kernel");
     if (rc != PAINTRL_OK) return rc;
-    const bool staged = h->pk.n_words_pad <= kStageWords;
+    const bool staged = h->pk.n_words_pad <= kStageWords && !h->force_unstaged;
     const dim3 grid(blocks), block(kWarpsPerBlock * 32);
     cudaStream_t s = as_stream(stream);
     const bool ax12 = h->pk.axis0 == 1 && h->pk.axis1 == 2;

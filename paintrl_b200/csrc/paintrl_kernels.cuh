@@ -840,7 +840,10 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
         if (lane == 2) { num = st.angle_diff; den = kPi; }                      // turning penalty (:338)
         if (lane == 3) { num = axis2_real - pk.range1_min + radius; den = pk.range1_max - pk.range1_min + 2 * radius; }   // bullet_paint_wrapper.py:969
         if (lane == 4) { num = axis2_real - pk.range1_min; den = pk.range1_max - pk.range1_min; }                         // :845
-        const double q = num / den;
+        // 0 / den is +0 for these positive denominators; skipping it keeps the lanes whose numerator is 0
+        // (nothing painted, no turn) out of the division's slow path
+        double q = 0.0;
+        if (num != 0.0) q = num / den;
         rate = n_possible ? __shfl_sync(kFull, q, 0) : 0.0;
         reward = __shfl_sync(kFull, q, 1);
         turn = __shfl_sync(kFull, q, 2);
@@ -877,7 +880,8 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
             o = lane == 2 ? open[0] : (lane == 3 ? open[1] : (lane == 4 ? open[2] : open[3]));
             num = (double)o; den = t ? (double)t : 1.0;
         }
-        const double q = num / den;
+        double q = 0.0;
+        if (num != 0.0) q = num / den;
         ratio = t == 0 ? 0.0 : q;                        // lanes 2..5: sector s = lane - 2 (bullet_paint_wrapper.py:1057-1060)
         avg_reward = __shfl_sync(kFull, q, 0);
         axis1_in = (ghi - glo == 0.0) ? 0.0 : __shfl_sync(kFull, q, 1);
