@@ -39,6 +39,12 @@ WORKLOADS = {
     'c3': dict(name='C3 quadratic sheet x16384 envs/GPU, HSI, turning+overlap penalties, hybrid termination',
                extra=dict(BASE, Part_NO=1, COLOR_MODE='HSI', TURNING_PENALTY=True, OVERLAP_PENALTY=True,
                           TERMINATION_MODE='hybrid'), kw={}, envs_per_gpu=16384, scaling='weak'),
+    # configs[3]: continuous 2-D actions, grid observation, every start point, 2048x2048 synthetic texture
+    'c4': dict(name='C4 door panel 2048x2048 synthetic texture x8192 envs/GPU, RGB, continuous ACTION_SHAPE=2, OBS_MODE=grid-4, '
+                    'START_POINT_MODE=all, late termination, auto-reset',
+               extra=dict(BASE, START_POINT_MODE='all'),
+               kw=dict(action_mode='continuous', action_shape=2, obs_mode='grid', obs_grad=4),
+               texture=(2048, 2048), envs_per_gpu=8192, scaling='weak'),
     # configs[4] env side: 65536 envs sharded over the GPUs (strong scaling)
     'c5': dict(name='C5 door panel, 65536 envs sharded over N GPUs, C2 settings',
                extra=dict(BASE), kw={}, envs_total=65536, scaling='strong'),
@@ -132,7 +138,10 @@ def cpu_baseline_sample(workload, seconds=12.0, threads=None):
     threads = threads or os.cpu_count() or 1
     cfg = EnvConfig(workload['extra'], **workload['kw'])
     pack = PartPack.for_part(cfg.part_no)
-    n_env = 16 * threads
+    if 'texture' in workload:
+        from oracle.oracle import retextured_pack
+        pack = retextured_pack(pack, *workload['texture'])
+    n_env = (16 if 'texture' not in workload else 1) * threads
     ora = OracleBatch(pack, cfg, n_env, threads=threads)
     rng = np.random.default_rng(1234)
     n_starts = pack.start_points(cfg.start_point_mode).shape[0]
@@ -216,7 +225,7 @@ def main():
     else:
         n_env = workload['envs_per_gpu']
     cfg = EnvConfig(workload['extra'], auto_reset=True, seed=1234 + rank, **workload['kw'])
-    env = BatchedPaintEnv(n_env, cfg, device=device)
+    env = BatchedPaintEnv(n_env, cfg, device=device, texture_size=workload.get('texture', (240, 240)))
 
     gen = torch.Generator(device=device)
     gen.manual_seed(1234 + rank)
@@ -277,7 +286,7 @@ def main():
     torch.cuda.synchronize(device)
     e2e_s = time.perf_counter() - t0
     act_bytes = int(host_actions[0].nbytes)
-    d2h_bytes = int(sum(host_out[k].nbytes for k in ('obs', 'reward', 'penalty', 'actual', 'done')))
+    d2h_bytes = int(sum(host_out[k].nbytes for k in ('obs', 'reward', 'penalty', 'actual', 'next_obs', 'done')))
 
     # ---- reduce over ranks: max time, summed work
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=device)

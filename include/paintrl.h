@@ -202,6 +202,20 @@ typedef struct PaintrlStats {
 } PaintrlStats;
 int paintrl_stats(PaintrlHandle h, PaintrlStats *out);
 
+/* Load-time texel rasterisation (Part.preprocess + BarycentricInterpolator.get_uv_pixels,
+ * bullet_paint_wrapper.py:604-618, 191-212) at an arbitrary texture size, on the GPU: the front
+ * texels (i, j) and their 3-D positions from the front triangles' corners and UV coordinates.
+ * This is what makes textures other than the reference's 240x240 usable (the reference's own loader
+ * is O(W * H * n) Python).  All pointers are HOST pointers; synchronous.
+ *   tri_a/b/c : float64[n_tris,3] corners, tri_uv: float64[n_tris,3,2], both in bary_list order;
+ *   capacity  : rows available in the outputs; 0 = only count (outputs may be NULL);
+ *   texel_ij_out: int32[capacity,2], texel_pos_out: float64[capacity,3], sorted by (i, j);
+ *   *n_texels_out: number of front texels. */
+int paintrl_rasterize_texels(const double *tri_a, const double *tri_b, const double *tri_c,
+                             const double *tri_uv, int32_t n_tris, int32_t width, int32_t height,
+                             int32_t device, int32_t capacity, int32_t *texel_ij_out,
+                             double *texel_pos_out, int32_t *n_texels_out);
+
 const char *paintrl_last_error(void);
 int32_t paintrl_abi_version(void);
 

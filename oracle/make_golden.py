@@ -127,6 +127,10 @@ def export_partpack(part_no):
         vertices=vertices, vtri_start=vtri_start, vtri_idx=np.array(vtri_idx, dtype=np.int32),
         tri_id=np.array(front_tris, dtype=np.int32),
         tri_a=col(lambda b: b._a), tri_v0=col(lambda b: b._v0), tri_v1=col(lambda b: b._v1),
+        # raw corners and UVs of the front triangles, in bary_list order: the inputs of the texel
+        # rasterisation (bullet_paint_wrapper.py:191-212), so packs at other texture sizes can be derived
+        tri_b=col(lambda b: b._b), tri_c=col(lambda b: b._c),
+        tri_uv=col(lambda b: [list(b._uva), list(b._uvb), list(b._uvc)]),
         tri_d00=col(lambda b: b._d00), tri_d01=col(lambda b: b._d01), tri_d11=col(lambda b: b._d11),
         tri_inv_denom=col(lambda b: b._inv_denom), tri_n=col(lambda b: b.get_normal()),
         grid_lo=grid_lo, grid_hi=grid_hi,

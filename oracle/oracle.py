@@ -72,6 +72,8 @@ def lib():
         h.oracle_ball_query.argtypes = [vp, dp, vp]
         h.oracle_nearest_vertex.restype = i32
         h.oracle_nearest_vertex.argtypes = [vp, dp]
+        h.oracle_rasterize.restype = i32
+        h.oracle_rasterize.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp]
         _lib = h
     return _lib
 
@@ -204,3 +206,28 @@ class OracleBatch(object):
     def nearest_vertex(self, point):
         point = np.ascontiguousarray(point, dtype=np.float64)
         return int(self._h.oracle_nearest_vertex(self.envs[0], _dp(point)))
+
+
+def rasterize(tri_a, tri_b, tri_c, tri_uv, width, height):
+    """Front texels of a part at a texture size, by the reference's rasterisation rule
+    (bullet_paint_wrapper.py:191-212, 604-618; oracle_rasterize in paint_oracle.c).
+    Returns (ij [N,2] int32 sorted by (i, j), pos [N,3] float64, owner [N] int32 = tri * 4 + kind)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (tri_a, tri_b, tri_c, tri_uv)]
+    n_tris = arrs[0].shape[0]
+    owner = np.empty(width * height, dtype=np.int32)
+    pos = np.zeros((width * height, 3), dtype=np.float64)
+    n = lib().oracle_rasterize(arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data,
+                               n_tris, width, height, owner.ctypes.data, pos.ctypes.data)
+    if n < 0:
+        raise ValueError('a UV coordinate maps outside the %dx%d texture' % (width, height))
+    idx = np.flatnonzero(owner >= 0)
+    assert len(idx) == n
+    ij = np.stack([idx // height, idx % height], axis=1).astype(np.int32)
+    return ij, pos[idx], owner[idx]
+
+
+def retextured_pack(base_pack, width, height):
+    """`PartPack.retextured` with the texels rasterised by this oracle instead of the GPU."""
+    a = base_pack.arrays
+    ij, pos, _ = rasterize(a['tri_a'], a['tri_b'], a['tri_c'], a['tri_uv'], width, height)
+    return base_pack.retextured(width, height, texels=(ij, pos))

@@ -633,3 +633,79 @@ int oracle_nearest_vertex(const OracleEnv *e, const double *point) {
     }
     return best;
 }
+
+/* ---------------------------------------------------------------------------------- load time
+ * Texel rasterisation of Part.preprocess (bullet_paint_wrapper.py:604-618) for one side: every
+ * triangle of the side, in bary_list order, contributes its three corner pixels and every pixel of
+ * the corners' bounding box whose normalised coordinate lies inside the UV triangle
+ * (BarycentricInterpolator.get_uv_pixels, :191-212); `profile_dicts[side].update(pixel_dict)` lets a
+ * later triangle overwrite an earlier one, and inside a triangle the interior value overwrites a
+ * corner's.  Restated sequentially with exactly those overwrite semantics.
+ *
+ * 2-vector np.dot is OpenBLAS ddot's scalar tail fma(x1,y1, x0*y0) (the n=3 chain of npdot3 cut
+ * after two terms); np.dot(scalar, vector) is an element-wise product, no FMA.
+ *
+ * owner[u * height + v]: -1 (not a texel of the side) or tri * 4 + kind, kind 0/1/2 = value of
+ * corner a/b/c, 3 = barycentric interior value; pos[(u * height + v) * 3 ..] its 3-D position.
+ * Returns the number of texels, or -1 if some pixel coordinate falls outside the texture.
+ */
+static double npdot2(const double *x, const double *y) { return fma(x[1], y[1], x[0] * y[0]); }
+
+/* bullet_paint_wrapper.py:165-171 _get_pixel_coordinate: Python round() is round-half-even */
+static void pixel_coordinate(double u, double v, int width, int height, int *i, int *j) {
+    double ri = nearbyint(width * u), rj = nearbyint(height * v);
+    *i = ri < width - 1 ? (int)ri : width - 1;
+    *j = rj < height - 1 ? (int)rj : height - 1;
+}
+
+int oracle_rasterize(const double *tri_a, const double *tri_b, const double *tri_c, const double *tri_uv,
+                     int n_tris, int width, int height, int32_t *owner, double *pos) {
+    for (long k = 0; k < (long)width * height; ++k) owner[k] = -1;
+    for (int t = 0; t < n_tris; ++t) {
+        const double *a = tri_a + 3 * t, *b = tri_b + 3 * t, *c = tri_c + 3 * t;
+        const double *uva = tri_uv + 6 * t, *uvb = uva + 2, *uvc = uva + 4;
+        const double *corner[3] = {a, b, c};
+        const double *uv[3] = {uva, uvb, uvc};
+        int ci[3], cj[3];
+        for (int k = 0; k < 3; ++k) {
+            pixel_coordinate(uv[k][0], uv[k][1], width, height, &ci[k], &cj[k]);
+            if (ci[k] < 0 || cj[k] < 0) return -1;
+        }
+        /* pixel_dict = {uva: a, uvb: b, uvc: c}  (:198) -- later keys win */
+        for (int k = 0; k < 3; ++k) {
+            long o = (long)ci[k] * height + cj[k];
+            owner[o] = t * 4 + k;
+            memcpy(pos + 3 * o, corner[k], 3 * sizeof(double));
+        }
+        /* uv_bary = BarycentricInterpolator(uva, uvb, uvc)  (:200, :123-134) */
+        double v0[2] = {uvb[0] - uva[0], uvb[1] - uva[1]}, v1[2] = {uvc[0] - uva[0], uvc[1] - uva[1]};
+        double d00 = npdot2(v0, v0), d01 = npdot2(v0, v1), d11 = npdot2(v1, v1);
+        double denom = d00 * d11 - d01 * d01;
+        double inv = denom != 0 ? 1.0 / denom : 0;
+        int x_min = ci[0], x_max = ci[0], y_min = cj[0], y_max = cj[0];
+        for (int k = 1; k < 3; ++k) {
+            if (ci[k] < x_min) x_min = ci[k];
+            if (ci[k] > x_max) x_max = ci[k];
+            if (cj[k] < y_min) y_min = cj[k];
+            if (cj[k] > y_max) y_max = cj[k];
+        }
+        for (int u = x_min; u <= x_max; ++u)
+            for (int v = y_min; v <= y_max; ++v) {
+                double pt[2] = {(double)u / width, (double)v / height};
+                double v2[2] = {pt[0] - uva[0], pt[1] - uva[1]};
+                double d20 = npdot2(v2, v0), d21 = npdot2(v2, v1);
+                double bv = (d11 * d20 - d01 * d21) * inv;
+                double bw = (d00 * d21 - d01 * d20) * inv;
+                double bu = 1.0 - bv - bw;
+                if (inv == 0) continue;                          /* (-1,-1,-1): never inside */
+                if (!(0 <= bu && bu <= 1 && 0 <= bv && bv <= 1 && 0 <= bw && bw <= 1)) continue;
+                long o = (long)u * height + v;
+                owner[o] = t * 4 + 3;
+                for (int k = 0; k < 3; ++k)                      /* :222-224 */
+                    pos[3 * o + k] = (bu * a[k] + bv * b[k]) + bw * c[k];
+            }
+    }
+    int n = 0;
+    for (long k = 0; k < (long)width * height; ++k) n += owner[k] >= 0;
+    return n;
+}

@@ -90,6 +90,7 @@ SIGNATURES = {
     'paintrl_set_state': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
     'paintrl_job_status': (ctypes.c_int, [_VP, _VP, _VP]),
     'paintrl_stats': (ctypes.c_int, [_VP, ctypes.POINTER(PaintrlStats)]),
+    'paintrl_rasterize_texels': (ctypes.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP]),
     'paintrl_last_error': (ctypes.c_char_p, []),
     'paintrl_abi_version': (_I32, []),
 }

@@ -36,10 +36,11 @@ class BatchedPaintEnv(object):
             extra_config, action_mode=action_mode, action_shape=action_shape,
             discrete_granularity=discrete_granularity, obs_mode=obs_mode, obs_grad=obs_grad,
             auto_reset=auto_reset, seed=seed, max_possible_point=max_possible_point)
-        self.pack = pack if pack is not None else PartPack.for_part(self.cfg.part_no, *texture_size)
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         if self.device.type != 'cuda':
             raise RuntimeError('paintrl_b200 runs on CUDA devices only')
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.pack = pack if pack is not None else PartPack.for_part(self.cfg.part_no, *texture_size, device=dev_index)
         self.num_envs = int(num_envs)
         self._lib = _capi.lib()
         cpack, keep_pack = self.pack.to_c(self.cfg.start_point_mode, self.cfg.color_mode)
@@ -143,6 +144,25 @@ class BatchedPaintEnv(object):
                 'next_obs': self.next_obs if self.cfg.auto_reset else self.obs}
         return self.obs, self.actual, self.done, info
 
+    def step_into(self, actions, obs, reward, penalty, actual, done, next_obs=None, new_texels=None):
+        """`step` writing straight into caller tensors (e.g. row t of a rollout fragment): contiguous
+        CUDA tensors of this environment's device, float64 [B, obs_dim] / [B], uint8 [B], int32 [B];
+        `actions` int64 [B] or float64 [B, action_dim].  Nothing is returned and nothing is copied."""
+        B = self.num_envs
+        want = (torch.int64, B) if self.cfg.action_mode == 'discrete' else (torch.float64, B * self.action_dim)
+        for t, (dt, n) in ((actions, want), (obs, (torch.float64, B * self.obs_dim)), (reward, (torch.float64, B)),
+                           (penalty, (torch.float64, B)), (actual, (torch.float64, B)), (done, (torch.uint8, B)),
+                           (next_obs, (torch.float64, B * self.obs_dim)), (new_texels, (torch.int32, B))):
+            if t is None:
+                continue
+            if t.dtype != dt or t.numel() != n or not t.is_contiguous() or t.device != self.device:
+                raise ValueError('step_into: expected a contiguous %s tensor of %d elements on %s' % (dt, n, self.device))
+        _capi.check(self._lib.paintrl_step(
+            self._h, _ptr(actions), _ptr(obs), _ptr(reward), _ptr(penalty), _ptr(actual), _ptr(done), _ptr(new_texels),
+            _ptr(next_obs) if self.cfg.auto_reset else None, None, self._stream()))
+        if next_obs is not None and not self.cfg.auto_reset:
+            next_obs.copy_(obs)
+
     def step_host(self, actions, out=None):
         """The same step through HOST buffers (paintrl_step_host): actions are copied host->device
         and obs / reward / penalty / actual / done device->host inside the call."""
@@ -161,16 +181,21 @@ class BatchedPaintEnv(object):
             ctypes.c_void_p(nxt.ctypes.data) if nxt is not None else None, self._stream()))
         return out
 
-    def host_buffers(self, pinned=True):
-        """Host result buffers for `step_host` (pinned by default so the copies are asynchronous)."""
-        B = self.num_envs
-
-        def buf(shape, dtype):
-            t = torch.zeros(shape, dtype=dtype, pin_memory=pinned)
-            return t.numpy()
-        return {'obs': buf((B, self.obs_dim), torch.float64), 'reward': buf((B,), torch.float64),
-                'penalty': buf((B,), torch.float64), 'actual': buf((B,), torch.float64),
-                'done': buf((B,), torch.uint8), 'next_obs': buf((B, self.obs_dim), torch.float64)}
+    def host_buffers(self, pinned=True, next_obs=True):
+        """Host result buffers for `step_host`: views into ONE (pinned) allocation laid out
+        obs | reward | penalty | actual | [next_obs] | done, the order `paintrl_step_host` stages its
+        results in, so that they come back with a single device->host copy."""
+        B, od = self.num_envs, self.obs_dim
+        n_f64 = B * (od * (2 if next_obs else 1) + 3)
+        raw = torch.zeros(n_f64 * 8 + B, dtype=torch.uint8, pin_memory=pinned)
+        f64 = raw[:n_f64 * 8].view(torch.float64).numpy()
+        out = {'obs': f64[:B * od].reshape(B, od), 'reward': f64[B * od:B * od + B],
+               'penalty': f64[B * od + B:B * od + 2 * B], 'actual': f64[B * od + 2 * B:B * od + 3 * B]}
+        if next_obs:
+            out['next_obs'] = f64[B * od + 3 * B:].reshape(B, od)
+        out['done'] = raw[n_f64 * 8:].numpy()
+        out['_storage'] = raw
+        return out
 
     # ------------------------------------------------------------------ state
     def get_state(self, env_ids=None, status=True):

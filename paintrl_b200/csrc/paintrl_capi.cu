@@ -11,6 +11,7 @@
 
 #include "../../include/paintrl.h"
 #include "paintrl_kernels.cuh"
+#include "paintrl_raster.cuh"
 
 using namespace paintrl;
 
@@ -74,8 +75,9 @@ struct PaintrlEngine {
     unsigned long long *stats = nullptr;
     // staging for the host-buffer entry points
     void *stage_actions = nullptr;
-    double *stage_obs = nullptr, *stage_next_obs = nullptr, *stage_scalars = nullptr;   // scalars: reward|penalty|actual
-    uint8_t *stage_done = nullptr;
+    // paintrl_step_host: one contiguous block, laid out per call as obs | reward | penalty | actual | [next_obs] | done,
+    // so that host buffers carved from one allocation in that order come back with a single copy
+    unsigned char *stage_out = nullptr;
     unsigned long long launches = 0;
     double move_cell_planes_mean = 0.0, move_cell_verts_mean = 0.0;
     int move_lanes = 32;             // lanes per environment in move_kernel (8, 16 or 32)
@@ -633,6 +635,58 @@ int launch_check(PaintrlEngine *e, const char *what) {
 extern "C" {
 
 int32_t paintrl_abi_version(void) { return PAINTRL_ABI_VERSION; }
+
+/* Part.preprocess texel rasterisation on the GPU (see paintrl_raster.cuh and paintrl.h). */
+int paintrl_rasterize_texels(const double *tri_a, const double *tri_b, const double *tri_c, const double *tri_uv,
+                             int32_t n_tris, int32_t width, int32_t height, int32_t device, int32_t capacity,
+                             int32_t *texel_ij_out, double *texel_pos_out, int32_t *n_texels_out) {
+    if (!tri_a || !tri_b || !tri_c || !tri_uv || !n_texels_out) return fail(PAINTRL_E_INVALID, "null argument");
+    if (n_tris <= 0 || width <= 0 || height <= 0 || (long long)width * height > (1ll << 29) || n_tris > (1 << 28))
+        return fail(PAINTRL_E_INVALID, "bad triangle count or texture size");
+    if (capacity > 0 && (!texel_ij_out || !texel_pos_out)) return fail(PAINTRL_E_INVALID, "null output buffer");
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t n_pix = (size_t)width * height;
+    DeviceArena arena;
+    double *d_a = nullptr, *d_b = nullptr, *d_c = nullptr, *d_uv = nullptr;
+    int *d_owner = nullptr, *d_bad = nullptr;
+    if (arena.alloc((void **)&d_a, sizeof(double) * 3 * n_tris) != cudaSuccess || arena.alloc((void **)&d_b, sizeof(double) * 3 * n_tris) != cudaSuccess ||
+        arena.alloc((void **)&d_c, sizeof(double) * 3 * n_tris) != cudaSuccess || arena.alloc((void **)&d_uv, sizeof(double) * 6 * n_tris) != cudaSuccess ||
+        arena.alloc((void **)&d_owner, sizeof(int) * n_pix) != cudaSuccess || arena.alloc((void **)&d_bad, sizeof(int)) != cudaSuccess)
+        return fail(PAINTRL_E_CUDA, "device allocation failed (rasteriser)");
+    CUDA_TRY(cudaMemcpy(d_a, tri_a, sizeof(double) * 3 * n_tris, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_b, tri_b, sizeof(double) * 3 * n_tris, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_c, tri_c, sizeof(double) * 3 * n_tris, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_uv, tri_uv, sizeof(double) * 6 * n_tris, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(d_owner, 0xff, sizeof(int) * n_pix));
+    CUDA_TRY(cudaMemset(d_bad, 0, sizeof(int)));
+    raster_owner_kernel<<<(n_tris + 3) / 4, 128>>>(d_uv, n_tris, width, height, d_owner, d_bad);
+    CUDA_TRY(cudaGetLastError());
+    std::vector<int> owner(n_pix);
+    int bad = 0;
+    CUDA_TRY(cudaMemcpy(owner.data(), d_owner, sizeof(int) * n_pix, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) return fail(PAINTRL_E_INVALID, "a UV coordinate maps to a negative pixel coordinate");
+    std::vector<int> pix;
+    for (size_t k = 0; k < n_pix; ++k)
+        if (owner[k] >= 0) pix.push_back((int)k);
+    *n_texels_out = (int32_t)pix.size();
+    if (capacity <= 0) return PAINTRL_OK;                 /* count only */
+    if ((size_t)capacity < pix.size()) return fail(PAINTRL_E_INVALID, "output capacity is smaller than the texel count");
+    if (pix.empty()) return PAINTRL_OK;
+    int *d_pix = nullptr, *d_ij = nullptr;
+    double *d_pos = nullptr;
+    if (arena.alloc((void **)&d_pix, sizeof(int) * pix.size()) != cudaSuccess || arena.alloc((void **)&d_ij, sizeof(int) * 2 * pix.size()) != cudaSuccess ||
+        arena.alloc((void **)&d_pos, sizeof(double) * 3 * pix.size()) != cudaSuccess)
+        return fail(PAINTRL_E_CUDA, "device allocation failed (rasteriser output)");
+    CUDA_TRY(cudaMemcpy(d_pix, pix.data(), sizeof(int) * pix.size(), cudaMemcpyHostToDevice));
+    raster_position_kernel<<<(unsigned)((pix.size() + 255) / 256), 256>>>(d_a, d_b, d_c, d_uv, width, height, d_owner, d_pix,
+                                                                          (int)pix.size(), d_ij, d_pos);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(texel_ij_out, d_ij, sizeof(int) * 2 * pix.size(), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(texel_pos_out, d_pos, sizeof(double) * 3 * pix.size(), cudaMemcpyDeviceToHost));
+    return PAINTRL_OK;
+}
+
 const char *paintrl_last_error(void) { return g_error.c_str(); }
 
 /* Debug only (not in paintrl.h): phase cycle counters of a -DPAINTRL_PROFILE build; returns 0 slots otherwise. */
@@ -742,10 +796,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
               e->arena.alloc((void **)&e->stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
               e->arena.alloc((void **)&reset_obs, sizeof(double) * od * (size_t)e->pk.n_starts) == cudaSuccess &&
               e->arena.alloc(&e->stage_actions, adim * num_envs) == cudaSuccess &&
-              e->arena.alloc((void **)&e->stage_obs, sizeof(double) * od * (size_t)num_envs) == cudaSuccess &&
-              e->arena.alloc((void **)&e->stage_next_obs, sizeof(double) * od * (size_t)num_envs) == cudaSuccess &&
-              e->arena.alloc((void **)&e->stage_scalars, sizeof(double) * 3 * (size_t)num_envs) == cudaSuccess &&
-              e->arena.alloc((void **)&e->stage_done, (size_t)num_envs) == cudaSuccess;
+              e->arena.alloc((void **)&e->stage_out, (sizeof(double) * (2 * od + 3) + 1) * (size_t)num_envs) == cudaSuccess;
     if (!ok) { delete e; return fail(PAINTRL_E_CUDA, "device allocation failed (state / status planes)"); }
     cudaMemset(e->states, 0, sizeof(EnvState) * (size_t)num_envs);
     cudaMemset(e->moves, 0xff, sizeof(MoveOut) * (size_t)num_envs);   // miss_cache = none
@@ -886,19 +937,35 @@ int paintrl_step_host(PaintrlHandle h, const void *actions_host, double *obs_hos
     const size_t abytes = (h->cfg.action_mode == 0 ? sizeof(long long) : sizeof(double) * h->cfg.action_shape) * nenv;
     const size_t obytes = sizeof(double) * h->cfg.obs_dim * nenv;
     CUDA_TRY(cudaMemcpyAsync(h->stage_actions, actions_host, abytes, cudaMemcpyHostToDevice, s));
-    double *sc = h->stage_scalars;
-    int rc = paintrl_step(h, h->stage_actions, h->stage_obs, sc, sc + nenv, sc + 2 * nenv, h->stage_done, nullptr,
-                          next_obs_host ? h->stage_next_obs : nullptr, nullptr, stream);
+    // device staging in the order obs | reward | penalty | actual | [next_obs] | done, no gaps
+    const bool want_next = next_obs_host != nullptr, dev_next = want_next && h->cfg.auto_reset;
+    unsigned char *d = h->stage_out;
+    double *d_obs = reinterpret_cast<double *>(d);
+    double *d_sc = reinterpret_cast<double *>(d + obytes);
+    double *d_next = dev_next ? reinterpret_cast<double *>(d + obytes + 3 * sizeof(double) * nenv) : nullptr;
+    uint8_t *d_done = d + obytes + 3 * sizeof(double) * nenv + (dev_next ? obytes : 0);
+    int rc = paintrl_step(h, h->stage_actions, d_obs, d_sc, d_sc + nenv, d_sc + 2 * nenv, d_done, nullptr, d_next, nullptr, stream);
     if (rc != PAINTRL_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(obs_host, h->stage_obs, obytes, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(reward_host, sc, sizeof(double) * nenv, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(penalty_host, sc + nenv, sizeof(double) * nenv, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(actual_host, sc + 2 * nenv, sizeof(double) * nenv, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(done_host, h->stage_done, nenv, cudaMemcpyDeviceToHost, s));
-    if (next_obs_host) {
-        const double *src = h->cfg.auto_reset ? h->stage_next_obs : h->stage_obs;
-        CUDA_TRY(cudaMemcpyAsync(next_obs_host, src, obytes, cudaMemcpyDeviceToHost, s));
-    }
+    // device -> host: segments that are adjacent on both sides travel as one copy
+    struct Seg { void *dst; const void *src; size_t n; };
+    Seg segs[7];
+    int ns = 0;
+    auto push = [&](void *dst, const void *src, size_t n) {
+        if (ns > 0 && (const char *)segs[ns - 1].src + segs[ns - 1].n == (const char *)src &&
+            (char *)segs[ns - 1].dst + segs[ns - 1].n == (char *)dst) {
+            segs[ns - 1].n += n;
+        } else {
+            segs[ns].dst = dst; segs[ns].src = src; segs[ns].n = n; ++ns;
+        }
+    };
+    push(obs_host, d_obs, obytes);
+    push(reward_host, d_sc, sizeof(double) * nenv);
+    push(penalty_host, d_sc + nenv, sizeof(double) * nenv);
+    push(actual_host, d_sc + 2 * nenv, sizeof(double) * nenv);
+    if (dev_next) push(next_obs_host, d_next, obytes);
+    push(done_host, d_done, nenv);
+    if (want_next && !dev_next) push(next_obs_host, d_obs, obytes);   // no auto-reset: the next observation is this one
+    for (int i = 0; i < ns; ++i) CUDA_TRY(cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return PAINTRL_OK;
 }

@@ -63,16 +63,63 @@ class PartPack(object):
         return cls(meta, arrays)
 
     @classmethod
-    def for_part(cls, part_no, width=240, height=240):
-        """Pack of `Part_Dict[part_no]` (robot_gym_env.py:106-117) at a texture size."""
+    def for_part(cls, part_no, width=240, height=240, device=0):
+        """Pack of `Part_Dict[part_no]` (robot_gym_env.py:106-117) at a texture size.  Sizes without a
+        stored pack are derived from the part's 240x240 pack by rasterising its front triangles on
+        GPU `device` (`retextured`)."""
         if part_no not in PART_DICT:
             raise KeyError(part_no)
         name = os.path.splitext(PART_DICT[part_no][0])[0]
         path = os.path.join(PACK_DIR, '%s_%dx%d.npz' % (name, width, height))
-        if not os.path.isfile(path):
+        if os.path.isfile(path):
+            return cls.load(path)
+        base = os.path.join(PACK_DIR, '%s_240x240.npz' % name)
+        if not os.path.isfile(base):
             raise FileNotFoundError(
                 'no part pack for Part_NO=%d (%s) at %dx%d: %s' % (part_no, name, width, height, path))
-        return cls.load(path)
+        return cls.load(base).retextured(width, height, device=device)
+
+    def rasterize(self, width, height, device=0):
+        """Front texels at a texture size: `(ij [N,2] int32, pos [N,3] float64)` sorted by (i, j), from
+        the front triangles' corners and UVs by the reference's rule (Part.preprocess,
+        bullet_paint_wrapper.py:604-618, 191-212) -- computed by `paintrl_rasterize_texels` on the GPU."""
+        for key in ('tri_b', 'tri_c', 'tri_uv'):
+            if key not in self.arrays:
+                raise ValueError('this part pack carries no %s: re-mint it (oracle/make_golden.py packs)' % key)
+        lib = _capi.lib()
+        tri = [np.ascontiguousarray(self.arrays[k], dtype=np.float64) for k in ('tri_a', 'tri_b', 'tri_c', 'tri_uv')]
+        n_tris = tri[0].shape[0]
+        n = ctypes.c_int32(0)
+        ptrs = [ctypes.c_void_p(a.ctypes.data) for a in tri]
+        _capi.check(lib.paintrl_rasterize_texels(*ptrs, n_tris, width, height, device, 0, None, None, ctypes.byref(n)))
+        ij = np.zeros((n.value, 2), dtype=np.int32)
+        pos = np.zeros((n.value, 3), dtype=np.float64)
+        _capi.check(lib.paintrl_rasterize_texels(*ptrs, n_tris, width, height, device, n.value,
+                                                 ctypes.c_void_p(ij.ctypes.data), ctypes.c_void_p(pos.ctypes.data),
+                                                 ctypes.byref(n)))
+        return ij, pos
+
+    def retextured(self, width, height, device=0, texels=None):
+        """The same part with a synthetic blank `width` x `height` texture (BASELINE config C4): geometry,
+        hull, start points and silhouette table are texture-independent and kept; the front texels are
+        re-rasterised; `max_points` (robot_gym_env.py:106-117, a texel count) scales with the texel
+        density so that `finished` (robot_gym_env.py:292) keeps its meaning.
+        `texels=(ij, pos)` supplies the rasterisation instead (the tests' CPU oracle does)."""
+        ij, pos = texels if texels is not None else self.rasterize(width, height, device=device)
+        arrays = dict(self.arrays)
+        arrays['front_ij'], arrays['front_pos'] = ij, pos
+        n = ij.shape[0]
+        for key in ('status_init_rgb', 'status_init_hsi'):
+            arrays[key] = np.full(n, self.arrays[key][0], dtype=np.int16)
+        for key in ('texel_off', 'init_texture_rgb', 'init_texture_hsi', 'grid_cells_4', 'grid_cells_10'):
+            arrays.pop(key, None)          # texture-size specific and not needed by the step path
+        meta = dict(self.meta)
+        scale = (width / float(self.width)) * (height / float(self.height))
+        meta.update(width=int(width), height=int(height), max_points=float(self.max_points) * scale,
+                    density=float(self.meta.get('density', 0.0)) * scale,
+                    source='retextured from %s %dx%d by paintrl_rasterize_texels' % (
+                        self.meta.get('part_name'), self.width, self.height))
+        return PartPack(meta, arrays)
 
     @property
     def n_texels(self):

@@ -1,0 +1,173 @@
+"""On-GPU rollout collection against the batched paint environment (BASELINE config C5).
+
+The reference collects PPO experience with RLlib: 15 CPU rollout workers, one PaintGymEnv each,
+`sample_batch_size` = 100 steps per fragment, `batch_mode` = truncate_episodes, a fully connected
+policy with hidden layers [256, 128] and a shared value branch (paint_ppo.py:170-195), and
+per-episode totals of reward / penalty / return gathered by callbacks (paint_ppo.py:36-72).  Ray and
+TensorFlow are absent here, so this module is the built-in torch stand-in SURVEY.md section 8(d) C5
+asks for: the same fragment shape and statistics, with the policy evaluated and sampled on the GPU
+the environments live on -- observations and actions never visit the host.
+
+One process per GPU owns a shard of the environments (`sharding.shard_range`); the step path has no
+collective; `iteration_stats` reduces the per-iteration statistics with one small all-reduce.
+The policy is a plain torch MLP (library GEMMs): it is the consumer of the hot path, not part of it.
+"""
+import math
+
+import torch
+
+from . import sharding
+
+
+class MlpPolicy(object):
+    """Fully connected policy of paint_ppo.py:179-183: obs -> 256 -> 128 -> {logits | mean, value},
+    tanh activations (RLlib's fcnet default), value branch sharing the hidden layers
+    (`vf_share_layers`).  Random-init FP32 weights; discrete actions are sampled with the Gumbel-max
+    trick, continuous ones from a unit-variance Gaussian around tanh(mean)."""
+
+    def __init__(self, obs_dim, n_out, hiddens=(256, 128), device=None, seed=0, discrete=True):
+        gen = torch.Generator(device='cpu')
+        gen.manual_seed(seed)
+        dims = [obs_dim] + list(hiddens)
+        self.layers = []
+        for i in range(len(hiddens)):
+            bound = 1.0 / math.sqrt(dims[i])
+            w = (torch.rand(dims[i], dims[i + 1], generator=gen) * 2 - 1) * bound
+            b = torch.zeros(dims[i + 1])
+            self.layers.append((w.to(device), b.to(device)))
+        bound = 1.0 / math.sqrt(dims[-1])
+        self.head_w = ((torch.rand(dims[-1], n_out + 1, generator=gen) * 2 - 1) * bound * 0.1).to(device)
+        self.head_b = torch.zeros(n_out + 1, device=device)
+        self.n_out = n_out
+        self.discrete = discrete
+        self.device = device
+        self.gen = torch.Generator(device=device)
+        self.gen.manual_seed(seed + 1)
+
+    def forward(self, obs):
+        """obs [B, obs_dim] (any float dtype) -> (logits or means [B, n_out], value [B]) in FP32."""
+        h = obs.to(torch.float32)
+        for w, b in self.layers:
+            h = torch.tanh(torch.addmm(b, h, w))
+        out = torch.addmm(self.head_b, h, self.head_w)
+        return out[:, :self.n_out], out[:, self.n_out]
+
+    def act(self, obs):
+        """Sample one action per environment: (actions, log-probability, value)."""
+        out, value = self.forward(obs)
+        if self.discrete:
+            logp_all = torch.log_softmax(out, dim=1)
+            u = torch.rand(out.shape, generator=self.gen, device=out.device).clamp_(1e-10, 1.0)
+            a = torch.argmax(logp_all - torch.log(-torch.log(u)), dim=1)
+            return a, logp_all.gather(1, a[:, None])[:, 0], value
+        mean = torch.tanh(out)
+        noise = torch.randn(out.shape, generator=self.gen, device=out.device)
+        a = mean + noise
+        logp = (-0.5 * noise * noise - 0.5 * math.log(2 * math.pi)).sum(dim=1)
+        return a.to(torch.float64), logp, value
+
+
+class RolloutFragment(object):
+    """Time-major buffers of one fragment: T steps of B environments, all on the device."""
+
+    def __init__(self, T, B, obs_dim, action_shape, device):
+        f64, f32 = torch.float64, torch.float32
+        self.T, self.B = T, B
+        self.obs = torch.zeros(T + 1, B, obs_dim, dtype=f64, device=device)     # obs[t] is what the policy saw at step t
+        self.term_obs = torch.zeros(T, B, obs_dim, dtype=f64, device=device)    # observation returned with step t (terminal if done)
+        self.actions = torch.zeros((T, B) + tuple(action_shape), dtype=torch.int64 if not action_shape else f64,
+                                   device=device)
+        self.reward = torch.zeros(T, B, dtype=f64, device=device)               # info['reward']   (robot_gym_env.py:368)
+        self.penalty = torch.zeros(T, B, dtype=f64, device=device)              # info['penalty']
+        self.actual = torch.zeros(T, B, dtype=f64, device=device)               # the gym reward = reward - penalty
+        self.done = torch.zeros(T, B, dtype=torch.uint8, device=device)
+        self.new_texels = torch.zeros(T, B, dtype=torch.int32, device=device)
+        self.logp = torch.zeros(T, B, dtype=f32, device=device)
+        self.value = torch.zeros(T + 1, B, dtype=f32, device=device)
+
+
+class RolloutWorker(object):
+    """Collects fragments from a `BatchedPaintEnv` created with `auto_reset=True`."""
+
+    def __init__(self, env, policy, fragment_length=100):
+        if not env.cfg.auto_reset:
+            raise ValueError('RolloutWorker needs an environment created with auto_reset=True')
+        self.env, self.policy, self.T = env, policy, int(fragment_length)
+        shape = () if env.cfg.action_mode == 'discrete' else (env.action_dim,)
+        self.frag = RolloutFragment(self.T, env.num_envs, env.obs_dim, shape, env.device)
+        dev, B = env.device, env.num_envs
+        # running per-episode totals (the reference's on_episode_step / on_episode_end callbacks)
+        self.ep_reward = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.ep_penalty = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.ep_len = torch.zeros(B, dtype=torch.int64, device=dev)
+        self._started = False
+
+    def start(self, start_index=None):
+        """Reset every environment; the first observation of the first fragment."""
+        self.frag.obs[0].copy_(self.env.reset(start_index))
+        self.ep_reward.zero_(); self.ep_penalty.zero_(); self.ep_len.zero_()
+        self._started = True
+
+    @torch.no_grad()
+    def collect(self):
+        """One fragment of T steps (truncate_episodes: episodes continue across fragments).
+        Returns (fragment, stats) where stats holds this rank's sums for `iteration_stats`; the
+        only host synchronisation is the read of those eight numbers at the end."""
+        if not self._started:
+            self.start()
+        f, env, pol = self.frag, self.env, self.policy
+        dev = env.device
+        acc = torch.zeros(6, dtype=torch.float64, device=dev)     # episodes, reward, penalty, return, new texels, max len
+        for t in range(self.T):
+            a, logp, value = pol.act(f.obs[t])
+            f.actions[t].copy_(a)
+            f.logp[t].copy_(logp)
+            f.value[t].copy_(value)
+            env.step_into(f.actions[t], f.term_obs[t], f.reward[t], f.penalty[t], f.actual[t], f.done[t],
+                          next_obs=f.obs[t + 1], new_texels=f.new_texels[t])
+            d = f.done[t].bool()
+            self.ep_reward += f.reward[t]
+            self.ep_penalty += f.penalty[t]
+            self.ep_len += 1
+            acc[0] += d.sum()
+            acc[1] += (self.ep_reward * d).sum()
+            acc[2] += (self.ep_penalty * d).sum()
+            acc[4] += f.new_texels[t].sum()
+            acc[5] = torch.maximum(acc[5], (self.ep_len * d).max().to(torch.float64))
+            keep = (~d).to(torch.float64)
+            self.ep_reward *= keep
+            self.ep_penalty *= keep
+            self.ep_len *= (~d)
+        f.value[self.T].copy_(pol.forward(f.obs[self.T])[1])      # bootstrap value of the truncated episodes
+        acc[3] = acc[1] - acc[2]
+        host = acc.cpu()
+        next_first = f.obs[self.T].clone()
+        stats = {'env_steps': float(self.T * env.num_envs), 'episodes': float(host[0]), 'sum_reward': float(host[1]),
+                 'sum_penalty': float(host[2]), 'sum_return': float(host[3]), 'new_texels': float(host[4]),
+                 'max_episode_len': float(host[5])}
+        self._next_first = next_first
+        return f, stats
+
+    def advance(self):
+        """Make the last observation of the collected fragment the first of the next one."""
+        self.frag.obs[0].copy_(self._next_first)
+
+
+def gae(frag, gamma=0.99, lam=1.0):
+    """Generalised advantage estimates over a fragment (RLlib PPO defaults gamma 0.99, lambda 1.0):
+    advantages and value targets [T, B] in FP32; `done` cuts the bootstrap."""
+    T = frag.T
+    adv = torch.zeros(T, frag.B, dtype=torch.float32, device=frag.value.device)
+    last = torch.zeros(frag.B, dtype=torch.float32, device=frag.value.device)
+    r = frag.actual.to(torch.float32)
+    nd = 1.0 - frag.done.to(torch.float32)
+    for t in range(T - 1, -1, -1):
+        delta = r[t] + gamma * frag.value[t + 1] * nd[t] - frag.value[t]
+        last = delta + gamma * lam * nd[t] * last
+        adv[t] = last
+    return adv, adv + frag.value[:T]
+
+
+def iteration_stats(stats, device=None):
+    """All-reduce one iteration's rollout statistics over the ranks (sums; maxima for `max_*`)."""
+    return sharding.allreduce_stats(stats, device=device)

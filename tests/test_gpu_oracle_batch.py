@@ -33,13 +33,21 @@ CASES = {
 }
 
 
-def _run_case(extra, kw, num_envs, steps, device, auto_reset=True):
-    from oracle.oracle import OracleBatch, action_directions
+def _run_case(extra, kw, num_envs, steps, device, auto_reset=True, texture=None, status_every=7):
+    from oracle.oracle import OracleBatch, action_directions, retextured_pack
     from paintrl_b200.batched_env import BatchedPaintEnv
     cfg = EnvConfig(extra, auto_reset=auto_reset, **kw)
     pack = PartPack.for_part(cfg.part_no)
-    env = BatchedPaintEnv(num_envs, cfg, device=device, pack=pack)
-    ora = OracleBatch(pack, cfg, num_envs)
+    if texture is None:
+        env = BatchedPaintEnv(num_envs, cfg, device=device, pack=pack)
+        ora = OracleBatch(pack, cfg, num_envs)
+    else:
+        # the engine rasterises its texels on the GPU, the oracle with its own C restatement
+        env = BatchedPaintEnv(num_envs, cfg, device=device, texture_size=texture)
+        opack = retextured_pack(pack, *texture)
+        assert np.array_equal(env.pack.front_ij, opack.front_ij) and np.array_equal(env.pack.front_pos, opack.front_pos)
+        assert env.pack.max_points == opack.max_points
+        ora = OracleBatch(opack, cfg, num_envs)
     rng = np.random.default_rng(20261017)
     n_starts = env.n_starts
     start = rng.integers(0, n_starts, size=num_envs).astype(np.int32)
@@ -73,7 +81,7 @@ def _run_case(extra, kw, num_envs, steps, device, auto_reset=True):
             assert np.array_equal(info['penalty'].cpu().numpy(), p_o), ctx
             assert np.array_equal(a_g, a_o), ctx
         # status planes: bit-exact, before the oracle side applies the auto-reset
-        if t % 7 == 0 or t == steps - 1:
+        if t % status_every == 0 or t == steps - 1:
             pre_reset = env.get_state()['status'].cpu().numpy()
             for e in range(num_envs):
                 if not d_o[e] or not auto_reset:
@@ -112,5 +120,41 @@ def test_host_step_matches_device_step(cuda_device):
         assert np.array_equal(actual.cpu().numpy(), out['actual'])
         assert np.array_equal(done.cpu().numpy(), out['done'])
         assert np.array_equal(info['reward'].cpu().numpy(), out['reward'])
+        assert np.array_equal(info['penalty'].cpu().numpy(), out['penalty'])
+        assert np.array_equal(info['next_obs'].cpu().numpy(), out['next_obs'])
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize('auto_reset', [True, False])
+def test_host_step_scattered_buffers(cuda_device, auto_reset):
+    """paintrl_step_host merges device->host copies when the host buffers are carved from one
+    allocation (host_buffers); separately allocated, unpinned buffers must give the same results."""
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    n = 48
+    cfg = dict(BASE)
+    a = BatchedPaintEnv(n, cfg, device=cuda_device, auto_reset=auto_reset, seed=5)
+    b = BatchedPaintEnv(n, cfg, device=cuda_device, auto_reset=auto_reset, seed=5)
+    start = np.arange(n, dtype=np.int32) % 4
+    a.reset(start)
+    b.reset(start)
+    rng = np.random.default_rng(4)
+    one = a.host_buffers(pinned=True)
+    od = a.obs_dim
+    scattered = {'obs': np.zeros((n, od)), 'next_obs': np.full((n, od), -7.0), 'done': np.zeros(n, np.uint8),
+                 'actual': np.zeros(n), 'penalty': np.zeros(n), 'reward': np.zeros(n)}
+    for _ in range(30):
+        acts = rng.integers(0, 4, size=n)
+        a.step_host(acts, one)
+        b.step_host(acts, scattered)
+        for k in ('obs', 'reward', 'penalty', 'actual', 'done', 'next_obs'):
+            assert np.array_equal(one[k], scattered[k]), k
+    no_next = {k: v for k, v in a.host_buffers(pinned=False, next_obs=False).items()}
+    assert 'next_obs' not in no_next
+    acts = rng.integers(0, 4, size=n)
+    a.step_host(acts, no_next)
+    b.step_host(acts, scattered)
+    for k in ('obs', 'reward', 'penalty', 'actual', 'done'):
+        assert np.array_equal(no_next[k], scattered[k]), k
     a.close()
     b.close()
