@@ -187,6 +187,61 @@ def run_reference(args, workload, rank, world_size):
     print(json.dumps(line), flush=True)
 
 
+def run_rollout(args, workload, env, cfg, rank, world_size, device, warmup):
+    """--rollout: fragments of 100 steps collected by paintrl_b200.rollout (policy obs->256->128->{logits, value}
+    evaluated and sampled on the GPU, paint_ppo.py:179-190), one all-reduce of rollout statistics per fragment."""
+    import torch
+    import torch.distributed as dist
+    from paintrl_b200 import rollout, sharding
+    T = 100
+    n_out = cfg.discrete_granularity if cfg.action_mode == 'discrete' else cfg.action_dim
+    policy = rollout.MlpPolicy(env.obs_dim, n_out, device=device, seed=rank, discrete=cfg.action_mode == 'discrete')
+    worker = rollout.RolloutWorker(env, policy, fragment_length=T)
+    worker.start()
+    for _ in range(max(1, min(warmup, 2))):
+        worker.collect(); worker.advance()
+    torch.cuda.synchronize(device)
+    if world_size > 1:
+        dist.barrier()
+    sampler = ClockSampler(physical_gpu_index(int(os.environ.get('LOCAL_RANK', 0))))
+    sampler.start()
+    s0 = env.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total = {}
+    e0.record()
+    for _ in range(args.steps):
+        _, st = worker.collect()
+        worker.advance()
+        red = rollout.iteration_stats(st, device=device)
+        for k, v in red.items():
+            total[k] = max(total.get(k, 0.0), v) if k.startswith('max') else total.get(k, 0.0) + v
+    e1.record()
+    torch.cuda.synchronize(device)
+    if world_size > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    s1 = env.stats()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank == 0:
+        print(json.dumps({
+            'metric': METRIC, 'value': total['env_steps'] / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world_size, 'steps': args.steps,
+            'warmup': warmup, 'ms_per_step': ms / (args.steps * T), 'higher_is_better': True, 'scaling': workload['scaling'],
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': workload['name'] + '; rollout fragments of %d steps with the on-GPU MLP policy '
+                       '(obs->256->128->logits+value, FP32, random init), one stats all-reduce per fragment' % T,
+                       'envs_per_gpu': env.num_envs, 'l2': 'not flushed (policy and fragment traffic between steps)',
+                       'timing': 'CUDA events around all fragments, max over ranks',
+                       'parallelism': 'env-sharded x%d, no step-path collective' % world_size},
+            'clocks': clocks, 'gpu_launches': s1['kernel_launches'] - s0['kernel_launches'], 'rollout_stats': total}), flush=True)
+    env.close()
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -197,6 +252,9 @@ def main():
     ap.add_argument('--envs', type=int, default=None, help='override environments per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-flush', action='store_true', help='keep the L2 warm between steps (not the headline)')
+    ap.add_argument('--rollout', action='store_true',
+                    help='time whole rollout fragments (on-GPU MLP policy + env step, paintrl_b200.rollout) instead of bare steps; '
+                         '--steps counts fragments of 100 steps (BASELINE config C5 / paint_ppo.py sample_batch_size)')
     args = ap.parse_args()
     workload = WORKLOADS[args.workload]
 
@@ -227,6 +285,9 @@ def main():
     cfg = EnvConfig(workload['extra'], auto_reset=True, seed=1234 + rank, **workload['kw'])
     env = BatchedPaintEnv(n_env, cfg, device=device, texture_size=workload.get('texture', (240, 240)))
 
+    if args.rollout:
+        run_rollout(args, workload, env, cfg, rank, world_size, device, warmup)
+        return
     gen = torch.Generator(device=device)
     gen.manual_seed(1234 + rank)
     e2e_steps = max(10, min(args.steps, 200))
@@ -278,13 +339,16 @@ def main():
     for i in range(3):
         env.step_host(host_actions[i], host_out)
     barrier()
-    t0 = time.perf_counter()
+    e2e_runs = []
     checksum = 0.0
-    for i in range(e2e_steps):
-        env.step_host(host_actions[i], host_out)
-        checksum += float(host_out['actual'][0])
-    torch.cuda.synchronize(device)
-    e2e_s = time.perf_counter() - t0
+    for rep in range(5):                      # median of 5 repeats: the host side of this leg is noisy
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            env.step_host(host_actions[i], host_out)
+            checksum += float(host_out['actual'][0])
+        torch.cuda.synchronize(device)
+        e2e_runs.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(e2e_runs))
     act_bytes = int(host_actions[0].nbytes)
     d2h_bytes = int(sum(host_out[k].nbytes for k in ('obs', 'reward', 'penalty', 'actual', 'next_obs', 'done')))
 
@@ -322,7 +386,7 @@ def main():
                        'parallelism': 'env-sharded x%d, no step-path collective' % world_size},
             'clocks': clocks,
             'e2e': {'value': total_envs * e2e_steps / e2e_s_max, 'unit': UNIT, 'h2d_bytes_per_step': act_bytes,
-                    'd2h_bytes_per_step': d2h_bytes, 'steps': e2e_steps, 'api': 'BatchedPaintEnv.step_host -> paintrl_step_host'},
+                    'd2h_bytes_per_step': d2h_bytes, 'steps': e2e_steps, 'repeats': 5, 'statistic': 'median repeat', 'api': 'BatchedPaintEnv.step_host -> paintrl_step_host'},
             'gpu_launches': s1['kernel_launches'] - s0['kernel_launches'],
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': captured_traffic(args.workload), 'traffic_unit': 'bytes per step (ncu capture, profiles/)',

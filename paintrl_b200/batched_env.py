@@ -165,20 +165,26 @@ class BatchedPaintEnv(object):
 
     def step_host(self, actions, out=None):
         """The same step through HOST buffers (paintrl_step_host): actions are copied host->device
-        and obs / reward / penalty / actual / done device->host inside the call."""
+        and obs / reward / penalty / actual / done (/ next_obs) device->host inside the call."""
         B = self.num_envs
-        if self.cfg.action_mode == 'discrete':
-            a = np.ascontiguousarray(actions, dtype=np.int64).reshape(B)
-        else:
-            a = np.ascontiguousarray(actions, dtype=np.float64).reshape(B, self.action_dim)
+        discrete = self.cfg.action_mode == 'discrete'
+        want = np.int64 if discrete else np.float64
+        a = actions
+        if not (isinstance(a, np.ndarray) and a.dtype == want and a.flags.c_contiguous):
+            a = np.ascontiguousarray(actions, dtype=want)
+        if a.size != (B if discrete else B * self.action_dim):
+            raise ValueError('expected %d actions' % B)
         if out is None:
             out = self.host_buffers()
-        nxt = out.get('next_obs')
-        _capi.check(self._lib.paintrl_step_host(
-            self._h, ctypes.c_void_p(a.ctypes.data), ctypes.c_void_p(out['obs'].ctypes.data),
-            ctypes.c_void_p(out['reward'].ctypes.data), ctypes.c_void_p(out['penalty'].ctypes.data),
-            ctypes.c_void_p(out['actual'].ctypes.data), ctypes.c_void_p(out['done'].ctypes.data),
-            ctypes.c_void_p(nxt.ctypes.data) if nxt is not None else None, self._stream()))
+        ptrs = out.get('_ptrs')
+        if ptrs is None:       # buffers not made by host_buffers(): resolve the addresses every call
+            nxt = out.get('next_obs')
+            ptrs = tuple(out[k].ctypes.data for k in ('obs', 'reward', 'penalty', 'actual', 'done')) + (
+                nxt.ctypes.data if nxt is not None else None,)
+        rc = self._lib.paintrl_step_host(self._h, a.ctypes.data, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5],
+                                         torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            _capi.check(rc)
         return out
 
     def host_buffers(self, pinned=True, next_obs=True):
@@ -195,6 +201,8 @@ class BatchedPaintEnv(object):
             out['next_obs'] = f64[B * od + 3 * B:].reshape(B, od)
         out['done'] = raw[n_f64 * 8:].numpy()
         out['_storage'] = raw
+        out['_ptrs'] = tuple(out[k].ctypes.data for k in ('obs', 'reward', 'penalty', 'actual', 'done')) + (
+            out['next_obs'].ctypes.data if next_obs else None,)
         return out
 
     # ------------------------------------------------------------------ state

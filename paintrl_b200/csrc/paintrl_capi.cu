@@ -936,9 +936,9 @@ int paintrl_step_host(PaintrlHandle h, const void *actions_host, double *obs_hos
     const size_t nenv = (size_t)h->num_envs;
     const size_t abytes = (h->cfg.action_mode == 0 ? sizeof(long long) : sizeof(double) * h->cfg.action_shape) * nenv;
     const size_t obytes = sizeof(double) * h->cfg.obs_dim * nenv;
+    const bool want_next = next_obs_host != nullptr, dev_next = want_next && h->cfg.auto_reset;
     CUDA_TRY(cudaMemcpyAsync(h->stage_actions, actions_host, abytes, cudaMemcpyHostToDevice, s));
     // device staging in the order obs | reward | penalty | actual | [next_obs] | done, no gaps
-    const bool want_next = next_obs_host != nullptr, dev_next = want_next && h->cfg.auto_reset;
     unsigned char *d = h->stage_out;
     double *d_obs = reinterpret_cast<double *>(d);
     double *d_sc = reinterpret_cast<double *>(d + obytes);

@@ -24,6 +24,9 @@ def test_fragment_replays_through_the_oracle(cuda_device):
     start = (np.arange(n) % env.n_starts).astype(np.int32)
     worker.start(start)
     ora = OracleBatch(pack, cfg, n)
+    probe = OracleBatch(pack, cfg, 1)
+    reset_obs = [probe.reset(np.array([i], np.int32))[0].copy() for i in range(env.n_starts)]
+    probe.close()
     assert np.array_equal(worker.frag.obs[0].cpu().numpy(), ora.reset(start))
     totals = {'episodes': 0.0, 'sum_reward': 0.0, 'sum_penalty': 0.0, 'new_texels': 0.0, 'max_episode_len': 0.0}
     ep_r, ep_p, ep_l = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.int64)
@@ -46,18 +49,12 @@ def test_fragment_replays_through_the_oracle(cuda_device):
                 exp['sum_reward'] += ep_r[ids].sum(); exp['sum_penalty'] += ep_p[ids].sum()
                 exp['max_episode_len'] = max(exp['max_episode_len'], float(ep_l[ids].max()))
                 ep_r[ids] = 0; ep_p[ids] = 0; ep_l[ids] = 0
-                # the engine drew the new episodes' start points from its own seeded stream: follow it
-                st = env.get_state(env_ids=ids, status=False)
-                for k, e in enumerate(ids):
-                    pose = st['pose'][k].cpu().numpy()
-                    idx = int(np.argmin(np.abs(pack.start_points(cfg.start_point_mode)[:, 0, :] - pose).sum(1))) \
-                        if int(st['step_counter'][k]) == 0 else None
-                    if idx is None:
-                        # the environment already stepped again in this fragment: look its start up by observation
-                        cands = [i for i in range(env.n_starts)
-                                 if np.array_equal(OracleBatch(pack, cfg, 1).reset(np.array([i], np.int32))[0], nxt[e])]
-                        idx = cands[0]
-                    assert np.array_equal(ora.reset(np.array([idx], np.int32), env_ids=[int(e)])[0], nxt[e])
+                # the engine drew the new episodes' start points from its own seeded stream: follow it by
+                # matching the first observation of the new episode against each start point's
+                for e in ids:
+                    idx = [i for i in range(env.n_starts) if np.array_equal(reset_obs[i], nxt[e])]
+                    assert len(idx) == 1, (it, t, e)
+                    assert np.array_equal(ora.reset(np.array(idx, np.int32), env_ids=[int(e)])[0], nxt[e])
         for k in totals:
             totals[k] = max(totals[k], stats[k]) if k.startswith('max') else totals[k] + stats[k]
         adv, target = gae(f)
