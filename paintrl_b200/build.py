@@ -41,6 +41,7 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     extra = ['-DPAINTRL_PROFILE'] if os.environ.get('PAINTRL_PROFILE') else []   # phase timing build (profiles/)
+    extra += ['-DPAINTRL_TRACE'] if os.environ.get('PAINTRL_TRACE') else []     # per-warp timeline build (profiles/timeline.py)
     cmd = [nvcc_path()] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + SOURCES + ['-o', LIB]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:

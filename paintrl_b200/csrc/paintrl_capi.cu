@@ -73,6 +73,13 @@ struct PaintrlEngine {
     int16_t *thick = nullptr;        // [num_envs][n_slots] HSI thickness plane (HSI only)
     unsigned *grid_cnt = nullptr;    // [num_envs][n_gcells_pad] (grid observation only)
     unsigned long long *stats = nullptr;
+    unsigned *ready = nullptr;       // [num_envs] per-environment move -> paint hand-off flags (step sequence numbers)
+    // PAINTRL_CARVEOUT=<percent>: ask for the same L1 / shared-memory split for both step kernels, so that paint CTAs can
+    // share an SM with the move kernel's last wave (CTAs of kernels with different carveouts cannot).  Off by default:
+    // measured slower at C2 (the move phase loses L1 and issue slots to the co-resident paint warps).
+    int carveout_percent = -1;
+    bool carveout_set = false;       // the step kernels' shared-memory carveout has been requested on this device
+    unsigned step_seq = 0;           // sequence number of the last step launched
     // staging for the host-buffer entry points
     void *stage_actions = nullptr;
     // paintrl_step_host: one contiguous block, laid out per call as obs | reward | penalty | actual | [next_obs] | done,
@@ -81,6 +88,7 @@ struct PaintrlEngine {
     unsigned long long launches = 0;
     double move_cell_planes_mean = 0.0, move_cell_verts_mean = 0.0;
     int move_lanes = 32;             // lanes per environment in move_kernel (8, 16 or 32)
+    int move_warps = 4, paint_warps = 1;   // warps per block of the two step kernels (1, 2 or 4)
     int move_minb = 4;               // its __launch_bounds__ min blocks per SM (4: 128 registers ... 7: 72)
     bool force_unstaged = false;     // PAINTRL_FORCE_UNSTAGED: run the global-memory bit-plane path (tests)
 };
@@ -136,7 +144,7 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
     std::vector<int> pidx;            // the current cell's plane indices
     std::vector<VertCand> vcs;        // the current cell's vertex candidates
     size_t plane_refs = 0;
-    const double kPadBelow = 5e-4, kPadAbove = 1e-4, kFootSlack = 1e-6, kMargin = 1e-9, kVertSlack = 1e-9;
+    const double kPadBelow = 5e-4, kPadBelowEdge = 0.025, kPadAbove = 1e-4, kFootSlack = 1e-6, kMargin = 1e-9, kVertSlack = 1e-9;
     const int K = 5;
     // the tool hovers on the side the start normals point away from and looks along them
     const double side = pack->start_normal[np] <= 0.0 ? 1.0 : -1.0;
@@ -192,6 +200,13 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
                     region = std::isfinite(fa) && std::isfinite(fb) && std::isfinite(fc);
                 }
             }
+            if (!region && hits >= 1) {
+                // a corner or one edge of the footprint under the hull (too few samples, or all on one line:
+                // the fit is singular): constant plane through the mean sampled depth
+                fa = fb = fc = 0;
+                for (int q = 0; q < hits; ++q) fa += sd[q] / hits;
+                region = std::isfinite(fa);
+            }
             if (region) {
                 // ---- the hull surface passes over the cell: region hugging it
                 double rmin = INFINITY, rmax = -INFINITY;
@@ -199,8 +214,13 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
                     const double res = sd[q] - (fa + fb * sx[q] + fc * sy[q]);
                     rmin = std::min(rmin, res); rmax = std::max(rmax, res);
                 }
-                // tool side is +side: above the surface = larger side * depth
-                const double rlo = rmin - (side > 0 ? kPadBelow : kPadAbove), rhi = rmax + (side > 0 ? kPadAbove : kPadBelow);
+                // tool side is +side: above the surface = larger side * depth.  A cell the silhouette of the hull
+                // runs through (not every sample ray hit) also holds part of the hull's side wall, which tilted rays
+                // enter well below the tool-side surface: its slab reaches kPadBelowEdge down (measured: entry
+                // points up to 14 mm below the fitted plane; such cells sent 1 % of the environments through
+                // the verify pass on every sub-step and were the tail of the move phase).
+                const double below = hits < K * K ? kPadBelowEdge : kPadBelow;
+                const double rlo = rmin - (side > 0 ? below : kPadAbove), rhi = rmax + (side > 0 ? kPadAbove : below);
                 mc.a = fa - fb * mid0 - fc * mid1;
                 mc.b = fb;
                 mc.c = fc;
@@ -620,6 +640,8 @@ EnvArrays env_arrays(PaintrlEngine *e) {
     ea.bits = e->bits;
     ea.thick = e->thick;
     ea.grid_cnt = e->grid_cnt;
+    ea.ready = e->ready;
+    ea.seq = e->step_seq;
     return ea;
 }
 
@@ -705,6 +727,19 @@ int paintrl_debug_profile(unsigned long long *out64, int reset) {
 #endif
 }
 
+/* Debug only: the last step's phase cycles per environment ([n][32] u32, slot 14 = the move counters). */
+int paintrl_debug_profile_env(unsigned *out, int n) {
+#ifdef PAINTRL_PROFILE
+    cudaDeviceSynchronize();
+    n = std::min(n, 65536);
+    if (out && n > 0) cudaMemcpyFromSymbol(out, g_prof_env, (size_t)n * 32 * sizeof(unsigned));
+    return n;
+#else
+    (void)out; (void)n;
+    return 0;
+#endif
+}
+
 /* Debug only: rays that left the fast path (instrumented build); returns the number copied (<= max_rays). */
 int paintrl_debug_rays(double *out, int max_rays, int reset) {
 #ifdef PAINTRL_PROFILE
@@ -720,6 +755,20 @@ int paintrl_debug_rays(double *out, int max_rays, int reset) {
     return n;
 #else
     (void)out; (void)max_rays; (void)reset;
+    return 0;
+#endif
+}
+
+/* Debug only: the last step's per-environment timeline of a -DPAINTRL_TRACE build ([n][8] u64: move start / end,
+ * paint start / dependency resolved / inputs loaded / end (globaltimer ns), move SM, paint SM); returns rows copied. */
+int paintrl_debug_trace(unsigned long long *out, int n) {
+#ifdef PAINTRL_TRACE
+    cudaDeviceSynchronize();
+    n = std::min(n, 65536);
+    if (out && n > 0) cudaMemcpyFromSymbol(out, g_trace, (size_t)n * 8 * sizeof(unsigned long long));
+    return n;
+#else
+    (void)out; (void)n;
     return 0;
 #endif
 }
@@ -794,6 +843,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
               (thick_bytes == 0 || e->arena.alloc((void **)&e->thick, thick_bytes) == cudaSuccess) &&
               (gcnt_bytes == 0 || e->arena.alloc((void **)&e->grid_cnt, gcnt_bytes) == cudaSuccess) &&
               e->arena.alloc((void **)&e->stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              e->arena.alloc((void **)&e->ready, sizeof(unsigned) * (size_t)num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&reset_obs, sizeof(double) * od * (size_t)e->pk.n_starts) == cudaSuccess &&
               e->arena.alloc(&e->stage_actions, adim * num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&e->stage_out, (sizeof(double) * (2 * od + 3) + 1) * (size_t)num_envs) == cudaSuccess;
@@ -805,6 +855,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     if (e->thick) cudaMemset(e->thick, 0, thick_bytes);
     if (e->grid_cnt) cudaMemset(e->grid_cnt, 0, gcnt_bytes);
     cudaMemset(e->stats, 0, 4 * sizeof(unsigned long long));
+    cudaMemset(e->ready, 0, sizeof(unsigned) * (size_t)num_envs);
     // observation of a fresh environment at every start point, from environment 0's all-zero planes
     e->pk.reset_obs = reset_obs;
     reset_obs_kernel<<<(e->pk.n_starts + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32>>>(
@@ -819,6 +870,12 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
         int lanes = ml ? atoi(ml) : (num_envs <= 16384 ? 32 : 8);
         e->move_lanes = (lanes == 16 || lanes == 8) ? lanes : 32;
         e->force_unstaged = getenv("PAINTRL_FORCE_UNSTAGED") != nullptr;
+        const char *mw = getenv("PAINTRL_MOVE_WARPS"), *pwv = getenv("PAINTRL_PAINT_WARPS");
+        const int mwi = mw ? atoi(mw) : 4, pwi = pwv ? atoi(pwv) : 1;
+        e->move_warps = (mwi == 1 || mwi == 2) ? mwi : 4;
+        e->paint_warps = (pwi == 4 || pwi == 2) ? pwi : 1;   // one warp per block: a finished environment frees its slot at once
+        const char *co = getenv("PAINTRL_CARVEOUT");
+        e->carveout_percent = co ? std::min(100, std::max(-1, atoi(co))) : -1;
         const char *mb = getenv("PAINTRL_MOVE_MINB");
         e->move_minb = mb ? std::min(7, std::max(4, atoi(mb))) : 4;
     }
@@ -874,15 +931,20 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     io.actual = actual_dev; io.done = done_dev; io.new_texels = new_texels_dev;
     io.next_obs = h->cfg.auto_reset ? next_obs_dev : nullptr;
     io.reset_start_idx = reset_start_idx_dev;
-    const int blocks = (h->num_envs + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    h->step_seq += 1;
+    if (h->step_seq == 0) h->step_seq = 1;   // 0 is the flags' initial value
     {   // lanes per environment in the move phase: fewer when there are enough environments to fill the GPU
-        const int threads = kWarpsPerBlock * 32;
+        const int threads = h->move_warps * 32;
         cudaStream_t ms = as_stream(stream);
         const int L = h->move_lanes;
         const int mblocks = (int)(((long long)h->num_envs * L + threads - 1) / threads);
         const bool ax12m = h->pk.axis0 == 1 && h->pk.axis1 == 2;
 #define PAINTRL_MOVE(G, MINB)                                                                                              \
     do {                                                                                                                   \
+        if (!h->carveout_set && h->carveout_percent >= 0) {                                                                \
+            cudaFuncSetAttribute(move_kernel<G, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout_percent);  \
+            cudaFuncSetAttribute(move_kernel<G, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout_percent); \
+        }                                                                                                                  \
         if (ax12m) move_kernel<G, MINB, true><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);  \
         else move_kernel<G, MINB, false><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);       \
     } while (0)
@@ -900,7 +962,8 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     int rc = launch_check(h, "move_kernel");
     if (rc != PAINTRL_OK) return rc;
     const bool staged = h->pk.n_words_pad <= kStageWords && !h->force_unstaged;
-    const dim3 grid(blocks), block(kWarpsPerBlock * 32);
+    const int pw = h->paint_warps;
+    const dim3 grid((h->num_envs + pw - 1) / pw), block(pw * 32);
     cudaStream_t s = as_stream(stream);
     const bool ax12 = h->pk.axis0 == 1 && h->pk.axis1 == 2;
     // programmatic dependent launch after move_kernel (see griddepcontrol.* in the kernels)
@@ -911,10 +974,19 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     lattr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = lattr; lc.numAttrs = 1;
     const EnvArrays pea = env_arrays(h);
-#define PAINTRL_PAINT(C, ST)                                                                              \
-    do {                                                                                                  \
-        if (ax12) cudaLaunchKernelEx(&lc, paint_kernel<C, ST, true>, h->pk, h->cfg, pea, h->num_envs, io);  \
-        else cudaLaunchKernelEx(&lc, paint_kernel<C, ST, false>, h->pk, h->cfg, pea, h->num_envs, io);      \
+#define PAINTRL_PAINT_W(C, ST, W)                                                                           \
+    do {                                                                                                    \
+        if (!h->carveout_set && h->carveout_percent >= 0) {                                                 \
+            cudaFuncSetAttribute(paint_kernel<C, ST, true, W>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout_percent);  \
+            cudaFuncSetAttribute(paint_kernel<C, ST, false, W>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout_percent); \
+        }                                                                                                   \
+        if (ax12) cudaLaunchKernelEx(&lc, paint_kernel<C, ST, true, W>, h->pk, h->cfg, pea, h->num_envs, io);  \
+        else cudaLaunchKernelEx(&lc, paint_kernel<C, ST, false, W>, h->pk, h->cfg, pea, h->num_envs, io);      \
+    } while (0)
+#define PAINTRL_PAINT(C, ST)                                                                 \
+    do {                                                                                     \
+        if (pw == 1) PAINTRL_PAINT_W(C, ST, 1); else if (pw == 2) PAINTRL_PAINT_W(C, ST, 2); \
+        else PAINTRL_PAINT_W(C, ST, 4);                                                      \
     } while (0)
     if (h->color == 0) {
         if (staged) PAINTRL_PAINT(0, true); else PAINTRL_PAINT(0, false);
@@ -922,6 +994,8 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
         if (staged) PAINTRL_PAINT(1, true); else PAINTRL_PAINT(1, false);
     }
 #undef PAINTRL_PAINT
+#undef PAINTRL_PAINT_W
+    h->carveout_set = true;
     return launch_check(h, "paint_kernel");
 }
 

@@ -16,20 +16,48 @@ namespace paintrl {
 // PAINTRL_PROF marks, summed over environments into a 64-slot device array.
 #ifdef PAINTRL_PROFILE
 __device__ unsigned long long g_prof[64];
-#define PAINTRL_PROF_BEGIN long long prof_t = clock64();
+__device__ unsigned g_prof_env[65536][32];   // the same marks per environment, last step only (profiles/phase_profile.py --per-env)
+#define PAINTRL_PROF_BEGIN(envidx, lo, hi)                                                \
+    long long prof_t = clock64();                                                         \
+    unsigned *prof_row = g_prof_env[(envidx) < 65536 ? (envidx) : 65535];                 \
+    if ((threadIdx.x & 31) == 0) for (int prof_k = (lo); prof_k < (hi); ++prof_k) prof_row[prof_k] = 0;
 #define PAINTRL_PROF(slot, leader)                                                        \
     do {                                                                                  \
         long long prof_now = clock64();                                                   \
-        if (leader) atomicAdd(&g_prof[slot], (unsigned long long)(prof_now - prof_t));    \
+        if (leader) {                                                                     \
+            atomicAdd(&g_prof[slot], (unsigned long long)(prof_now - prof_t));            \
+            if ((threadIdx.x & 31) == 0) prof_row[(slot) & 31] += (unsigned)(prof_now - prof_t); \
+        }                                                                                 \
         prof_t = prof_now;                                                                \
     } while (0)
-#define PAINTRL_PROF_PARAM , long long &prof_t
-#define PAINTRL_PROF_PASS , prof_t
+#define PAINTRL_PROF_PARAM , long long &prof_t, unsigned *prof_row
+#define PAINTRL_PROF_PASS , prof_t, prof_row
 #else
-#define PAINTRL_PROF_BEGIN
+#define PAINTRL_PROF_BEGIN(envidx, lo, hi)
 #define PAINTRL_PROF(slot, leader) do {} while (0)
 #define PAINTRL_PROF_PARAM
 #define PAINTRL_PROF_PASS
+#endif
+
+// Optional per-warp timeline (build with -DPAINTRL_TRACE; profiles/timeline.py): %globaltimer at the start and
+// end of each environment's move and paint work plus the SM it ran on, last step only.
+#ifdef PAINTRL_TRACE
+__device__ unsigned long long g_trace[65536][8];
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned trace_smid() {
+    unsigned s;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+    return s;
+}
+#define PAINTRL_TRACE_MARK(env, slot, leader) do { if ((leader) && (env) < 65536) g_trace[env][slot] = trace_now(); } while (0)
+#define PAINTRL_TRACE_SM(env, slot, leader) do { if ((leader) && (env) < 65536) g_trace[env][slot] = trace_smid(); } while (0)
+#else
+#define PAINTRL_TRACE_MARK(env, slot, leader) do {} while (0)
+#define PAINTRL_TRACE_SM(env, slot, leader) do {} while (0)
 #endif
 
 constexpr double kPaintRadius = 0.051;        // bullet_paint_wrapper.py:42
@@ -385,12 +413,63 @@ constexpr double kVerifyMargin = 1e-9;
 template <int G>
 __device__ __forceinline__ int near_violations(const double2 *planes, int n, const Vec3 &h, const Grp &g) {
     int c = 0;
-    for (int i = g.gl; i < n; i += G) {
+    int i = g.gl;
+    // long lists (the whole plane table): four planes per lane in flight, their loads issued together
+    for (; i + 3 * G < n; i += 4 * G) {
+        double2 lo[4], hi[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { lo[k] = __ldg(planes + 2 * (i + k * G)); hi[k] = __ldg(planes + 2 * (i + k * G) + 1); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double sd = fma(hi[k].x, h.z, fma(lo[k].y, h.y, lo[k].x * h.x)) - hi[k].y;
+            c += (sd > -kVerifyMargin) ? 1 : 0;
+        }
+    }
+    for (; i < n; i += G) {
         const double2 lo = __ldg(planes + 2 * i), hi2 = __ldg(planes + 2 * i + 1);
         double sd = fma(hi2.x, h.z, fma(lo.y, h.y, lo.x * h.x)) - hi2.y;
         c += (sd > -kVerifyMargin) ? 1 : 0;
     }
     return grp_sum<G>(c, g);
+}
+
+// The slab test over the WHOLE plane table (the slow path of ray_test), tracking the planes that attain
+// t_in / t_out.  Same per-plane arithmetic as slab_pass; two planes per lane in flight and a branch-free
+// body, so the loads and the two FP64 divisions of an iteration overlap.
+template <int G>
+__device__ __forceinline__ SlabResult slab_pass_all(const double2 *planes, int n, const Vec3 &frm, double d0, double d1, double d2,
+                                                    const Grp &g, unsigned *args) {
+    double t_in = -INFINITY, t_out = INFINITY;
+    bool outside = false;
+    int a_in = 0xffff, a_out = 0xffff;
+    auto one = [&](int i, const double2 &lo, const double2 &hi2) {
+        const double den = (lo.x * d0 + lo.y * d1) + hi2.x * d2;
+        const double num = hi2.y - ((lo.x * frm.x + lo.y * frm.y) + hi2.x * frm.z);
+        const double t = num / (den == 0.0 ? 1.0 : den);
+        outside |= (den == 0.0 && num < 0.0);
+        const bool ent = den < 0.0, ext = den > 0.0;
+        if (ent && t > t_in) a_in = i;
+        if (ext && t < t_out) a_out = i;
+        t_in = ent ? fmax(t_in, t) : t_in;
+        t_out = ext ? fmin(t_out, t) : t_out;
+    };
+    int i = g.gl;
+    for (; i + G < n; i += 2 * G) {
+        const double2 lo0 = __ldg(planes + 2 * i), hi0 = __ldg(planes + 2 * i + 1);
+        const double2 lo1 = __ldg(planes + 2 * (i + G)), hi1 = __ldg(planes + 2 * (i + G) + 1);
+        one(i, lo0, hi0);
+        one(i + G, lo1, hi1);
+    }
+    if (i < n) one(i, __ldg(planes + 2 * i), __ldg(planes + 2 * i + 1));
+    SlabResult r;
+    r.t_in = grp_max<G>(t_in, g);
+    r.t_out = grp_min<G>(t_out, g);
+    r.outside = grp_any<G>(outside, g);
+    const unsigned m_in = grp_ballot<G>(t_in == r.t_in && a_in != 0xffff, g), m_out = grp_ballot<G>(t_out == r.t_out && a_out != 0xffff, g);
+    const int w_in = m_in ? __shfl_sync(g.mask, a_in, g.base + __ffs(m_in) - 1) : 0xffff;
+    const int w_out = m_out ? __shfl_sync(g.mask, a_out, g.base + __ffs(m_out) - 1) : 0xffff;
+    *args = (unsigned)min(w_in, 0xffff) | ((unsigned)min(w_out, 0xffff) << 16);
+    return r;
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -458,15 +537,21 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Ax &ax, const 
     // the TCP hovers kHookDistance above the surface: first guess = the point that far along the ray;
     // later guesses = the entry point of the previous cell's list
     Vec3 h = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
+#ifdef PAINTRL_PROFILE
+    int why = 0;   // why the last attempt did not accept: 1 outside the grid, 2 empty cell, 3 no entering plane, 4 other cell, 5 below, 6 above the slab
+#define PAINTRL_WHY(v) why = (v)
+#else
+#define PAINTRL_WHY(v)
+#endif
 #pragma unroll 1
     for (int attempt = 0; attempt < kRayAttempts; ++attempt) {
         const double g0 = comp(h, ax.a0), g1 = comp(h, ax.a1);
         int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
         int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
-        if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) break;
+        if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) { PAINTRL_WHY(1); break; }
         const uint2 entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
         const int n_planes = (int)(entry.y & 0xffffu), n_verts = (int)(entry.y >> 16);
-        if (n_planes <= 0) break;
+        if (n_planes <= 0) { PAINTRL_WHY(2); break; }
         const double2 *blob = pk.mc_blob + (size_t)entry.x * 2;
         // one round of independent loads: region, this lane's plane(s) (in slab_pass), first vertex candidate
         const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);   // (a, b) (c, rlo) (rhi, -)
@@ -490,7 +575,7 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Ax &ax, const 
         PAINTRL_PROF(7, grp.gl == 0);
         if (r.outside || r.t_in > r.t_out || r.t_in > 1.0 || r.t_out < 0.0) return false;   // (1)
         candidate = false;
-        if (!(r.t_in > -INFINITY)) break;
+        if (!(r.t_in > -INFINITY)) { PAINTRL_WHY(3); break; }
         candidate = true;
         sub = blob + 4; n_sub = n_planes;
         h.x = frm.x + d0 * r.t_in; h.y = frm.y + d1 * r.t_in; h.z = frm.z + d2 * r.t_in;
@@ -499,6 +584,15 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Ax &ax, const 
             ref.blob = blob; ref.n_planes = n_planes; ref.n_verts = n_verts;
             break;
         }
+#ifdef PAINTRL_PROFILE
+        {
+            const double h0 = comp(h, ax.a0), h1 = comp(h, ax.a1);
+            const int hx = (int)floor((h0 - pk.mc_o0) * pk.mc_inv), hy = (int)floor((h1 - pk.mc_o1) * pk.mc_inv);
+            const double resid = comp(h, npax) - (abv.x + abv.y * h0 + clv.x * h1);
+            why = (hx != cx || hy != cy) ? 4 : (resid < clv.y ? 5 : 6);
+            if (why >= 5) why += 10 * (n_verts > 0 ? 1 : 0) + 100 * min(99, (int)(fabs(resid - (resid < clv.y ? clv.y : hpv.x)) * 1e4));
+        }
+#endif
     }
     PAINTRL_PROF(8, grp.gl == 0);
     if (!accepted) {
@@ -531,12 +625,14 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Ax &ax, const 
     }
     if (!accepted) {
         unsigned args = 0xffffffffu;
-        r = slab_pass<G, true>(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, frm, d0, d1, d2, grp, &args);
+        r = slab_pass_all<G>(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, frm, d0, d1, d2, grp, &args);
         miss_cache = args;
         counts += 1 << 8;
     }
     const bool is_hit = !(r.outside || !(r.t_in <= r.t_out && 0.0 <= r.t_in && r.t_in <= 1.0));
-    if (!ref.blob) g_dbg_log_ray(frm, d0, d1, d2, accepted ? 1 : 2, is_hit, grp.gl == 0);
+#ifdef PAINTRL_PROFILE
+    if (!ref.blob) g_dbg_log_ray(frm, d0, d1, d2, (accepted ? 1 : 2) + 10 * why, is_hit, grp.gl == 0);
+#endif
     if (!is_hit) return false;
     hit.x = frm.x + d0 * r.t_in;
     hit.y = frm.y + d1 * r.t_in;
@@ -594,7 +690,10 @@ __device__ __forceinline__ unsigned nearest_vertex_cell(const Vec3 &p, const Cel
     return brec;
 }
 
-// Slow path (point outside every accepted cell region): grid search over (axis0, axis1) with ring expansion.
+// Slow path (point outside every accepted cell region): the 3 x 3 block of vertex-grid cells around the
+// point, accepted when it proves that no vertex outside the block can be nearer; otherwise (hull faces
+// bridging an opening of the part: the nearest vertex is far away) one coalesced brute-force pass over
+// all front vertices -- a bounded ~n/32 iterations instead of a growing ring search.
 template <int G>
 __device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const Ax &ax, const Vec3 &p, const Grp &g) {
     double q0 = comp(p, ax.a0), q1 = comp(p, ax.a1);
@@ -602,28 +701,32 @@ __device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const
     int cy = (int)floor((q1 - pk.vg_o1) * pk.vg_inv);
     cx = min(max(cx, 0), pk.vg_nx - 1);
     cy = min(max(cy, 0), pk.vg_ny - 1);
-    double best_d = INFINITY;
-    unsigned best_i = 0xFFFFFFFFu;
-    for (int k = 1;; ++k) {
-        int x0 = max(cx - k, 0), x1 = min(cx + k, pk.vg_nx - 1);
-        int y0 = max(cy - k, 0), y1 = min(cy + k, pk.vg_ny - 1);
-        double bd = INFINITY;
-        unsigned bi = 0xFFFFFFFFu, dummy = 0;
-        for (int row = y0; row <= y1; ++row) {
-            int begin = __ldg(&pk.vg_start[row * pk.vg_nx + x0]);
-            int end = __ldg(&pk.vg_start[row * pk.vg_nx + x1 + 1]);
-            for (int j = begin + g.gl; j < end; j += G) {
-                double dx = __ldg(&pk.vx[j]) - p.x, dy = __ldg(&pk.vy[j]) - p.y, dz = __ldg(&pk.vz[j]) - p.z;
-                double d = dx * dx + dy * dy + dz * dz;
-                unsigned id = (unsigned)__ldg(&pk.vid[j]);
-                if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
-            }
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, pk.vg_nx - 1);
+    const int y0 = max(cy - 1, 0), y1 = min(cy + 1, pk.vg_ny - 1);
+    double bd = INFINITY;
+    unsigned bi = 0xFFFFFFFFu, dummy = 0;
+    // the (at most three) row ranges are looked up together, then scanned
+    int begin[3], end[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int row = y0 + r;
+        begin[r] = end[r] = 0;
+        if (row <= y1) {
+            begin[r] = __ldg(&pk.vg_start[row * pk.vg_nx + x0]);
+            end[r] = __ldg(&pk.vg_start[row * pk.vg_nx + x1 + 1]);
         }
-        grp_argmin<G>(bd, bi, dummy, g);
-        best_d = bd;
-        best_i = bi;
-        bool whole = (x0 == 0 && y0 == 0 && x1 == pk.vg_nx - 1 && y1 == pk.vg_ny - 1);
-        if (whole) break;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        for (int j = begin[r] + g.gl; j < end[r]; j += G) {
+            double dx = __ldg(&pk.vx[j]) - p.x, dy = __ldg(&pk.vy[j]) - p.y, dz = __ldg(&pk.vz[j]) - p.z;
+            double d = dx * dx + dy * dy + dz * dz;
+            unsigned id = (unsigned)__ldg(&pk.vid[j]);
+            if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
+        }
+    grp_argmin<G>(bd, bi, dummy, g);
+    bool proven = (x0 == 0 && y0 == 0 && x1 == pk.vg_nx - 1 && y1 == pk.vg_ny - 1);
+    if (!proven) {
         // every vertex outside the scanned block is at least m away in the (axis0, axis1) plane
         double m = INFINITY;
         if (x0 > 0) m = fmin(m, q0 - (pk.vg_o0 + x0 * pk.vg_cs));
@@ -631,10 +734,22 @@ __device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const
         if (y0 > 0) m = fmin(m, q1 - (pk.vg_o1 + y0 * pk.vg_cs));
         if (y1 < pk.vg_ny - 1) m = fmin(m, (pk.vg_o1 + (y1 + 1) * pk.vg_cs) - q1);
         m -= 1e-9;
-        if (m > 0.0 && best_d < m * m) break;
+        proven = m > 0.0 && bd < m * m;
     }
-    if (best_i == 0xFFFFFFFFu) return 0xFFFFFFFFu;
-    return __ldg(&pk.vrec[best_i]);
+    if (!proven) {
+        const int n = __ldg(&pk.vg_start[pk.vg_nx * pk.vg_ny]);
+        bd = INFINITY; bi = 0xFFFFFFFFu;
+#pragma unroll 4
+        for (int j = g.gl; j < n; j += G) {
+            double dx = __ldg(&pk.vx[j]) - p.x, dy = __ldg(&pk.vy[j]) - p.y, dz = __ldg(&pk.vz[j]) - p.z;
+            double d = dx * dx + dy * dy + dz * dz;
+            unsigned id = (unsigned)__ldg(&pk.vid[j]);
+            if (d < bd || (d == bd && id < bi)) { bd = d; bi = id; }
+        }
+        grp_argmin<G>(bd, bi, dummy, g);
+    }
+    if (bi == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+    return __ldg(&pk.vrec[bi]);
 }
 
 // Part._get_hook_point + _get_closest_bary (bullet_paint_wrapper.py:525-534, 508-523, 154-185):

@@ -42,6 +42,8 @@ struct EnvArrays {
     unsigned *bits;        // [num_envs][n_words_pad]  flip bit per slot
     int16_t *thick;        // [num_envs][n_slots]      HSI thickness (HSI only)
     unsigned *grid_cnt;    // [num_envs][n_gcells_pad] flipped texels per grid-observation cell (grid mode only)
+    unsigned *ready;       // [num_envs] sequence number of the last step whose move phase has been published
+    unsigned seq;          // this step's sequence number
 };
 
 // Words of the per-environment bit-plane a warp stages in shared memory (one TMA bulk copy in,
@@ -658,10 +660,12 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
     asm volatile("griddepcontrol.launch_dependents;");
     const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
     const int lane = threadIdx.x & 31;
-    const int env = (blockIdx.x * (kWarpsPerBlock * 32) + threadIdx.x) / G;
+    const int env = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // launched with 32, 64 or 128 threads per block
     if (env >= num_envs) return;
     const Grp grp = make_grp<G>(lane);
-    PAINTRL_PROF_BEGIN
+    PAINTRL_PROF_BEGIN(env, 0, 15)
+    PAINTRL_TRACE_MARK(env, 0, grp.gl == 0);
+    PAINTRL_TRACE_SM(env, 6, grp.gl == 0);
     // the fields of the record this phase reads: pose, quaternion, turning angle, off-part state
     EnvState *gst = &ea.states[env];
     const double2 s0 = reinterpret_cast<const double2 *>(gst)[0], s1 = reinterpret_cast<const double2 *>(gst)[1],
@@ -765,41 +769,69 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
         gst->flags = flags;
         ea.moves[env].counts = counts | (term_counter - counter_before);
         ea.moves[env].miss_cache = miss_cache;
+        // publish: this lane wrote the record and the move output; the paint kernel's warp for this
+        // environment acquires the flag instead of waiting for the whole grid
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ea.ready + env), "r"(ea.seq) : "memory");
     }
     PAINTRL_PROF(13, grp.gl == 0);
+#ifdef PAINTRL_PROFILE
+    if (lane == 0) prof_row[14] = (unsigned)(counts | (term_counter - counter_before));
+#endif
+    PAINTRL_TRACE_MARK(env, 1, grp.gl == 0);
+#ifdef PAINTRL_TRACE
+    if (grp.gl == 0 && env < 65536) g_trace[env][6] |= (unsigned long long)(unsigned)(counts | (term_counter - counter_before)) << 16;
+#endif
 }
 
 // Everything after the move: stamp, score, observe, auto-reset.  The environment's record, the
 // move kernel's output and (STAGED) its flip bits come in through one TMA bulk-copy group per warp
 // and the bits go back the same way.
-template <int COLOR, bool STAGED, bool AX12>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, STAGED ? 7 : 4)
+template <int COLOR, bool STAGED, bool AX12, int WPB>
+__global__ void __launch_bounds__(WPB * 32, (STAGED ? 28 : 16) / WPB)
 paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
     typedef WarpScratch<STAGED> WS;
-    __shared__ WS scratch[kWarpsPerBlock];
+    __shared__ WS scratch[WPB];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int env = blockIdx.x * kWarpsPerBlock + warp;
+    const int env = blockIdx.x * WPB + warp;
     if (env >= num_envs) return;
     WS &ws = scratch[warp];
-    PAINTRL_PROF_BEGIN
+    PAINTRL_PROF_BEGIN(env, 15, 32)
+    PAINTRL_TRACE_MARK(env, 2, lane == 0);
+    PAINTRL_TRACE_SM(env, 7, lane == 0);
     unsigned *gbits = bits_of(pk, ea, env), *grid_cnt = grid_cnt_of(pk, ea, env);
     int16_t *thick = thick_of(pk, ea, env);
     const unsigned plane_bytes = (unsigned)pk.n_words_pad * 4u;
-    if (lane == 0) {
+    if (STAGED && lane == 0) {
         mbar_init(&ws.bar, 1);
-        mbar_expect_tx(&ws.bar, (unsigned)(sizeof(EnvState) + sizeof(MoveOut)) + (STAGED ? plane_bytes : 0u));
-        if (STAGED) bulk_g2s(ws.sbits, gbits, plane_bytes, &ws.bar);   // not written by the move kernel
+        mbar_expect_tx(&ws.bar, plane_bytes);
+        bulk_g2s(ws.sbits, gbits, plane_bytes, &ws.bar);   // not written by the move kernel
     }
-    // launched with programmatic stream serialization: everything above overlaps the move kernel's tail,
-    // its outputs (record, shot centres) are read only after it has completed
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Launched with programmatic stream serialization: this grid's CTAs start as soon as every CTA of the
+    // move kernel has started, and each warp waits only for ITS environment's move phase (acquire of the
+    // flag the move warp released) -- not for the whole grid: a slow environment of the move phase delays
+    // nobody else, and the paint phase fills the SMs the move kernel's last wave leaves idle.
     if (lane == 0) {
-        bulk_g2s(&ws.st, &ea.states[env], (unsigned)sizeof(EnvState), &ws.bar);
-        bulk_g2s(&ws.mv, &ea.moves[env], (unsigned)sizeof(MoveOut), &ws.bar);
+        const unsigned *flag = ea.ready + env;
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == ea.seq) break;
+            __nanosleep(200);
+        }
     }
     __syncwarp();
-    mbar_wait(&ws.bar, 0);
+    PAINTRL_TRACE_MARK(env, 3, lane == 0);
+    // the record and the move output: L2 loads (another SM wrote them while this grid was already running)
+    if (lane < 16) {
+        const double2 *src = lane < 8 ? reinterpret_cast<const double2 *>(&ea.states[env]) + lane
+                                      : reinterpret_cast<const double2 *>(&ea.moves[env]) + (lane - 8);
+        double2 *dst = lane < 8 ? reinterpret_cast<double2 *>(&ws.st) + lane : reinterpret_cast<double2 *>(&ws.mv) + (lane - 8);
+        *dst = __ldcg(src);
+    }
+    __syncwarp();
+    if (STAGED) mbar_wait(&ws.bar, 0);
+    PAINTRL_TRACE_MARK(env, 4, lane == 0);
     PAINTRL_PROF(16, lane == 0);
     const Bits<STAGED> bits = {gbits, ws.sbits};
     EnvState &st = ws.st;
@@ -967,6 +999,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     if (lane < 8) reinterpret_cast<double2 *>(&ea.states[env])[lane] = reinterpret_cast<const double2 *>(&st)[lane];
     if (STAGED && lane == 0) bulk_wait_read();
     PAINTRL_PROF(26, lane == 0);
+    PAINTRL_TRACE_MARK(env, 5, lane == 0);
 }
 
 // PaintGymEnv.reset / Robot.reset(pose) for the listed environments, with their first observation.
@@ -994,7 +1027,7 @@ reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, const int32_t *env_ids, in
     __syncwarp();
     const Bits<false> bits = {gbits, nullptr};
     Vec3 pose = {st.pose[0], st.pose[1], st.pose[2]};
-    PAINTRL_PROF_BEGIN
+    PAINTRL_PROF_BEGIN(65535, 0, 0)
     write_observation(pk, ax, cfg, bits, grid_cnt, pose, lane, scratch[warp], obs_out ? obs_out + (size_t)k * cfg.obs_dim : nullptr,
                       nullptr PAINTRL_PROF_PASS);
     store_state(&ea.states[env], st, lane);
@@ -1011,7 +1044,7 @@ reset_obs_kernel(DevPack pk, DevConfig cfg, unsigned *zero_bits, const unsigned 
     if (k >= pk.n_starts) return;
     const Bits<false> bits = {zero_bits, nullptr};
     Vec3 pose = {pk.start_pos[3 * k], pk.start_pos[3 * k + 1], pk.start_pos[3 * k + 2]};
-    PAINTRL_PROF_BEGIN
+    PAINTRL_PROF_BEGIN(65535, 0, 0)
     write_observation(pk, ax, cfg, bits, grid_cnt, pose, lane, scratch[warp], table + (size_t)k * cfg.obs_dim, nullptr PAINTRL_PROF_PASS);
 }
 

@@ -27,6 +27,7 @@ ap.add_argument('--envs', type=int, default=4096)
 ap.add_argument('--workload', default='c2')
 ap.add_argument('--steps', type=int, default=50)
 ap.add_argument('--no-flush', action='store_true')
+ap.add_argument('--per-env', action='store_true', help='last step: phase cycles of the slowest move warps and by slow-path class')
 ap.add_argument('--dump-rays', default=None, help='write the rays that left the fast path to this .npy file')
 args = ap.parse_args()
 w = bench.WORKLOADS[args.workload]
@@ -65,3 +66,22 @@ for i in range(32):
     if buf[i]:
         print('  [%2d] %-44s %9.0f' % (i, NAMES.get(i, '?'), buf[i] / n))
 print('  move kernel total %.0f cycles, paint kernel total %.0f cycles' % (tot_m / n, tot_p / n))
+
+if args.per_env:
+    import numpy as np
+    lib.paintrl_debug_profile_env.restype = ctypes.c_int
+    lib.paintrl_debug_profile_env.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    rows = np.zeros((min(args.envs, 65536), 32), dtype=np.uint32)
+    lib.paintrl_debug_profile_env(rows.ctypes.data, rows.shape[0])
+    cnt = rows[:, 14].astype(np.int64)
+    off, full, verify = cnt & 0xf, (cnt >> 8) & 0xff, (cnt >> 16) & 0xff
+    ph = rows.astype(np.int64)
+    ph[:, 14] = 0
+    move_total = ph[:, :14].sum(1)
+    slots = [k for k in range(14) if ph[:, k].any()]
+    print('last step, move phases per environment (cycles): ' + ' '.join('[%d]' % k for k in slots))
+    for nm, sel in (('no slow path', (full == 0) & (verify == 0)), ('verify only', (full == 0) & (verify > 0)), ('full scans', full > 0)):
+        if sel.any():
+            print('  %-12s n %5d  total %7.0f : %s' % (nm, sel.sum(), move_total[sel].mean(), ' '.join('%6.0f' % ph[sel, k].mean() for k in slots)))
+    for i in np.argsort(-move_total)[:12]:
+        print('  env %5d off %d full %d verify %d total %7d : %s' % (i, off[i], full[i], verify[i], move_total[i], ' '.join('%6d' % ph[i, k] for k in slots)))
