@@ -64,8 +64,8 @@ def measured_peaks():
 
 def captured_traffic(workload_key):
     """DRAM bytes (read + write) per step from the committed `ncu --set full` capture of this workload
-    (profiles/r01_v4_dram_traffic.json, both kernels of the step summed), or None."""
-    path = os.path.join(ROOT, 'profiles', 'r01_v4_dram_traffic.json')
+    (profiles/r01_v5_dram_traffic.json, both kernels of the step summed), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r01_v5_dram_traffic.json')
     try:
         with open(path) as f:
             t = json.load(f).get(workload_key)
@@ -318,7 +318,7 @@ def main():
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
-    sum_reward = torch.zeros((), dtype=torch.float64, device=device)
+    acc = torch.zeros(4, dtype=torch.float64, device=device)   # rollout statistics, accumulated outside the timed event pairs
     t_wall = time.perf_counter()
     for i in range(args.steps):
         if flush is not None:
@@ -326,6 +326,7 @@ def main():
         starts[i].record()
         env.step(actions[warmup + i])
         stops[i].record()
+        acc += torch.stack([env.reward.sum(), env.penalty.sum(), env.actual.sum(), env.new_texels.sum().to(torch.float64)])
     barrier()
     wall_s = time.perf_counter() - t_wall
     clocks = sampler.stop()
@@ -362,7 +363,8 @@ def main():
     total_envs = int(w[0])
     rollout = sharding.allreduce_stats({
         'env_steps': s1['env_steps'] - s0['env_steps'], 'episodes': s1['episodes_ended'] - s0['episodes_ended'],
-        'new_texels': 0.0, 'max_step_ms': float(step_ms.max())}, device=device)
+        'sum_reward': float(acc[0]), 'sum_penalty': float(acc[1]), 'sum_return': float(acc[2]), 'new_texels': float(acc[3]),
+        'max_step_ms': float(step_ms.max())}, device=device)
 
     if rank == 0:
         steps_done = s1['env_steps'] - s0['env_steps']
@@ -390,7 +392,7 @@ def main():
             'gpu_launches': s1['kernel_launches'] - s0['kernel_launches'],
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': captured_traffic(args.workload), 'traffic_unit': 'bytes per step (ncu capture, profiles/)',
-                         'peak_source': peak_src, 'kernel': 'paintrl::move_kernel + paintrl::paint_kernel (one step = two launches)',
+                         'peak_source': peak_src, 'kernel': 'paintrl::move_kernel + paintrl::paint_kernel (one step = two launches; the paint grid is a programmatic dependent launch whose warps acquire per-environment flags)',
                          'kernel_ms': kernel_ms, 'algorithmic_bytes_per_env_step': b_alg,
                          'footprint_union_texels_mean': u_mean, 'p_reset': p_reset,
                          'ray_full_scans_per_env_step': (s1['ray_full_scans'] - s0['ray_full_scans']) / max(1, steps_done)},

@@ -549,6 +549,9 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Ax &ax, const 
         int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
         int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
         if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) { PAINTRL_WHY(1); break; }
+#if defined(PAINTRL_TRACE) || defined(PAINTRL_PROFILE)
+        counts += 1 << 24;   // cell attempts of the step (diagnostic builds only)
+#endif
         const uint2 entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
         const int n_planes = (int)(entry.y & 0xffffu), n_verts = (int)(entry.y >> 16);
         if (n_planes <= 0) { PAINTRL_WHY(2); break; }

@@ -598,6 +598,7 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BIT
             if (uni == 0u) return;
             n_possible += __popc(__ballot_sync(kFull, possible));
             const unsigned old = bits.ld(w);
+            __syncwarp();                                  // every lane has read the word before lane 0 rewrites it
             const unsigned flipped = uni & ~old;           // slots whose painted predicate changes
             if (flipped) {
                 n_new += __popc(flipped);
@@ -653,15 +654,10 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BIT
 // ------------------------------------------------------------------------------ kernels
 // Robot._get_actions (robot.py:302-329): action -> direction, five guided sub-steps.
 // G lanes per environment (the plane / vertex / triangle lists of a sub-step are short).
-template <int G, int MINB, bool AX12>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
-move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *actions) {
-    // programmatic dependent launch: let the paint kernel's CTAs be scheduled as this grid drains
-    asm volatile("griddepcontrol.launch_dependents;");
+template <int G, bool AX12>
+__device__ __forceinline__ void move_body(const DevPack &pk, const DevConfig &cfg, const EnvArrays &ea, int env, const void *actions) {
     const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
     const int lane = threadIdx.x & 31;
-    const int env = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // launched with 32, 64 or 128 threads per block
-    if (env >= num_envs) return;
     const Grp grp = make_grp<G>(lane);
     PAINTRL_PROF_BEGIN(env, 0, 15)
     PAINTRL_TRACE_MARK(env, 0, grp.gl == 0);
@@ -783,19 +779,25 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
 #endif
 }
 
+template <int G, int MINB, bool AX12>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
+move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *actions) {
+    // programmatic dependent launch: let the paint kernel's CTAs be scheduled as this grid drains
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int env = (blockIdx.x * blockDim.x + threadIdx.x) / G;   // launched with 32, 64 or 128 threads per block
+    if (env >= num_envs) return;
+    move_body<G, AX12>(pk, cfg, ea, env, actions);
+}
+
 // Everything after the move: stamp, score, observe, auto-reset.  The environment's record, the
 // move kernel's output and (STAGED) its flip bits come in through one TMA bulk-copy group per warp
 // and the bits go back the same way.
-template <int COLOR, bool STAGED, bool AX12, int WPB>
-__global__ void __launch_bounds__(WPB * 32, (STAGED ? 28 : 16) / WPB)
-paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
+template <int COLOR, bool STAGED, bool AX12>
+__device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &cfg, const EnvArrays &ea, int env, const StepIO &io,
+                                           WarpScratch<STAGED> &ws) {
     const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
     typedef WarpScratch<STAGED> WS;
-    __shared__ WS scratch[WPB];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int env = blockIdx.x * WPB + warp;
-    if (env >= num_envs) return;
-    WS &ws = scratch[warp];
+    const int lane = threadIdx.x & 31;
     PAINTRL_PROF_BEGIN(env, 15, 32)
     PAINTRL_TRACE_MARK(env, 2, lane == 0);
     PAINTRL_TRACE_SM(env, 7, lane == 0);
@@ -1000,6 +1002,16 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     if (STAGED && lane == 0) bulk_wait_read();
     PAINTRL_PROF(26, lane == 0);
     PAINTRL_TRACE_MARK(env, 5, lane == 0);
+}
+
+template <int COLOR, bool STAGED, bool AX12, int WPB>
+__global__ void __launch_bounds__(WPB * 32, (STAGED ? 28 : 16) / WPB)
+paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
+    __shared__ WarpScratch<STAGED> scratch[WPB];
+    const int warp = threadIdx.x >> 5;
+    const int env = blockIdx.x * WPB + warp;
+    if (env >= num_envs) return;
+    paint_body<COLOR, STAGED, AX12>(pk, cfg, ea, env, io, scratch[warp]);
 }
 
 // PaintGymEnv.reset / Robot.reset(pose) for the listed environments, with their first observation.

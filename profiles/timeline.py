@@ -52,10 +52,14 @@ for nm, d in (('move duration per warp', dm), ('paint duration per warp (after i
     print('  %-40s min %6.2f  p10 %6.2f  median %6.2f  p90 %6.2f  p99 %6.2f  max %6.2f' % (nm, d.min(), np.percentile(d, 10), np.median(d), np.percentile(d, 90), np.percentile(d, 99), d.max()))
 sm_m, sm_p = (tr[:, 6] & 0xffff).astype(int), tr[:, 7].astype(int)
 cnt = (tr[:, 6] >> 16).astype(np.int64)
-off, full, verify = cnt & 0xf, (cnt >> 8) & 0xff, (cnt >> 16) & 0xff
+off, full, verify, attempts = cnt & 0xf, (cnt >> 8) & 0xff, (cnt >> 16) & 0xff, (cnt >> 24) & 0x7f
 slow = np.argsort(-dm)[:24]
-print('  slowest move warps: duration us / off-part sub-steps / full plane scans / verify passes')
-print('   ' + '  '.join('%.1f/%d/%d/%d' % (dm[i], off[i], full[i], verify[i]) for i in slow))
+print('  slowest move warps: duration us / off-part sub-steps / full plane scans / verify passes / cell attempts')
+print('   ' + '  '.join('%.1f/%d/%d/%d/%d' % (dm[i], off[i], full[i], verify[i], attempts[i]) for i in slow))
+for k in range(5, 16):
+    sel = attempts == k
+    if sel.any():
+        print('  move duration, %2d cell attempts: n %5d  median %6.2f  p90 %6.2f  max %6.2f' % (k, sel.sum(), np.median(dm[sel]), np.percentile(dm[sel], 90), dm[sel].max()))
 for nm, sel in (('no slow path', (full == 0) & (verify == 0)), ('verify only', (full == 0) & (verify > 0)), ('full scans', full > 0)):
     if sel.any():
         print('  move duration, %-12s: n %5d  median %6.2f  p90 %6.2f  max %6.2f' % (nm, sel.sum(), np.median(dm[sel]), np.percentile(dm[sel], 90), dm[sel].max()))
