@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.log
-(time python bench.py) 2>&1 | tee gpurun_out/bench_default.json | cut -c1-2500
-(time python bench.py --impl reference --steps 5 --warmup 1) 2>&1 | tee gpurun_out/bench_reference.json | cut -c1-900
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 300 --warmup 10 2>&1 | tail -2 | tee gpurun_out/bench_n2.json | cut -c1-700
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 1 --impl reference 2>&1 | tail -1 | cut -c1-300
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --workload c5 --rollout --steps 3 --warmup 2 2>&1 | tail -1 | tee gpurun_out/bench_n2_c5_rollout.json | cut -c1-900
