@@ -852,7 +852,8 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     cudaMemset(e->moves, 0xff, sizeof(MoveOut) * (size_t)num_envs);   // miss_cache = none
     cudaMemset(e->env_stats, 0, sizeof(EnvStat) * (size_t)num_envs);
     cudaMemset(e->bits, 0, bits_bytes);
-    if (e->thick) cudaMemset(e->thick, 0, thick_bytes);
+    if (e->thick)   // the initial colour everywhere; resets only rewrite what an episode touched (clear_planes)
+        fill_thickness_kernel<<<1184, 256>>>(e->thick, thick_bytes / sizeof(int16_t), (int16_t)e->pk.status_init);
     if (e->grid_cnt) cudaMemset(e->grid_cnt, 0, gcnt_bytes);
     cudaMemset(e->stats, 0, 4 * sizeof(unsigned long long));
     cudaMemset(e->ready, 0, sizeof(unsigned) * (size_t)num_envs);

@@ -335,16 +335,39 @@ __device__ __forceinline__ void write_observation(const DevPack &pk, const Ax &a
 
 // ------------------------------------------------------------------------------ reset pieces
 // Part.reset_part (bullet_paint_wrapper.py:706-708): restore the init colour, 128-bit stores.
-__device__ __forceinline__ void clear_planes(const DevPack &pk, unsigned *bits, int16_t *thick, unsigned *grid_cnt, int lane) {
+// HSI thickness plane: a texel's flip bit is set exactly when its thickness has left the initial 255
+// (values only decrease, bullet_paint_wrapper.py:429-431; set_status_kernel keeps the same invariant), so
+// only the 32-texel words with a bit set are rewritten -- a short episode touches a few hundred of the
+// part's ~14 k texels, and the plane is 30 KB per environment.  `bits` is the environment's current
+// bit-plane (shared copy or global), `gbits` its global home.
+template <typename BITS>
+__device__ __forceinline__ void clear_planes(const DevPack &pk, const BITS &bits, unsigned *gbits, int16_t *thick, unsigned *grid_cnt,
+                                             int lane) {
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int w = lane * 4; w < pk.n_words_pad; w += 128) *reinterpret_cast<uint4 *>(bits + w) = z;
     if (thick) {
         const unsigned v2 = ((unsigned)(uint16_t)pk.status_init) * 0x10001u;
         const uint4 v = make_uint4(v2, v2, v2, v2);
-        for (int j = lane * 8; j < pk.n_slots; j += 256) *reinterpret_cast<uint4 *>(thick + j) = v;
+        if (pk.status_init == kPainted) {
+            for (int w = lane; w < pk.n_words; w += 32) {
+                if (bits.ld(w) != 0u) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(thick + (size_t)w * 32);
+                    dst[0] = v; dst[1] = v; dst[2] = v; dst[3] = v;
+                }
+            }
+            __syncwarp();      // every lane has read its words before the plane is zeroed below
+        } else {
+            for (int j = lane * 8; j < pk.n_slots; j += 256) *reinterpret_cast<uint4 *>(thick + j) = v;
+        }
     }
+    for (int w = lane * 4; w < pk.n_words_pad; w += 128) *reinterpret_cast<uint4 *>(gbits + w) = z;
     if (grid_cnt)
         for (int w = lane * 4; w < pk.n_gcells_pad; w += 128) *reinterpret_cast<uint4 *>(grid_cnt + w) = z;
+}
+
+// Initial fill of the thickness planes (paintrl_create): from then on resets are incremental.
+__global__ void fill_thickness_kernel(int16_t *thick, size_t n, int16_t value) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) thick[i] = value;
 }
 
 // Robot.reset(pose) (robot.py:366-372, 208-212)
@@ -985,7 +1008,7 @@ __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &c
     if (resetting) {
         int idx = io.reset_start_idx ? io.reset_start_idx[env] : auto_start_index(pk, cfg, env, st.episode);
         idx = min(max(idx, 0), pk.n_starts - 1);
-        clear_planes(pk, gbits, thick, grid_cnt, lane);
+        clear_planes(pk, bits, gbits, thick, grid_cnt, lane);
         __syncwarp();
         if (lane == 0) state_reset(pk, st, idx);
         if (next_obs) {
@@ -1031,7 +1054,7 @@ reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, const int32_t *env_ids, in
     if (mode == 0) {
         int idx = start_idx ? start_idx[k] : auto_start_index(pk, cfg, env, st.episode);
         idx = min(max(idx, 0), pk.n_starts - 1);
-        clear_planes(pk, gbits, thick, grid_cnt, lane);
+        clear_planes(pk, Bits<false>{gbits, nullptr}, gbits, thick, grid_cnt, lane);
         state_reset(pk, st, idx);
     } else {
         robot_reset(st, set_pos + 3 * k, set_normal + 3 * k);
