@@ -216,6 +216,36 @@ int paintrl_rasterize_texels(const double *tri_a, const double *tri_b, const dou
                              int32_t device, int32_t capacity, int32_t *texel_ij_out,
                              double *texel_pos_out, int32_t *n_texels_out);
 
+/*
+ * The grid-world ParamTestEnv (PaintRLEnv/param_test_env.py:96-246; driven by param_test_*.py), batched:
+ * one handle = num_envs independent size x size worlds on one GPU.  Same conventions as above.
+ */
+enum { PAINTRL_PARAM_OBS_SECTION = 0, PAINTRL_PARAM_OBS_SIMPLE = 1, PAINTRL_PARAM_OBS_DIRECT = 2, PAINTRL_PARAM_OBS_GRID = 3 };
+typedef struct PaintrlParamConfig {
+    int32_t abi_version;            /* PAINTRL_ABI_VERSION */
+    int32_t size;                   /* ParamTestEnv(size, ...)                      (param_test_env.py:110) */
+    int32_t max_len;                /* EPISODE_MAX_LENGTH = max(max_len, (size-2)^2) (:112) */
+    int32_t termination_by_repeat;  /* (:146) */
+    int32_t obs_mode;               /* class attribute OBS_MODE (:101): section 4+2, simple 2, direct size^2+2, grid 100+2 */
+    int32_t auto_reset;             /* reset a finished world inside the step; next_obs gets reset()'s observation */
+} PaintrlParamConfig;
+typedef struct PaintrlParamEngine *PaintrlParamHandle;
+
+int paintrl_param_create(const PaintrlParamConfig *cfg, int32_t num_envs, int32_t device, PaintrlParamHandle *out);
+void paintrl_param_destroy(PaintrlParamHandle h);
+int32_t paintrl_param_obs_dim(PaintrlParamHandle h);
+/* ParamTestEnv.reset (:150-160); env_ids_dev NULL = all; obs_dev float64[n, obs_dim] or NULL */
+int paintrl_param_reset(PaintrlParamHandle h, const int32_t *env_ids_dev, int32_t n, double *obs_dev, void *stream);
+/* ParamTestEnv.step (:218-240): actions int64[num_envs] in 0..3 (anything else raises the bad-action flag of
+ * paintrl_param_stats and leaves that world untouched; the reference raises IndexError) */
+int paintrl_param_step(PaintrlParamHandle h, const int64_t *actions_dev, double *obs_dev, double *reward_dev,
+                       double *penalty_dev, double *actual_dev, uint8_t *done_dev, double *next_obs_dev, void *stream);
+/* world / visit_table (:113-131) of the listed worlds as int32[n, size*size] (visit counts saturate at 255) */
+int paintrl_param_tables(PaintrlParamHandle h, const int32_t *env_ids_dev, int32_t n, int32_t *world_dev,
+                         int32_t *visit_dev, void *stream);
+int paintrl_param_stats(PaintrlParamHandle h, uint64_t *env_steps, uint64_t *episodes_ended,
+                        uint64_t *kernel_launches, int32_t *bad_action_seen);
+
 const char *paintrl_last_error(void);
 int32_t paintrl_abi_version(void);
 

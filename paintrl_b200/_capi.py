@@ -70,6 +70,11 @@ class PaintrlStats(ctypes.Structure):
                 ('ray_full_scans', ctypes.c_uint64)]
 
 
+class PaintrlParamConfig(ctypes.Structure):
+    _fields_ = [('abi_version', ctypes.c_int32), ('size', ctypes.c_int32), ('max_len', ctypes.c_int32),
+                ('termination_by_repeat', ctypes.c_int32), ('obs_mode', ctypes.c_int32), ('auto_reset', ctypes.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/paintrl.h declares
 _VP = ctypes.c_void_p
 _I32 = ctypes.c_int32
@@ -91,6 +96,14 @@ SIGNATURES = {
     'paintrl_job_status': (ctypes.c_int, [_VP, _VP, _VP]),
     'paintrl_stats': (ctypes.c_int, [_VP, ctypes.POINTER(PaintrlStats)]),
     'paintrl_rasterize_texels': (ctypes.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP]),
+    'paintrl_param_create': (ctypes.c_int, [ctypes.POINTER(PaintrlParamConfig), _I32, _I32, ctypes.POINTER(_VP)]),
+    'paintrl_param_destroy': (None, [_VP]),
+    'paintrl_param_obs_dim': (_I32, [_VP]),
+    'paintrl_param_reset': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP]),
+    'paintrl_param_step': (ctypes.c_int, [_VP] * 9),
+    'paintrl_param_tables': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _VP]),
+    'paintrl_param_stats': (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
+                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(_I32)]),
     'paintrl_last_error': (ctypes.c_char_p, []),
     'paintrl_abi_version': (_I32, []),
 }

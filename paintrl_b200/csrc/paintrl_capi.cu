@@ -12,6 +12,7 @@
 #include "../../include/paintrl.h"
 #include "paintrl_kernels.cuh"
 #include "paintrl_raster.cuh"
+#include "paintrl_param.cuh"
 
 using namespace paintrl;
 
@@ -658,6 +659,117 @@ extern "C" {
 
 int32_t paintrl_abi_version(void) { return PAINTRL_ABI_VERSION; }
 
+/* ---- the grid-world ParamTestEnv (PaintRLEnv/param_test_env.py), see paintrl_param.cuh ---- */
+struct PaintrlParamEngine {
+    int device = 0;
+    ParamWorld w{};
+    DeviceArena arena;
+    int *bad_action = nullptr;
+    unsigned long long launches = 0;
+};
+
+int paintrl_param_create(const PaintrlParamConfig *cfg, int32_t num_envs, int32_t device, PaintrlParamHandle *out) {
+    if (!cfg || !out) return fail(PAINTRL_E_INVALID, "null argument");
+    if (cfg->abi_version != PAINTRL_ABI_VERSION) return fail(PAINTRL_E_INVALID, "ABI version mismatch");
+    if (num_envs <= 0) return fail(PAINTRL_E_INVALID, "num_envs must be positive");
+    if (cfg->size < 3 || cfg->size > 255) return fail(PAINTRL_E_INVALID, "size must be in 3..255");
+    if (cfg->obs_mode < 0 || cfg->obs_mode > 3) return fail(PAINTRL_E_INVALID, "unknown observation mode");
+    if (cfg->obs_mode == kParamObsGrid && cfg->size != 22)
+        return fail(PAINTRL_E_INVALID, "the grid observation is defined for size 22 only (param_test_env.py:50-63 indexes a 10 x 10 table)");
+    CUDA_TRY(cudaSetDevice(device));
+    PaintrlParamEngine *e = new PaintrlParamEngine();
+    e->device = device;
+    ParamWorld &w = e->w;
+    w.num_envs = num_envs;
+    w.size = cfg->size;
+    w.episode_max_length = std::max(cfg->max_len, (cfg->size - 2) * (cfg->size - 2));   /* param_test_env.py:112 */
+    w.repeat_termination = cfg->termination_by_repeat ? 1 : 0;
+    w.obs_mode = cfg->obs_mode;
+    w.obs_dim = cfg->obs_mode == kParamObsSection ? 6 : cfg->obs_mode == kParamObsSimple ? 2
+              : cfg->obs_mode == kParamObsDirect ? cfg->size * cfg->size + 2 : 102;
+    w.auto_reset = cfg->auto_reset ? 1 : 0;
+    w.init_reward_counter = (cfg->size - 2) * (cfg->size - 2);
+    const size_t cells = (size_t)cfg->size * cfg->size * num_envs;
+    bool ok = e->arena.alloc((void **)&w.world, cells) == cudaSuccess && e->arena.alloc((void **)&w.visit, cells) == cudaSuccess &&
+              e->arena.alloc((void **)&w.pos_i, sizeof(int) * num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&w.pos_j, sizeof(int) * num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&w.reward_counter, sizeof(int) * num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&w.step_counter, sizeof(int) * num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&w.flags, num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&w.stats, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+              e->arena.alloc((void **)&e->bad_action, sizeof(int)) == cudaSuccess;
+    if (!ok) { delete e; return fail(PAINTRL_E_CUDA, "device allocation failed (grid world)"); }
+    cudaMemset(w.stats, 0, 2 * sizeof(unsigned long long));
+    cudaMemset(e->bad_action, 0, sizeof(int));
+    param_reset_kernel<<<(num_envs + 127) / 128, 128>>>(w, nullptr, num_envs, nullptr);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, cudaGetErrorString(err)); }
+    *out = e;
+    return PAINTRL_OK;
+}
+
+void paintrl_param_destroy(PaintrlParamHandle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    delete h;
+}
+
+int32_t paintrl_param_obs_dim(PaintrlParamHandle h) { return h ? h->w.obs_dim : 0; }
+
+int paintrl_param_reset(PaintrlParamHandle h, const int32_t *env_ids_dev, int32_t n, double *obs_dev, void *stream) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (n <= 0 || n > h->w.num_envs || (!env_ids_dev && n != h->w.num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
+    CUDA_TRY(cudaSetDevice(h->device));
+    param_reset_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(h->w, env_ids_dev, n, obs_dev);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PAINTRL_OK;
+}
+
+int paintrl_param_step(PaintrlParamHandle h, const int64_t *actions_dev, double *obs_dev, double *reward_dev, double *penalty_dev,
+                       double *actual_dev, uint8_t *done_dev, double *next_obs_dev, void *stream) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (!actions_dev || !obs_dev || !reward_dev || !penalty_dev || !actual_dev || !done_dev)
+        return fail(PAINTRL_E_INVALID, "null I/O buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    param_step_kernel<<<(h->w.num_envs + 127) / 128, 128, 0, as_stream(stream)>>>(
+        h->w, reinterpret_cast<const long long *>(actions_dev), obs_dev, reward_dev, penalty_dev, actual_dev, done_dev, next_obs_dev,
+        h->bad_action);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PAINTRL_OK;
+}
+
+int paintrl_param_tables(PaintrlParamHandle h, const int32_t *env_ids_dev, int32_t n, int32_t *world_dev, int32_t *visit_dev, void *stream) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (n <= 0 || n > h->w.num_envs || (!env_ids_dev && n != h->w.num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int cells = h->w.size * h->w.size;
+    param_tables_kernel<<<dim3((cells + 127) / 128, n), 128, 0, as_stream(stream)>>>(h->w, env_ids_dev, n, world_dev, visit_dev);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PAINTRL_OK;
+}
+
+int paintrl_param_stats(PaintrlParamHandle h, uint64_t *env_steps, uint64_t *episodes_ended, uint64_t *kernel_launches,
+                        int32_t *bad_action_seen) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long host[2];
+    int bad = 0;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(host, h->w.stats, sizeof(host), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&bad, h->bad_action, sizeof(int), cudaMemcpyDeviceToHost));
+    if (env_steps) *env_steps = host[0];
+    if (episodes_ended) *episodes_ended = host[1];
+    if (kernel_launches) *kernel_launches = h->launches;
+    if (bad_action_seen) *bad_action_seen = bad;
+    return PAINTRL_OK;
+}
+
+
 /* Part.preprocess texel rasterisation on the GPU (see paintrl_raster.cuh and paintrl.h). */
 int paintrl_rasterize_texels(const double *tri_a, const double *tri_b, const double *tri_c, const double *tri_uv,
                              int32_t n_tris, int32_t width, int32_t height, int32_t device, int32_t capacity,
@@ -868,7 +980,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
         // lanes per environment in the move phase: a full warp while the batch alone cannot fill the GPU
         // (the phase is latency-bound there), 8 lanes once it can (then instruction issue is the limit)
         const char *ml = getenv("PAINTRL_MOVE_LANES");
-        int lanes = ml ? atoi(ml) : (num_envs <= 16384 ? 32 : 8);
+        int lanes = ml ? atoi(ml) : (num_envs < 16384 ? 32 : 8);   // measured: 4096 envs 60 vs 103 us, 16384 envs 292 vs 249 us (32 vs 8 lanes)
         e->move_lanes = (lanes == 16 || lanes == 8) ? lanes : 32;
         e->force_unstaged = getenv("PAINTRL_FORCE_UNSTAGED") != nullptr;
         const char *mw = getenv("PAINTRL_MOVE_WARPS"), *pwv = getenv("PAINTRL_PAINT_WARPS");

@@ -60,6 +60,7 @@ struct alignas(128) WarpScratch {
     int rowWa[kMaxRows], rowWn[kMaxRows];         // stamp candidates of the row: first word, word count
                                                   // (reused as the K != 4 section histogram)
     uint16_t cand[STAGED ? kStageWords : 2];      // flat list of the step's candidate words (STAGED only)
+    double hsi_r[8];                              // HSI: r = distances.max() of each shot (stamp)
     unsigned long long bar;                       // mbarrier of the bulk copies
 };
 static_assert(2 * kMaxRows >= 2 * kMaxObs, "the section histogram aliases rowWa / rowWn");
@@ -608,6 +609,11 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BIT
         });
 #pragma unroll
         for (int s = 0; s < NS; ++s) rmax[s] = sqrt(warp_max(rmax[s]));   // sqrt is monotone
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) ws.hsi_r[s] = rmax[s];
+        }
+        __syncwarp();
     }
 
     int n_new = 0, n_possible = 0;   // RGB: warp-uniform; HSI n_new: per-lane partial
@@ -645,11 +651,13 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BIT
                 const int sv0 = (int)__ldcg(&thick[j]);
                 int sv = sv0;
                 const double x = __ldg(&pk.tx[j]), y = __ldg(&pk.ty[j]), z = __ldg(&pk.tz[j]);
-#pragma unroll
+                // not unrolled: one copy of the FP64 square root and division in the instruction stream (unrolled
+                // five times the kernel outgrew the instruction cache: "no instruction" was its top stall at C3)
+#pragma unroll 1
                 for (int s = 0; s < NS; ++s) {
                     if ((shots & (1u << s)) && sv > 0) {
                         const double dx = x - cen(ws, s, 0), dy = y - cen(ws, s, 1), dz = z - cen(ws, s, 2);
-                        const double ratio = sqrt(dx * dx + dy * dy + dz * dz) / rmax[s];
+                        const double ratio = sqrt(dx * dx + dy * dy + dz * dz) / ws.hsi_r[s];
                         const int quantity = (int)(kHsiTargetMax * (1.0 - ratio * ratio)) + 1;   // :429
                         sv -= quantity;
                         n_new += quantity;
