@@ -196,9 +196,9 @@ def run_rollout(args, workload, env, cfg, rank, world_size, device, warmup):
     T = 100
     n_out = cfg.discrete_granularity if cfg.action_mode == 'discrete' else cfg.action_dim
     policy = rollout.MlpPolicy(env.obs_dim, n_out, device=device, seed=rank, discrete=cfg.action_mode == 'discrete')
-    worker = rollout.RolloutWorker(env, policy, fragment_length=T)
+    worker = rollout.RolloutWorker(env, policy, fragment_length=T, use_cuda_graph=not args.no_graph)
     worker.start()
-    for _ in range(max(1, min(warmup, 2))):
+    for _ in range(max(2, min(warmup, 3))):      # the first fragment runs eagerly, the second captures the CUDA graph
         worker.collect(); worker.advance()
     torch.cuda.synchronize(device)
     if world_size > 1:
@@ -231,7 +231,7 @@ def run_rollout(args, workload, env, cfg, rank, world_size, device, warmup):
             'warmup': warmup, 'ms_per_step': ms / (args.steps * T), 'higher_is_better': True, 'scaling': workload['scaling'],
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload['name'] + '; rollout fragments of %d steps with the on-GPU MLP policy '
-                       '(obs->256->128->logits+value, FP32, random init), one stats all-reduce per fragment' % T,
+                       '(obs->256->128->logits+value, FP32/TF32, random init), one stats all-reduce per fragment; %s' % (T, 'whole fragment replayed from one CUDA graph' if worker._graph is not None else 'eager launches (%s)' % (worker.graph_error or 'graph off')),
                        'envs_per_gpu': env.num_envs, 'l2': 'not flushed (policy and fragment traffic between steps)',
                        'timing': 'CUDA events around all fragments, max over ranks',
                        'parallelism': 'env-sharded x%d, no step-path collective' % world_size},
@@ -252,6 +252,7 @@ def main():
     ap.add_argument('--envs', type=int, default=None, help='override environments per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-flush', action='store_true', help='keep the L2 warm between steps (not the headline)')
+    ap.add_argument('--no-graph', action='store_true', help='--rollout: keep the eager per-step launch loop (no CUDA graph)')
     ap.add_argument('--rollout', action='store_true',
                     help='time whole rollout fragments (on-GPU MLP policy + env step, paintrl_b200.rollout) instead of bare steps; '
                          '--steps counts fragments of 100 steps (BASELINE config C5 / paint_ppo.py sample_batch_size)')

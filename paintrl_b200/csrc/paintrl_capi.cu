@@ -80,7 +80,6 @@ struct PaintrlEngine {
     // measured slower at C2 (the move phase loses L1 and issue slots to the co-resident paint warps).
     int carveout_percent = -1;
     bool carveout_set = false;       // the step kernels' shared-memory carveout has been requested on this device
-    unsigned step_seq = 0;           // sequence number of the last step launched
     // staging for the host-buffer entry points
     void *stage_actions = nullptr;
     // paintrl_step_host: one contiguous block, laid out per call as obs | reward | penalty | actual | [next_obs] | done,
@@ -642,7 +641,6 @@ EnvArrays env_arrays(PaintrlEngine *e) {
     ea.thick = e->thick;
     ea.grid_cnt = e->grid_cnt;
     ea.ready = e->ready;
-    ea.seq = e->step_seq;
     return ea;
 }
 
@@ -1044,8 +1042,6 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     io.actual = actual_dev; io.done = done_dev; io.new_texels = new_texels_dev;
     io.next_obs = h->cfg.auto_reset ? next_obs_dev : nullptr;
     io.reset_start_idx = reset_start_idx_dev;
-    h->step_seq += 1;
-    if (h->step_seq == 0) h->step_seq = 1;   // 0 is the flags' initial value
     {   // lanes per environment in the move phase: fewer when there are enough environments to fill the GPU
         const int threads = h->move_warps * 32;
         cudaStream_t ms = as_stream(stream);

@@ -42,8 +42,7 @@ struct EnvArrays {
     unsigned *bits;        // [num_envs][n_words_pad]  flip bit per slot
     int16_t *thick;        // [num_envs][n_slots]      HSI thickness (HSI only)
     unsigned *grid_cnt;    // [num_envs][n_gcells_pad] flipped texels per grid-observation cell (grid mode only)
-    unsigned *ready;       // [num_envs] sequence number of the last step whose move phase has been published
-    unsigned seq;          // this step's sequence number
+    unsigned *ready;       // [num_envs] 1 once the step's move phase of the environment has been published (paint consumes it)
 };
 
 // Words of the per-environment bit-plane a warp stages in shared memory (one TMA bulk copy in,
@@ -798,7 +797,7 @@ __device__ __forceinline__ void move_body(const DevPack &pk, const DevConfig &cf
         ea.moves[env].miss_cache = miss_cache;
         // publish: this lane wrote the record and the move output; the paint kernel's warp for this
         // environment acquires the flag instead of waiting for the whole grid
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ea.ready + env), "r"(ea.seq) : "memory");
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ea.ready + env), "r"(1u) : "memory");
     }
     PAINTRL_PROF(13, grp.gl == 0);
 #ifdef PAINTRL_PROFILE
@@ -849,9 +848,12 @@ __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &c
         unsigned v;
         for (;;) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            if (v == ea.seq) break;
+            if (v != 0u) break;
             __nanosleep(200);
         }
+        // consume: the next step's move kernel (which starts after this grid has completed) raises it again.
+        // No sequence number in the kernel arguments, so a captured step can be replayed from a CUDA graph.
+        ea.ready[env] = 0u;
     }
     __syncwarp();
     PAINTRL_TRACE_MARK(env, 3, lane == 0);

@@ -40,6 +40,8 @@ class MlpPolicy(object):
         self.head_b = torch.zeros(n_out + 1, device=device)
         self.n_out = n_out
         self.discrete = discrete
+        if torch.cuda.is_available():
+            torch.backends.cuda.matmul.allow_tf32 = True     # the policy's three small GEMMs on the tensor cores
         self.device = device
         self.gen = torch.Generator(device=device)
         self.gen.manual_seed(seed + 1)
@@ -89,10 +91,16 @@ class RolloutFragment(object):
 class RolloutWorker(object):
     """Collects fragments from a `BatchedPaintEnv` created with `auto_reset=True`."""
 
-    def __init__(self, env, policy, fragment_length=100):
+    def __init__(self, env, policy, fragment_length=100, use_cuda_graph=False):
+        """`use_cuda_graph`: after one eager fragment, capture the whole T-step loop (policy kernels and the
+        two step kernels per step, ~25 launches each) into one CUDA graph and replay it per fragment -- the
+        fragment buffers are persistent, so every address in the loop is static.  Small batches are
+        launch-bound without it."""
         if not env.cfg.auto_reset:
             raise ValueError('RolloutWorker needs an environment created with auto_reset=True')
         self.env, self.policy, self.T = env, policy, int(fragment_length)
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graph, self._eager_fragments, self.graph_error = None, 0, None
         shape = () if env.cfg.action_mode == 'discrete' else (env.action_dim,)
         self.frag = RolloutFragment(self.T, env.num_envs, env.obs_dim, shape, env.device)
         dev, B = env.device, env.num_envs
@@ -108,16 +116,8 @@ class RolloutWorker(object):
         self.ep_reward.zero_(); self.ep_penalty.zero_(); self.ep_len.zero_()
         self._started = True
 
-    @torch.no_grad()
-    def collect(self):
-        """One fragment of T steps (truncate_episodes: episodes continue across fragments).
-        Returns (fragment, stats) where stats holds this rank's sums for `iteration_stats`; the
-        only host synchronisation is the read of those eight numbers at the end."""
-        if not self._started:
-            self.start()
+    def _run_steps(self):
         f, env, pol = self.frag, self.env, self.policy
-        dev = env.device
-        acc = torch.zeros(6, dtype=torch.float64, device=dev)     # episodes, reward, penalty, return, new texels, max len
         for t in range(self.T):
             a, logp, value = pol.act(f.obs[t])
             f.actions[t].copy_(a)
@@ -125,21 +125,55 @@ class RolloutWorker(object):
             f.value[t].copy_(value)
             env.step_into(f.actions[t], f.term_obs[t], f.reward[t], f.penalty[t], f.actual[t], f.done[t],
                           next_obs=f.obs[t + 1], new_texels=f.new_texels[t])
-            d = f.done[t].bool()
-            self.ep_reward += f.reward[t]
-            self.ep_penalty += f.penalty[t]
-            self.ep_len += 1
-            acc[0] += d.sum()
-            acc[1] += (self.ep_reward * d).sum()
-            acc[2] += (self.ep_penalty * d).sum()
-            acc[4] += f.new_texels[t].sum()
-            acc[5] = torch.maximum(acc[5], (self.ep_len * d).max().to(torch.float64))
-            keep = (~d).to(torch.float64)
-            self.ep_reward *= keep
-            self.ep_penalty *= keep
-            self.ep_len *= (~d)
         f.value[self.T].copy_(pol.forward(f.obs[self.T])[1])      # bootstrap value of the truncated episodes
-        acc[3] = acc[1] - acc[2]
+
+    def _capture(self):
+        try:
+            torch.cuda.synchronize(self.env.device)
+            graph = torch.cuda.CUDAGraph()
+            if hasattr(graph, 'register_generator_state'):
+                graph.register_generator_state(self.policy.gen)
+            with torch.cuda.graph(graph):
+                self._run_steps()
+            self._graph = graph
+        except Exception as exc:                   # noqa: BLE001 - stay on the eager loop, keep the reason
+            self._graph = None
+            self.graph_error = '%s: %s' % (type(exc).__name__, exc)
+            torch.cuda.synchronize(self.env.device)
+
+    @torch.no_grad()
+    def collect(self):
+        """One fragment of T steps (truncate_episodes: episodes continue across fragments).
+        Returns (fragment, stats) where stats holds this rank's sums for `iteration_stats`; the
+        only host synchronisation is the read of those eight numbers at the end."""
+        if not self._started:
+            self.start()
+        f, env = self.frag, self.env
+        if self.use_cuda_graph and self._graph is None and self._eager_fragments >= 1 and self.graph_error is None:
+            self._capture()
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._run_steps()
+            self._eager_fragments += 1
+        # per-episode totals (the reference's on_episode_step / on_episode_end callbacks), once per fragment:
+        # running sums over time; an episode's total is the running sum at its `done` minus the running sum at
+        # the previous `done` (rewards, penalties and step counts are non-negative, so that is a running maximum)
+        done = f.done.bool()
+        ones = torch.ones_like(f.reward)
+        totals = []
+        carries = []
+        for carry, x in ((self.ep_reward, f.reward), (self.ep_penalty, f.penalty), (self.ep_len.to(torch.float64), ones)):
+            cs = carry.unsqueeze(0) + torch.cumsum(x, dim=0)
+            at_done = torch.where(done, cs, torch.zeros_like(cs))
+            seen = torch.cummax(at_done, dim=0).values                      # running sum at the latest done <= t
+            prev = torch.cat([torch.zeros_like(seen[:1]), seen[:-1]], dim=0)
+            totals.append(torch.where(done, cs - prev, torch.zeros_like(cs)))
+            carries.append(cs[-1] - seen[-1])
+        self.ep_reward, self.ep_penalty = carries[0], carries[1]
+        self.ep_len = carries[2].round().to(torch.int64)
+        acc = torch.stack([done.sum().to(torch.float64), totals[0].sum(), totals[1].sum(), totals[0].sum() - totals[1].sum(),
+                           f.new_texels.sum().to(torch.float64), totals[2].max()])
         host = acc.cpu()
         next_first = f.obs[self.T].clone()
         stats = {'env_steps': float(self.T * env.num_envs), 'episodes': float(host[0]), 'sum_reward': float(host[1]),

@@ -67,3 +67,32 @@ def test_fragment_replays_through_the_oracle(cuda_device):
     assert totals['new_texels'] > 0
     env.close()
     ora.close()
+
+
+def test_cuda_graph_fragment_equals_eager_fragment(cuda_device):
+    """The same seeds through the eager loop and through the captured CUDA graph give identical fragments
+    (the per-environment move -> paint hand-off carries no per-launch argument, so a captured step replays)."""
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    from paintrl_b200.rollout import MlpPolicy, RolloutWorker
+    n, T = 128, 12
+    frags = []
+    for use_graph in (False, True):
+        cfg = EnvConfig(dict(BASE), auto_reset=True, seed=3)
+        env = BatchedPaintEnv(n, cfg, device=cuda_device)
+        worker = RolloutWorker(env, MlpPolicy(env.obs_dim, 4, device=cuda_device, seed=5), fragment_length=T,
+                               use_cuda_graph=use_graph)
+        worker.start((np.arange(n) % env.n_starts).astype(np.int32))
+        out = []
+        for it in range(4):
+            f, stats = worker.collect()
+            out.append({k: getattr(f, k).clone() for k in ('obs', 'actions', 'reward', 'done', 'term_obs', 'logp')})
+            out[-1]['stats'] = stats
+            worker.advance()
+        if use_graph:
+            assert worker._graph is not None, worker.graph_error
+        frags.append(out)
+        env.close()
+    for a, b in zip(*frags):
+        for k in ('obs', 'actions', 'reward', 'done', 'term_obs', 'logp'):
+            assert torch.equal(a[k], b[k]), k
+        assert a['stats'] == b['stats']
