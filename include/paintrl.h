@@ -96,7 +96,8 @@ typedef struct PaintrlConfig {
     int32_t action_mode;            /* PAINTRL_ACTION_*            ACTION_MODE  */
     int32_t action_shape;           /* 1 or 2                      ACTION_SHAPE */
     int32_t discrete_granularity;   /* DISCRETE_GRANULARITY */
-    /* [discrete_granularity,3] host table (u1, u2, turning angle) for the discrete actions,
+    /* [discrete_granularity + 1,3] host table (u1, u2, turning angle) for the discrete actions 0..n; row n
+     * serves every action >= n (the reference clips, robot.py:390-393), actions < 0 use row 0;
      * computed by the host exactly as robot_gym_env.py:342-347 + robot.py:151-160,352-358 do
      * (NumPy cos/sin, libm atan), so discrete directions are bit-identical to the reference. */
     const double *discrete_table;

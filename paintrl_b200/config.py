@@ -64,14 +64,16 @@ def turning_angle(delta_axis1, delta_axis2):
 
 
 def discrete_table(n):
-    """(u1, u2, turning angle) for each discrete action a in 0..n-1.
+    """(u1, u2, turning angle) for each discrete action a in 0..n (n + 1 rows).
 
     robot_gym_env.py:342-347 (`[2 * (a - n / 2) / n]`), robot.py:390-397 (clip, normalise, scale)
     and robot.py:352-358, evaluated on the host with the same NumPy / libm calls as the
-    reference so that discrete directions carry the reference's own 1e-16 residues.
+    reference so that discrete directions carry the reference's own 1e-16 residues.  Actions outside
+    0..n-1 are not rejected by the reference but clipped (robot.py:390-393): a < 0 acts like 0
+    (both give -1) and a >= n like the extra row n (clipped to +1).
     """
-    table = np.zeros((n, 3), dtype=np.float64)
-    for a in range(n):
+    table = np.zeros((n + 1, 3), dtype=np.float64)
+    for a in range(n + 1):
         act = a - n / 2
         act = [2 * act / n]
         act = [min(1, max(-1, v)) for v in act]

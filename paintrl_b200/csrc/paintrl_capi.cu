@@ -925,7 +925,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     c.discrete_granularity = cfg->discrete_granularity;
     c.discrete_table = nullptr;
     if (cfg->action_mode == PAINTRL_ACTION_DISCRETE) {
-        std::vector<double> t(cfg->discrete_table, cfg->discrete_table + 3 * (size_t)cfg->discrete_granularity);
+        std::vector<double> t(cfg->discrete_table, cfg->discrete_table + 3 * ((size_t)cfg->discrete_granularity + 1));
         if (e->arena.upload(t, &c.discrete_table) != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, "upload discrete table"); }
     }
     c.obs_mode = cfg->obs_mode; c.obs_grad = cfg->obs_grad; c.obs_dim = od;

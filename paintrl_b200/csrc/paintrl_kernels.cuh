@@ -703,21 +703,21 @@ __device__ __forceinline__ void move_body(const DevPack &pk, const DevConfig &cf
     double u1, u2, new_angle;
     if (cfg.action_mode == 0) {
         long long a = reinterpret_cast<const long long *>(actions)[env];
-        int ai = (int)min(max(a, 0ll), (long long)cfg.discrete_granularity - 1);
+        int ai = (int)min(max(a, 0ll), (long long)cfg.discrete_granularity);   // out-of-range actions are clipped, not rejected (robot.py:390-393)
         u1 = __ldg(&cfg.discrete_table[3 * ai]);
         u2 = __ldg(&cfg.discrete_table[3 * ai + 1]);
         new_angle = __ldg(&cfg.discrete_table[3 * ai + 2]);
     } else {
         const double *a = reinterpret_cast<const double *>(actions) + (size_t)env * cfg.action_shape;
         double a0 = a[0];
-        if (!(-1.0 <= a0 && a0 <= 1.0)) a0 = a0 < -1.0 ? -1.0 : (a0 > 1.0 ? 1.0 : a0);
+        if (!(-1.0 <= a0 && a0 <= 1.0)) a0 = a0 < -1.0 ? -1.0 : 1.0;   // robot.py:391-393 (a NaN ends up at 1 there too)
         if (cfg.action_shape == 1) {
             double phi = (a0 + 1.0) * kPi;
             u1 = cos(phi);
             u2 = sin(phi);
         } else {
             double a1v = a[1];
-            if (!(-1.0 <= a1v && a1v <= 1.0)) a1v = a1v < -1.0 ? -1.0 : (a1v > 1.0 ? 1.0 : a1v);
+            if (!(-1.0 <= a1v && a1v <= 1.0)) a1v = a1v < -1.0 ? -1.0 : 1.0;
             double phi = atan2(a1v, a0);
             double x = fabs(a0), y = fabs(a1v);
             if (x == 0.0 && y == 0.0) { u1 = x; u2 = y; }

@@ -158,3 +158,73 @@ def test_host_step_scattered_buffers(cuda_device, auto_reset):
         assert np.array_equal(no_next[k], scattered[k]), k
     a.close()
     b.close()
+
+
+def test_host_steps_interleaved_with_device_steps_and_resets(cuda_device):
+    """Repeated step_host calls with the same pinned buffers, interleaved with resets, device-side steps and a
+    change of buffers, against the device-path engine."""
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    n = 96
+    a = BatchedPaintEnv(n, dict(BASE), device=cuda_device, auto_reset=True, seed=9)      # host-buffer path
+    b = BatchedPaintEnv(n, dict(BASE), device=cuda_device, auto_reset=True, seed=9)      # device path (reference)
+    start = (np.arange(n) % 4).astype(np.int32)
+    a.reset(start)
+    b.reset(start)
+    rng = np.random.default_rng(12)
+    out = a.host_buffers(pinned=True)
+    acts_pinned = torch.zeros(n, dtype=torch.int64, pin_memory=True).numpy()
+    for t in range(60):
+        acts = rng.integers(0, 4, size=n)
+        if t == 25:                        # a reset in between
+            a.reset(start)
+            b.reset(start)
+        if t == 40:                        # new buffers
+            out = a.host_buffers(pinned=True)
+        if t in (10, 11):                  # device-side steps in between
+            a.step(acts)
+            b.step(acts)
+            continue
+        acts_pinned[:] = acts
+        a.step_host(acts_pinned, out)
+        o, actual, done, info = b.step(acts)
+        assert np.array_equal(o.cpu().numpy(), out['obs']), t
+        assert np.array_equal(actual.cpu().numpy(), out['actual']) and np.array_equal(done.cpu().numpy(), out['done']), t
+        assert np.array_equal(info['next_obs'].cpu().numpy(), out['next_obs']), t
+    assert np.array_equal(a.get_state()['status'].cpu().numpy(), b.get_state()['status'].cpu().numpy())
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize('continuous', [False, True])
+def test_out_of_range_actions_are_clipped_like_the_reference(cuda_device, continuous):
+    """robot.py:390-393 clips instead of rejecting: discrete actions outside 0..n-1, continuous components
+    beyond [-1, 1], infinities and NaN (which the reference's comparison chain sends to +1)."""
+    from oracle.oracle import OracleBatch
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    kw = dict(action_mode='continuous', action_shape=2) if continuous else dict(discrete_granularity=4)
+    cfg = EnvConfig(dict(BASE), auto_reset=False, **kw)
+    pack = PartPack.for_part(0)
+    n = 64
+    env = BatchedPaintEnv(n, cfg, device=cuda_device, pack=pack)
+    ora = OracleBatch(pack, cfg, n)
+    start = (np.arange(n) % 4).astype(np.int32)
+    assert np.array_equal(env.reset(start).cpu().numpy(), ora.reset(start))
+    rng = np.random.default_rng(5)
+    for t in range(12):
+        if continuous:
+            acts = rng.uniform(-3, 3, size=(n, 2))
+            acts[::7, 0] = np.nan
+            acts[3::11, 1] = np.inf
+            acts[5::13, 0] = -np.inf
+        else:
+            acts = rng.integers(-3, 9, size=n)
+        o_g, a_g, d_g, info = env.step(acts)
+        o_o, r_o, p_o, a_o, d_o = ora.step(acts)
+        assert np.array_equal(d_g.cpu().numpy(), d_o), t
+        if continuous:
+            assert np.allclose(o_g.cpu().numpy(), o_o, rtol=1e-5, atol=1e-12) and np.allclose(a_g.cpu().numpy(), a_o, rtol=1e-5, atol=1e-12)
+        else:
+            assert np.array_equal(o_g.cpu().numpy(), o_o) and np.array_equal(a_g.cpu().numpy(), a_o), t
+    assert np.array_equal(env.get_state()['status'].cpu().numpy(), ora.status())
+    env.close()
+    ora.close()

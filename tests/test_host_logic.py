@@ -43,6 +43,8 @@ def test_discrete_table_carries_the_reference_residues():
     assert t[0, 0] == 1.0 and t[0, 1] == 0.0
     assert abs(t[1, 0]) < 1e-15 and t[1, 0] != 0.0 and t[1, 1] == 1.0      # the 6e-17 residue is kept
     assert t[2, 0] == -1.0 and abs(t[2, 1]) < 1e-15 and t[2, 1] != 0.0
+    # row n: every action >= n is clipped to +1 (robot.py:390-393) -> phi = 2 pi
+    assert t.shape == (5, 3) and t[4, 0] == np.cos(2 * np.pi) and t[4, 1] == np.sin(2 * np.pi)
 
 
 def test_algorithmic_bytes_matches_survey_8d():
