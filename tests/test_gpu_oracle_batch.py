@@ -228,3 +228,40 @@ def test_out_of_range_actions_are_clipped_like_the_reference(cuda_device, contin
     assert np.array_equal(env.get_state()['status'].cpu().numpy(), ora.status())
     env.close()
     ora.close()
+
+
+@pytest.mark.parametrize('num_envs', [1, 5, 33, 257])
+def test_ragged_batch_sizes(cuda_device, num_envs):
+    """Batch sizes that fill neither a CTA nor a warp group, down to a single environment."""
+    _run_case(dict(BASE, START_POINT_MODE='edge'), dict(), num_envs, 12, cuda_device, status_every=5)
+
+
+def test_subset_reset_leaves_the_other_environments_alone(cuda_device):
+    """reset_at / paintrl_reset with env_ids (the RLlib VectorEnv contract): only the listed environments
+    start over; set_pose (spiral.py's robot.reset(pose)) moves without clearing the paint."""
+    from oracle.oracle import OracleBatch
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    cfg = EnvConfig(dict(BASE), auto_reset=False)
+    pack = PartPack.for_part(0)
+    n = 40
+    env = BatchedPaintEnv(n, cfg, device=cuda_device, pack=pack)
+    ora = OracleBatch(pack, cfg, n)
+    start = (np.arange(n) % 4).astype(np.int32)
+    env.reset(start)
+    ora.reset(start)
+    rng = np.random.default_rng(8)
+    for t in range(20):
+        acts = rng.integers(0, 4, size=n)
+        env.step(acts)
+        ora.step(acts)
+        if t % 5 == 4:
+            ids = rng.choice(n, size=7, replace=False).astype(np.int32)
+            st = rng.integers(0, 4, size=7).astype(np.int32)
+            assert np.array_equal(env.reset(st, env_ids=ids).cpu().numpy(), ora.reset(st, env_ids=list(ids)))
+        if t == 12:
+            pts = pack.start_points('all')
+            pos, nrm = pts[100, 0], pts[100, 1]
+            assert np.array_equal(env.set_pose(pos, nrm, env_ids=[3, 9]).cpu().numpy(), ora.set_pose(pos, nrm, env_ids=[3, 9]))
+    assert np.array_equal(env.get_state()['status'].cpu().numpy(), ora.status())
+    env.close()
+    ora.close()
