@@ -430,9 +430,8 @@ __device__ __forceinline__ double cen(const WS &ws, int s, int k) {
 
 // FP32 pre-test of slot j against the six balls: e[s] = |t - c_s|^2 - r^2 (negative inside);
 // returns true when some |e[s]| <= kBallEps, i.e. FP32 cannot decide and the FP64 test must.
-__device__ __forceinline__ bool ball_pretest(const DevPack &pk, const ShotsF &c, int j, float e[NS + 1]) {
+__device__ __forceinline__ bool ball_pretest_at(const ShotsF &c, float tx, float ty, float tz, float e[NS + 1]) {
     const float nr2f = -(float)(kPaintRadius * kPaintRadius);
-    const float tx = __ldg(&pk.fx[j]), ty = __ldg(&pk.fy[j]), tz = __ldg(&pk.fz[j]);
     float m = INFINITY;
 #pragma unroll
     for (int s = 0; s <= NS; ++s) {
@@ -441,6 +440,9 @@ __device__ __forceinline__ bool ball_pretest(const DevPack &pk, const ShotsF &c,
         m = fminf(m, fabsf(e[s]));
     }
     return m <= kBallEps;
+}
+__device__ __forceinline__ bool ball_pretest(const DevPack &pk, const ShotsF &c, int j, float e[NS + 1]) {
+    return ball_pretest_at(c, __ldg(&pk.fx[j]), __ldg(&pk.fy[j]), __ldg(&pk.fz[j]), e);
 }
 
 // the exact test `dx*dx + dy*dy + dz*dz <= r*r` of slot j against ball s (bullet_paint_wrapper.py:569)
@@ -472,11 +474,11 @@ __device__ __forceinline__ unsigned ball_mask(const DevPack &pk, const ShotsF &c
 // not inside the shot before it (bullet_paint_wrapper.py:575; the shot before shot 0 is the previous
 // step's last one).  Predicate logic only, no per-shot bit mask.
 template <typename WS>
-__device__ __forceinline__ void ball_flags(const DevPack &pk, const ShotsF &c, const WS &ws, int j, bool has_last, bool &any_shot,
-                                           bool &possible) {
+__device__ __forceinline__ void ball_flags_at(const DevPack &pk, const ShotsF &c, const WS &ws, int j, float tx, float ty, float tz,
+                                              bool has_last, bool &any_shot, bool &possible) {
     float e[NS + 1];
     bool in[NS + 1];
-    if (ball_pretest(pk, c, j, e)) {
+    if (ball_pretest_at(c, tx, ty, tz, e)) {
         const double x = __ldg(&pk.tx[j]), y = __ldg(&pk.ty[j]), z = __ldg(&pk.tz[j]);
 #pragma unroll
         for (int s = 0; s <= NS; ++s) in[s] = ball_exact(ws, x, y, z, s);
@@ -493,6 +495,11 @@ __device__ __forceinline__ void ball_flags(const DevPack &pk, const ShotsF &c, c
         possible = possible || (in[s] && !prev);
         prev = in[s];
     }
+}
+template <typename WS>
+__device__ __forceinline__ void ball_flags(const DevPack &pk, const ShotsF &c, const WS &ws, int j, bool has_last, bool &any_shot,
+                                           bool &possible) {
+    ball_flags_at(pk, c, ws, j, __ldg(&pk.fx[j]), __ldg(&pk.fy[j]), __ldg(&pk.fz[j]), has_last, any_shot, possible);
 }
 
 // Per row, the words whose texels can lie inside one of the step's shots: the row's axis1 interval
@@ -617,7 +624,52 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BIT
 
     int n_new = 0, n_possible = 0;   // RGB: warp-uniform; HSI n_new: per-lane partial
     unsigned any = 0;
-    if (COLOR == 0) {                                      // :358-365
+    if (COLOR == 0 && !STAGED) {
+        // Large textures (bit-plane in global memory, hundreds of candidate words per step): a word at a time the
+        // loop pays two dependent L2 round trips per word (the texels' coordinates, then the plane word; ncu at
+        // C4: 6.1 warps per issue on the long scoreboard, 50 % of the samples on those two waits).  Four words per
+        // iteration, all their loads issued before the first is tested.
+        constexpr int kBatch = 4;
+        for (int r0 = 0; r0 < pk.n_rows; r0 += 32) {
+            const int r = r0 + lane;
+            const int wa = r < pk.n_rows ? ws.rowWa[r] : 0, wn = r < pk.n_rows ? ws.rowWn[r] : 0;
+            unsigned m = __ballot_sync(kFull, wn > 0);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int a = __shfl_sync(kFull, wa, src), n = __shfl_sync(kFull, wn, src);
+                for (int w0 = a; w0 < a + n; w0 += kBatch) {
+                    float tx[kBatch], ty[kBatch], tz[kBatch];
+                    unsigned old[kBatch];
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q) {
+                        const int w = min(w0 + q, a + n - 1);          // the tail repeats the last word (not processed twice)
+                        const int j = w * 32 + lane;
+                        tx[q] = __ldg(&pk.fx[j]); ty[q] = __ldg(&pk.fy[j]); tz[q] = __ldg(&pk.fz[j]);
+                        old[q] = bits.ld(w);
+                    }
+#pragma unroll
+                    for (int q = 0; q < kBatch; ++q) {
+                        const int w = w0 + q;
+                        if (w >= a + n) break;
+                        const int j = w * 32 + lane;
+                        bool any_shot, possible;
+                        ball_flags_at(pk, c, ws, j, tx[q], ty[q], tz[q], has_last, any_shot, possible);
+                        const unsigned uni = __ballot_sync(kFull, any_shot);
+                        if (uni == 0u) continue;
+                        n_possible += __popc(__ballot_sync(kFull, possible));
+                        const unsigned flipped = uni & ~old[q];
+                        if (flipped) {
+                            n_new += __popc(flipped);
+                            if (lane == 0) bits.st(w, old[q] | uni);
+                            any |= flipped;
+                            if (grid_cnt && ((flipped >> lane) & 1u)) atomicAdd(grid_cnt + __ldg(&pk.gcell[j]), 1u);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (COLOR == 0) {                               // :358-365
         for_each_stamp_word<STAGED>(pk, lane, ws, n_cand, [&](int w) {
             const int j = w * 32 + lane;
             bool any_shot, possible;
