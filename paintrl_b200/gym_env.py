@@ -256,6 +256,16 @@ class PaintGymEnv(_GymEnv):
         profile[front], bullet_paint_wrapper.py:737-738), in part-pack order."""
         return self._engine.get_state()['status'][0].cpu().numpy()
 
+    def texture_image(self):
+        """`get_texture_image` (bullet_paint_wrapper.py:737-738): the part's texture as the simulation has
+        painted it so far, a PIL image when Pillow is importable, else the uint8 array [W, H, 3]."""
+        arr = self._engine.pack.texture_image(self.texture_status(), self._engine.cfg.color_mode)
+        try:
+            from PIL import Image
+            return Image.fromarray(arr, 'RGB')
+        except Exception:                       # noqa: BLE001 - Pillow is optional
+            return arr
+
     def close(self):
         if getattr(self, '_engine', None) is not None:
             self._engine.close()

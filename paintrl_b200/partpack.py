@@ -111,8 +111,15 @@ class PartPack(object):
         n = ij.shape[0]
         for key in ('status_init_rgb', 'status_init_hsi'):
             arrays[key] = np.full(n, self.arrays[key][0], dtype=np.int16)
-        for key in ('texel_off', 'init_texture_rgb', 'init_texture_hsi', 'grid_cells_4', 'grid_cells_10'):
-            arrays.pop(key, None)          # texture-size specific and not needed by the step path
+        for key in ('texel_off', 'grid_cells_4', 'grid_cells_10'):
+            arrays.pop(key, None)          # texture-size specific; offsets are recomputed on demand
+        # synthetic blank texture: everything irrelevant (black, bullet_paint_wrapper.py:583-590) except the front texels
+        off = np.minimum((ij[:, 0].astype(np.int64) + ij[:, 1].astype(np.int64) * width) * 3, width * height * 3 - 4)
+        for key, init in (('init_texture_rgb', self.arrays['status_init_rgb'][0]), ('init_texture_hsi', self.arrays['status_init_hsi'][0])):
+            tex = np.zeros(width * height * 3, dtype=np.uint8)
+            for k in range(3):
+                tex[off + k] = init
+            arrays[key] = tex
         meta = dict(self.meta)
         scale = (width / float(self.width)) * (height / float(self.height))
         meta.update(width=int(width), height=int(height), max_points=float(self.max_points) * scale,
@@ -142,6 +149,40 @@ class PartPack(object):
     def init_texture(self, color_mode):
         key = 'init_texture_rgb' if color_mode == 'RGB' else 'init_texture_hsi'
         return np.array(self.arrays[key], dtype=np.uint8)
+
+    def texel_offsets(self):
+        """Byte offset of every front texel in the texture plane: `Part.get_texel(i, j)`
+        (bullet_paint_wrapper.py:505-506) = min((i + j * W) * 3, len(texels) - 4)."""
+        if 'texel_off' in self.arrays:
+            return np.asarray(self.arrays['texel_off'], dtype=np.int64)
+        ij = self.front_ij.astype(np.int64)
+        return np.minimum((ij[:, 0] + ij[:, 1] * self.width) * 3, self.width * self.height * 3 - 4)
+
+    def compose_texture(self, status, color_mode):
+        """The reference's whole `Part.texels` array (bullet_paint_wrapper.py:467) rebuilt from the front-texel
+        status plane the engine keeps (`paintrl_get_state`): the labelled initial texture with, per front
+        texel, the painted colour (255, 0, 0) where the first channel reached 255 (RGB, :358-365), or all three
+        channels at the remaining thickness (HSI, :396-417; values below 0 are kept, as under the reference's
+        integer texels).  int16 [W * H * 3]; `texture_image` gives the uint8 picture."""
+        status = np.asarray(status).reshape(-1)
+        if status.shape[0] != self.n_texels:
+            raise ValueError('expected %d status values' % self.n_texels)
+        tex = self.init_texture(color_mode).astype(np.int16)
+        off = self.texel_offsets()
+        if color_mode == 'RGB':
+            painted = status == 255
+            tex[off[painted]] = 255
+            tex[off[painted] + 1] = 0
+            tex[off[painted] + 2] = 0
+        else:
+            for k in range(3):
+                tex[off + k] = status.astype(np.int16)
+        return tex
+
+    def texture_image(self, status, color_mode):
+        """`get_texture_image` (bullet_paint_wrapper.py:18-21, 737-738) as a uint8 array [W, H, 3]."""
+        tex = self.compose_texture(status, color_mode)
+        return (tex & 0xff).astype(np.uint8).reshape(self.width, self.height, 3)
 
     # ------------------------------------------------------------------------------ C view
     def to_c(self, start_mode, color_mode):

@@ -133,3 +133,25 @@ def test_vector_env_matches_single_envs(cuda_device):
     assert vec.get_unwrapped() == []
     vec.close()
     ora.close()
+
+
+def test_texture_image_follows_the_painted_status(cuda_device):
+    """`texture_image()` (get_texture_image, bullet_paint_wrapper.py:737-738): painted front texels show the
+    paint colour, everything else the labelled initial texture."""
+    import numpy as np
+    from PaintRLEnv.robot_gym_env import PaintGymEnv
+    from paintrl_b200.config import DEFAULT_EXTRA_CONFIG
+    env = PaintGymEnv('', with_robot=False, renders=False, rollout=True, extra_config=dict(DEFAULT_EXTRA_CONFIG))
+    env.reset()
+    for a in (1, 1, 0, 3):
+        env.step(a)
+    status = env.texture_status()
+    img = np.asarray(env.texture_image())
+    pack = env._engine.pack
+    assert img.shape == (240, 240, 3) and (status == 255).sum() > 0
+    flat = img.reshape(-1)
+    off = pack.texel_offsets()
+    painted = status == 255
+    assert (flat[off[painted]] == 255).all() and (flat[off[painted] + 1] == 0).all() and (flat[off[painted] + 2] == 0).all()
+    assert (flat[off[~painted]] == 191).all()
+    env.close()

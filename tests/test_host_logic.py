@@ -106,3 +106,21 @@ def test_world_size_2_gloo_statistics_allreduce(tmp_path):
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
         assert 'rank %d ok' % rank in out
+
+
+@pytest.mark.parametrize('name,part_no,mode', [('door_rgb', 0, 'RGB'), ('sheet_hsi', 1, 'HSI')])
+def test_compose_texture_rebuilds_the_reference_texels(name, part_no, mode):
+    """Part.texels of the verbatim reference after 25 steps (oracle/make_texture_golden.py) from its front-texel
+    status plane alone."""
+    from paintrl_b200.partpack import PartPack
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 't_texture.npz'))
+    pack = PartPack.for_part(part_no)
+    tex = pack.compose_texture(g[name + '/status'], mode)
+    assert np.array_equal(tex, g[name + '/texels'])
+    img = pack.texture_image(g[name + '/status'], mode)
+    assert img.shape == (240, 240, 3) and img.dtype == np.uint8
+    assert np.array_equal(img.reshape(-1), (g[name + '/texels'] & 0xff).astype(np.uint8))
+    # computed offsets equal the stored ones
+    stored = pack.arrays['texel_off']
+    bare = PartPack(pack.meta, {k: v for k, v in pack.arrays.items() if k != 'texel_off'})
+    assert np.array_equal(bare.texel_offsets(), stored)
