@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --steps 300 --warmup 10 2>&1 | tail -1 | tee gpurun_out/bench_n8.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('c2 x8', d['value']/1e6, d['ms_per_step']*1e3, d['e2e']['value']/1e6, d['n_gpus'], d['config']['envs_total'])"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 8 --workload c5 --rollout --steps 3 --warmup 3 2>&1 | tail -1 | tee gpurun_out/bench_n8_c5_rollout.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('c5 rollout x8', d['value']/1e6, d['ms_per_step']*1e3, d['config']['envs_per_gpu'])"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/pytest_gpu.log
+for i in 1 2; do python bench.py --steps 300 --warmup 10 --no-cpu-baseline | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('c2', d['value']/1e6, d['ms_per_step']*1e3, d['e2e']['value']/1e6)"; done

@@ -27,8 +27,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PACK_DIR = os.path.join(ROOT, 'paintrl_b200', 'data', 'partpacks')
 GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
 
-PART_NAMES = {0: 'door_test', 1: 'square'}
-MAX_POINTS = {0: 9148, 1: 14350}      # robot_gym_env.py:106-108
+PART_NAMES = {0: 'door_test', 1: 'square', 5: 'door_rr', 9: 'test'}
+MAX_POINTS = {0: 9148, 1: 14350, 5: 17000, 9: 9148}      # robot_gym_env.py:106-117 (the other parts carry 0: unusable)
 
 
 # ------------------------------------------------------------------------------ part packs
@@ -369,6 +369,18 @@ def g1_door_zigzag():
     ref, rec = _make({'Part_NO': 0, 'START_POINT_MODE': 'anchor'}, **kw)
     rec.run_episode(None, _zigzag_policy_simple({'up': True, 'h': 0}), 245)
     return _save('g1_door_zigzag', ref, rec, kw, 'C1: zigzag.py:77-104 policy on obs[-1]')
+
+
+@job
+def g10_door_rr_random():
+    """Part_NO 5 (door_rr, the third part with a usable max-points entry): RGB, anchor, random discrete-4."""
+    kw = dict(action_mode='discrete', action_shape=1, discrete_granularity=4, obs_mode='section',
+              obs_grad=4, rollout=False)
+    ref, rec = _make({'Part_NO': 5, 'START_POINT_MODE': 'anchor'}, **kw)
+    rng = np.random.default_rng(510)
+    for ep in range(3):
+        rec.run_episode(ep % len(ref.env._start_points), _random_discrete(rng, 4), 60)
+    return _save('g10_door_rr_random', ref, rec, kw, 'Part_NO 5, random discrete-4, 3 episodes of <= 60 steps')
 
 
 @job

@@ -30,6 +30,10 @@ CASES = {
                                Expected_Episode_Length=600),
                           dict(obs_mode='discrete', obs_grad=4, discrete_granularity=8), 64, 50),
     'sheet_simple': (dict(BASE, Part_NO=1, START_POINT_MODE='all'), dict(obs_mode='simple'), 64, 60),
+    # the other two parts of Part_Dict with a usable max-points entry (robot_gym_env.py:106-117)
+    'door_rr_hsi': (dict(BASE, Part_NO=5, COLOR_MODE='HSI', START_POINT_MODE='edge', OVERLAP_PENALTY=True), dict(), 64, 50),
+    'test_part_grid': (dict(BASE, Part_NO=9, START_POINT_MODE='all'),
+                       dict(action_mode='continuous', action_shape=2, obs_mode='grid', obs_grad=4), 64, 40),
 }
 
 

@@ -14,7 +14,7 @@ from test_gpu_oracle_batch import BASE, _run_case
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('part_no', [0, 1])
+@pytest.mark.parametrize('part_no', [0, 1, 5, 9])
 def test_rasteriser_reproduces_reference_packs(part_no, cuda_device):
     pack = PartPack.for_part(part_no)
     ij, pos = pack.rasterize(240, 240, device=0)

@@ -6,7 +6,7 @@ import pytest
 from paintrl_b200.partpack import PartPack
 
 
-@pytest.mark.parametrize('part_no', [0, 1])
+@pytest.mark.parametrize('part_no', [0, 1, 5, 9])
 def test_oracle_rasteriser_reproduces_reference_packs(part_no):
     from oracle.oracle import rasterize
     pack = PartPack.for_part(part_no)
