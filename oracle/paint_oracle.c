@@ -12,7 +12,7 @@
  * on top of the constant per-part tables of a PaintrlPartPack (include/paintrl.h) and the frozen
  * shim arithmetic of oracle/shims/pybullet.py (ray test, multiplyTransforms).  It is pinned by
  * tests/test_oracle_golden.py against traces minted from the reference's own Python sources
- * (oracle/make_golden.py -> tests/golden/*.npz).
+ * (oracle/make_golden.py -> tests/golden/g*.npz files).
  *
  * Everything is brute force on purpose (no bins, no ranks, no incremental counters): it shares
  * no acceleration structure with the CUDA engine.

@@ -1131,7 +1131,7 @@ int paintrl_step_host(PaintrlHandle h, const void *actions_host, double *obs_hos
     if (rc != PAINTRL_OK) return rc;
     // device -> host: segments that are adjacent on both sides travel as one copy
     struct Seg { void *dst; const void *src; size_t n; };
-    Seg segs[7];
+    Seg segs[7] = {};
     int ns = 0;
     auto push = [&](void *dst, const void *src, size_t n) {
         if (ns > 0 && (const char *)segs[ns - 1].src + segs[ns - 1].n == (const char *)src &&
