@@ -174,6 +174,7 @@ def run_reference(args, workload, rank, world_size):
     if rank != 0:
         return
     per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    per_step = float(os.environ.get('PAINTRL_BENCH_REFERENCE_SECONDS', per_step))     # tests shorten the sample
     for _ in range(min(args.warmup, 1)):
         cpu_baseline_sample(workload, seconds=0.5)
     samples = [cpu_baseline_sample(workload, seconds=per_step) for _ in range(max(1, min(args.steps, 5)))]

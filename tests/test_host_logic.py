@@ -124,3 +124,23 @@ def test_compose_texture_rebuilds_the_reference_texels(name, part_no, mode):
     stored = pack.arrays['texel_off']
     bare = PartPack(pack.meta, {k: v for k, v in pack.arrays.items() if k != 'texel_off'})
     assert np.array_equal(bare.texel_offsets(), stored)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
+    produced by the oracle port on the host cores; non-zero ranks print nothing."""
+    import json
+    env = dict(os.environ, PAINTRL_BENCH_REFERENCE_SECONDS='0.3')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'batched env steps/sec' and line['unit'] == 'env-steps/s'
+    assert line['value'] > 0 and line['higher_is_better'] is True and line['n_gpus'] == 1
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1 and line['cpu_baseline']['value'] == line['value']
+    assert line['e2e'] == {'value': line['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert line['config']['workload'].startswith('C2 door panel')
+    other = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300,
+                           env=dict(env, RANK='1', LOCAL_RANK='1', WORLD_SIZE='2'))
+    assert other.returncode == 0 and other.stdout.strip() == ''
