@@ -59,7 +59,7 @@ struct alignas(128) WarpScratch {
     int rowWa[kMaxRows], rowWn[kMaxRows];         // stamp candidates of the row: first word, word count
                                                   // (reused as the K != 4 section histogram)
     uint16_t cand[STAGED ? kStageWords : 2];      // flat list of the step's candidate words (STAGED only)
-    double hsi_r[8];                              // HSI: r = distances.max() of each shot (stamp)
+    double hsi_r[2 * kPaintPerAction];                         // HSI: r = distances.max() of each shot, then 1 / r^2 (stamp)
     unsigned long long bar;                       // mbarrier of the bulk copies
 };
 static_assert(2 * kMaxRows >= 2 * kMaxObs, "the section histogram aliases rowWa / rowWn");
@@ -615,9 +615,12 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BIT
         });
 #pragma unroll
         for (int s = 0; s < NS; ++s) rmax[s] = sqrt(warp_max(rmax[s]));   // sqrt is monotone
-        if (lane == 0) {
+        if (lane < NS) {                     // r and 1 / r^2 of shot `lane` (one division per lane)
+            double r = rmax[0];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) ws.hsi_r[s] = rmax[s];
+            for (int s = 1; s < NS; ++s) r = lane == s ? rmax[s] : r;
+            ws.hsi_r[lane] = r;
+            ws.hsi_r[NS + lane] = r > 0.0 ? 1.0 / (r * r) : 0.0;
         }
         __syncwarp();
     }
@@ -708,8 +711,19 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BIT
                 for (int s = 0; s < NS; ++s) {
                     if ((shots & (1u << s)) && sv > 0) {
                         const double dx = x - cen(ws, s, 0), dy = y - cen(ws, s, 1), dz = z - cen(ws, s, 2);
-                        const double ratio = sqrt(dx * dx + dy * dy + dz * dz) / ws.hsi_r[s];
-                        const int quantity = (int)(kHsiTargetMax * (1.0 - ratio * ratio)) + 1;   // :429
+                        const double d2 = dx * dx + dy * dy + dz * dz;
+                        // quantity = int(25 (1 - (d / r)^2)) + 1 (:429).  The reference's 25 (1 - ratio^2) (a square
+                        // root, a division, four roundings) and the screening value 25 (1 - d2 / r^2) differ by
+                        // < 1e-13, so when the latter is more than 1e-9 away from an integer both truncate to the same
+                        // one; otherwise -- and for the farthest texel, where it is 0 -- the reference's own
+                        // expression decides.
+                        const double qa = kHsiTargetMax * (1.0 - d2 * ws.hsi_r[NS + s]);
+                        const double qf = floor(qa);
+                        int quantity = (int)qf + 1;
+                        if (!(qa > 1e-9 && qa - qf > 1e-9 && (qf + 1.0) - qa > 1e-9)) {
+                            const double ratio = sqrt(d2) / ws.hsi_r[s];
+                            quantity = (int)(kHsiTargetMax * (1.0 - ratio * ratio)) + 1;
+                        }
                         sv -= quantity;
                         n_new += quantity;
                     }
