@@ -1103,8 +1103,11 @@ __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &c
     PAINTRL_TRACE_MARK(env, 5, lane == 0);
 }
 
+#ifndef PAINTRL_PAINT_OCC
+#define PAINTRL_PAINT_OCC 28
+#endif
 template <int COLOR, bool STAGED, bool AX12, int WPB>
-__global__ void __launch_bounds__(WPB * 32, (STAGED ? 28 : 16) / WPB)
+__global__ void __launch_bounds__(WPB * 32, (STAGED ? PAINTRL_PAINT_OCC : 16) / WPB)
 paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
     __shared__ WarpScratch<STAGED> scratch[WPB];
     const int warp = threadIdx.x >> 5;
