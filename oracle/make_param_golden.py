@@ -31,48 +31,23 @@ def load_reference():
     return importlib.import_module('param_test_env')
 
 
-def zigzag_actions(size, steps):
-    """The control loop of param_test_env.py:283-314 as an action generator keyed on the last observation."""
-    state = {'h': 0, 'up': True}
+def _from_generator(gen):
+    """Adapt an action generator of paintrl_b200.param_env (send the observation, receive the action) to the
+    `policy(obs, t)` shape used below."""
+    next(gen)
+    return lambda obs, t: gen.send(obs)
 
-    def policy(obs, t):
-        while True:
-            cur = round(size * obs[-1])
-            if state['up']:
-                if cur % size != size - 2:
-                    return 1
-                if state['h'] < 1:
-                    state['h'] += 1
-                    return 0
-                state['h'] = 0
-                state['up'] = False
-            else:
-                if cur % size != 1:
-                    return 3
-                if state['h'] < 1:
-                    state['h'] += 1
-                    return 0
-                state['h'] = 0
-                state['up'] = True
-    return policy
+
+def zigzag_actions(size, steps):
+    """The reference's own column sweep (param_test_env.py:283-314)."""
+    from paintrl_b200.param_env import zigzag_actions as gen
+    return _from_generator(gen(size))
 
 
 def spiral_actions(size):
-    """param_test_env.py:317-342."""
-    st = {'direction': 0, 'strait': size - 3, 'current': size - 3, 'use_len': 3}
-
-    def policy(obs, t):
-        st['current'] -= 1
-        a = st['direction'] % 4
-        if st['current'] == 0:
-            st['direction'] += 1
-            st['use_len'] -= 1
-            if st['use_len'] <= 0:
-                st['use_len'] = 2
-                st['strait'] -= 1
-            st['current'] = st['strait']
-        return a
-    return policy
+    """The reference's own inward spiral (param_test_env.py:317-342)."""
+    from paintrl_b200.param_env import spiral_actions as gen
+    return _from_generator(gen(size))
 
 
 def random_actions(seed, wall_bias):

@@ -107,29 +107,29 @@ class BatchedParamTestEnv(object):
 
 
 class Visualizer(object):
-    """param_test_env.py:252-280, without the terminal colours (termcolor is optional there too)."""
+    """Text dump of a size x size table (the role of param_test_env.py:252-280): interior cells whose value is in
+    `marks` get a leading `*` (the reference colours them red through termcolor)."""
 
     def __init__(self, size):
         self._size = size
-        self._template = '{0:3}' + ''.join('|{' + str(i) + ':3}' for i in range(1, size))
 
-    def _print_table(self, table, highlight_set=(1,)):
-        print(self._template.format(*[str(i) for i in range(self._size)]))
-        edge = (0, self._size - 1)
-        for i in range(self._size):
-            values = []
-            for j in range(self._size):
+    def _dump(self, title, table, marks):
+        n = self._size
+        print(title)
+        print('|'.join('%3s' % c for c in range(n)))
+        for i in range(n):
+            row = []
+            for j in range(n):
                 v = table[(i, j)]
-                values.append('*' + str(v) if v in highlight_set and i not in edge and j not in edge else v)
-            print(self._template.format(*values))
+                interior = 0 < i < n - 1 and 0 < j < n - 1
+                row.append('%3s' % (('*%s' % v) if interior and v in marks else v))
+            print('|'.join(row))
 
     def print_visit_table(self, table):
-        print('Visit Table: count of visit in each state')
-        self._print_table(table, highlight_set=[i for i in range(20) if i != 1])
+        self._dump('Visit Table: count of visit in each state', table, set(range(20)) - {1})
 
     def print_world_table(self, table):
-        print('World Table:')
-        self._print_table(table)
+        self._dump('World Table:', table, {1})
 
 
 class ParamTestEnv(_GymEnv):
@@ -209,58 +209,52 @@ class ParamTestEnv(_GymEnv):
         return seed
 
 
-def zigzag(grid_size=22, env=None):
-    """param_test_env.py:283-314: sweep the grid column by column; returns (steps, total return)."""
-    env = env or ParamTestEnv(grid_size, train_mode=False)
-    env.reset()
-    horizontal_move, up, terminated = 0, True, False
-    state = [0, 0]
-    total_return, step_counter = 0, 0
-    while not terminated:
-        current_pos = round(grid_size * state[-1])
-        if up:
-            if current_pos % grid_size != grid_size - 2:
-                state, step_reward, terminated, info = env.step(1)
-                step_counter += 1
-            elif horizontal_move < 1:
-                state, step_reward, terminated, info = env.step(0)
-                step_counter += 1
-                horizontal_move += 1
-            else:
-                horizontal_move, step_reward, up = 0, 0, False
+def zigzag_actions(grid_size):
+    """The column sweep of param_test_env.py:283-314 as a generator: send it the latest observation, receive the
+    next action (1 = +j until the last interior row, one step of 0 = +i, then 3 = -j back down, ...)."""
+    heading, obs = 1, (yield None)
+    while True:
+        row = round(grid_size * obs[-1]) % grid_size
+        at_end = row == (grid_size - 2 if heading == 1 else 1)
+        if at_end:
+            obs = yield 0                      # one column over, then turn around
+            heading = 3 if heading == 1 else 1
         else:
-            if current_pos % grid_size != 1:
-                state, step_reward, terminated, info = env.step(3)
-                step_counter += 1
-            elif horizontal_move < 1:
-                state, step_reward, terminated, info = env.step(0)
-                step_counter += 1
-                horizontal_move += 1
-            else:
-                horizontal_move, step_reward, up = 0, 0, True
-        total_return += step_reward
-    print('In {0} steps get {1} rewards'.format(step_counter, total_return))
-    return step_counter, total_return
+            obs = yield heading
+
+
+def spiral_actions(grid_size):
+    """The inward spiral of param_test_env.py:317-342 as a generator of actions (it ignores the observation):
+    three legs of grid_size - 3 steps, then legs shrinking by one every second turn."""
+    direction, leg, legs_left = 0, grid_size - 3, 3
+    yield None
+    while True:
+        for _ in range(leg):
+            yield direction % 4
+        direction += 1
+        legs_left -= 1
+        if legs_left <= 0:
+            legs_left, leg = 2, leg - 1
+
+
+def drive(env, actions):
+    """Run one episode of `env` under an action generator; returns (steps, total return)."""
+    obs = env.reset()
+    next(actions)
+    steps, total, done = 0, 0, False
+    while not done:
+        obs, reward, done, _ = env.step(actions.send(obs))
+        steps += 1
+        total += reward
+    print('In {0} steps get {1} rewards'.format(steps, total))
+    return steps, total
+
+
+def zigzag(grid_size=22, env=None):
+    """`zigzag()` of the reference module: sweep the grid column by column."""
+    return drive(env or ParamTestEnv(grid_size, train_mode=False), zigzag_actions(grid_size))
 
 
 def spiral(grid_size=22, env=None):
-    """param_test_env.py:317-342: spiral inwards; returns (steps, total return)."""
-    env = env or ParamTestEnv(grid_size, train_mode=False)
-    env.reset()
-    done, total_return, step_counter, direction = False, 0, 0, 0
-    strait_counter = grid_size - 3
-    current_counter, use_len = strait_counter, 3
-    while not done:
-        current_counter -= 1
-        obs, reward, done, info = env.step(direction % 4)
-        if current_counter == 0:
-            direction += 1
-            use_len -= 1
-            if use_len <= 0:
-                use_len = 2
-                strait_counter -= 1
-            current_counter = strait_counter
-        step_counter += 1
-        total_return += reward
-    print('In {0} steps get {1} rewards'.format(step_counter, total_return))
-    return step_counter, total_return
+    """`spiral()` of the reference module: spiral inwards."""
+    return drive(env or ParamTestEnv(grid_size, train_mode=False), spiral_actions(grid_size))
