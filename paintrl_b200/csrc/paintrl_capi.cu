@@ -89,7 +89,7 @@ struct PaintrlEngine {
     double move_cell_planes_mean = 0.0, move_cell_verts_mean = 0.0;
     int move_lanes = 32;             // lanes per environment in move_kernel (8, 16 or 32)
     int move_warps = 4, paint_warps = 1;   // warps per block of the two step kernels (1, 2 or 4)
-    int move_minb = 4;               // its __launch_bounds__ min blocks per SM (4: 128 registers ... 7: 72)
+    int move_minb = 4;               // its __launch_bounds__ min blocks per SM (4: 128 registers, 7: 72)
     bool force_unstaged = false;     // PAINTRL_FORCE_UNSTAGED: run the global-memory bit-plane path (tests)
 };
 
@@ -988,7 +988,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
         const char *co = getenv("PAINTRL_CARVEOUT");
         e->carveout_percent = co ? std::min(100, std::max(-1, atoi(co))) : -1;
         const char *mb = getenv("PAINTRL_MOVE_MINB");
-        e->move_minb = mb ? std::min(7, std::max(4, atoi(mb))) : 4;
+        e->move_minb = (mb && atoi(mb) >= 7) ? 7 : 4;     // 4: 128 registers, two waves at 4096 envs; 7: 72 registers (spills), one wave
     }
     *out = e;
     return PAINTRL_OK;
@@ -1059,10 +1059,6 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     } while (0)
         if (h->move_minb == 7) {
             if (L == 8) PAINTRL_MOVE(8, 7); else if (L == 16) PAINTRL_MOVE(16, 7); else PAINTRL_MOVE(32, 7);
-        } else if (h->move_minb == 6) {
-            if (L == 8) PAINTRL_MOVE(8, 6); else if (L == 16) PAINTRL_MOVE(16, 6); else PAINTRL_MOVE(32, 6);
-        } else if (h->move_minb == 5) {
-            if (L == 8) PAINTRL_MOVE(8, 5); else if (L == 16) PAINTRL_MOVE(16, 5); else PAINTRL_MOVE(32, 5);
         } else {
             if (L == 8) PAINTRL_MOVE(8, 4); else if (L == 16) PAINTRL_MOVE(16, 4); else PAINTRL_MOVE(32, 4);
         }
