@@ -1036,6 +1036,12 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     if (!h) return fail(PAINTRL_E_INVALID, "null handle");
     if (!actions_dev || !obs_dev || !reward_dev || !penalty_dev || !actual_dev || !done_dev)
         return fail(PAINTRL_E_INVALID, "null I/O buffer");
+    {   // the kernels store 8-byte (4-byte for new_texels / start indices) elements: refuse misaligned buffers
+        const uintptr_t a8 = (uintptr_t)actions_dev | (uintptr_t)obs_dev | (uintptr_t)reward_dev | (uintptr_t)penalty_dev |
+                             (uintptr_t)actual_dev | (uintptr_t)next_obs_dev;
+        const uintptr_t a4 = (uintptr_t)new_texels_dev | (uintptr_t)reset_start_idx_dev;
+        if ((a8 & 7u) || (a4 & 3u)) return fail(PAINTRL_E_INVALID, "misaligned I/O buffer (float64 / int64 buffers need 8-byte alignment)");
+    }
     CUDA_TRY(cudaSetDevice(h->device));
     StepIO io;
     io.actions = actions_dev; io.obs = obs_dev; io.reward = reward_dev; io.penalty = penalty_dev;

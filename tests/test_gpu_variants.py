@@ -108,3 +108,28 @@ def test_state_round_trip():
     assert torch.equal(a.get_state()['status'], b.get_state()['status'])
     a.close()
     b.close()
+
+
+def test_step_rejects_bad_buffers():
+    """paintrl_step refuses null and misaligned I/O buffers with PAINTRL_E_INVALID instead of launching."""
+    import ctypes
+    import torch
+    from paintrl_b200 import _capi
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    env = BatchedPaintEnv(8, dict(BASE), device=torch.device('cuda:0'))
+    env.reset(0)
+    lib = _capi.lib()
+    acts = torch.zeros(8, dtype=torch.int64, device='cuda:0')
+    raw = torch.zeros(8 * 6 * 8 + 16, dtype=torch.uint8, device='cuda:0')
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    good = [p(acts), p(env.obs), p(env.reward), p(env.penalty), p(env.actual), p(env.done), None, None, None, None]
+    assert lib.paintrl_step(env._h, *good) == 0
+    bad = list(good)
+    bad[1] = ctypes.c_void_p(raw.data_ptr() + 4)              # observation buffer off by 4 bytes
+    assert lib.paintrl_step(env._h, *bad) == -1               # PAINTRL_E_INVALID
+    assert b'misaligned' in lib.paintrl_last_error()
+    bad = list(good)
+    bad[2] = None
+    assert lib.paintrl_step(env._h, *bad) < 0 and b'null' in lib.paintrl_last_error()
+    torch.cuda.synchronize()
+    env.close()
