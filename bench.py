@@ -162,7 +162,7 @@ def cpu_baseline_sample(workload, seconds=12.0, threads=None):
         if dt >= seconds:
             break
     ora.close()
-    return {'value': steps / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+    return {'value': steps / dt, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'envs': n_env,
             'sample': '%d envs x %d steps of the same workload (C restatement oracle/paint_oracle.c, OpenMP, '
                       '%.1f s); the Python reference itself runs ~44 env-steps/s/core (BASELINE.md)'
                       % (n_env, steps // n_env, dt)}
@@ -385,7 +385,8 @@ def main():
             'scaling': workload['scaling'], 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload['name'], 'envs_per_gpu': n_env, 'envs_total': total_envs,
                        'n_front_texels': env.n_texels, 'status_bytes_per_texel': status_bytes,
-                       'obs_dim': env.obs_dim, 'l2': 'warm (no flush)' if flush is None else
+                       'obs_dim': env.obs_dim, 'state_bytes_per_gpu': env.state_bytes_per_env * n_env,
+                       'state_fits_l2': bool(env.state_bytes_per_env * n_env < 126e6), 'l2': 'warm (no flush)' if flush is None else
                        'flushed with a 512 MiB write between timed steps', 'timing': 'CUDA events per step, summed',
                        'parallelism': 'env-sharded x%d, no step-path collective' % world_size},
             'clocks': clocks,
@@ -402,6 +403,8 @@ def main():
         }
         if world_size == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_sample(workload)
+            one = cpu_baseline_sample(workload, seconds=3.0, threads=1)      # one core beside all cores
+            line['cpu_baseline']['single_core'] = {'value': one['value'], 'unit': UNIT, 'cores': 1, 'sample': one['sample']}
         print(json.dumps(line), flush=True)
     env.close()
     if world_size > 1:

@@ -133,6 +133,9 @@ int32_t paintrl_obs_dim(PaintrlHandle h);    /* observation_space.shape[0] (robo
 int32_t paintrl_action_dim(PaintrlHandle h); /* 1 (discrete, int64) or ACTION_SHAPE (float64) */
 int32_t paintrl_num_texels(PaintrlHandle h);
 int32_t paintrl_status_bytes(PaintrlHandle h); /* bytes per texel of the status plane: 1 RGB, 2 HSI */
+/* device bytes of per-environment state the step reads and writes: flip-bit plane (+ int16 thickness plane in HSI,
+ * + grid-cell counters in grid mode) + the 128-byte record, move output, counters and hand-off flag */
+int64_t paintrl_state_bytes_per_env(PaintrlHandle h);
 
 /* PaintGymEnv.reset (robot_gym_env.py:370-387) = Part.reset_part (bullet_paint_wrapper.py:706-712)
  * + Robot.reset (robot.py:366-372) + _augmented_observation.

@@ -87,6 +87,7 @@ SIGNATURES = {
     'paintrl_action_dim': (_I32, [_VP]),
     'paintrl_num_texels': (_I32, [_VP]),
     'paintrl_status_bytes': (_I32, [_VP]),
+    'paintrl_state_bytes_per_env': (ctypes.c_int64, [_VP]),
     'paintrl_reset': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _VP]),
     'paintrl_set_pose': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     'paintrl_step': (ctypes.c_int, [_VP] * 11),

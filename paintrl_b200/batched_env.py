@@ -55,6 +55,7 @@ class BatchedPaintEnv(object):
         self.obs_dim = int(self._lib.paintrl_obs_dim(self._h))
         self.action_dim = int(self._lib.paintrl_action_dim(self._h))
         self.n_texels = int(self._lib.paintrl_num_texels(self._h))
+        self.state_bytes_per_env = int(self._lib.paintrl_state_bytes_per_env(self._h))
         self.n_starts = self.pack.start_points(self.cfg.start_point_mode).shape[0]
         B, f64 = self.num_envs, torch.float64
         dev = self.device

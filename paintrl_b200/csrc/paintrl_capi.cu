@@ -1006,6 +1006,11 @@ int32_t paintrl_obs_dim(PaintrlHandle h) { return h ? h->cfg.obs_dim : 0; }
 int32_t paintrl_action_dim(PaintrlHandle h) { return h ? h->cfg.action_shape : 0; }
 int32_t paintrl_num_texels(PaintrlHandle h) { return h ? h->pk.n_texels : 0; }
 int32_t paintrl_status_bytes(PaintrlHandle h) { return h ? (h->color == 0 ? 1 : 2) : 0; }
+int64_t paintrl_state_bytes_per_env(PaintrlHandle h) {
+    if (!h) return 0;
+    return (int64_t)h->pk.n_words_pad * 4 + (h->color == 1 ? (int64_t)h->pk.n_slots * 2 : 0) + (int64_t)h->pk.n_gcells_pad * 4 +
+           (int64_t)(sizeof(EnvState) + sizeof(MoveOut) + sizeof(EnvStat) + sizeof(unsigned));
+}
 
 static int reset_like(PaintrlHandle h, const int32_t *env_ids, int32_t n, const int32_t *start_idx, const double *pos,
                       const double *normal, double *obs, void *stream, int mode) {
