@@ -1,6 +1,7 @@
 // paintrl_kernels.cuh -- the step kernels (one warp per environment).
 //
-// A step is two launches on the caller's stream:
+// A step is two launches on the caller's stream; the second is a programmatic dependent
+// launch whose warps wait for their own environment's move phase only (per-environment release / acquire flags):
 //   move_kernel   5 sub-steps of {ray vs hull, nearest vertex, closest triangle}    robot.py:302-329
 //   paint_kernel  stamp   5 ball queries, colour update, overlap bookkeeping
 //                                                     bullet_paint_wrapper.py:568-577, 352-434
@@ -885,9 +886,9 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
     move_body<G, AX12>(pk, cfg, ea, env, actions);
 }
 
-// Everything after the move: stamp, score, observe, auto-reset.  The environment's record, the
-// move kernel's output and (STAGED) its flip bits come in through one TMA bulk-copy group per warp
-// and the bits go back the same way.
+// Everything after the move: stamp, score, observe, auto-reset.  (STAGED) the environment's flip bits
+// come in through a TMA bulk copy issued before the warp waits for its environment's hand-off flag and go
+// back the same way; the record and the move kernel's output follow the flag with L2 loads.
 template <int COLOR, bool STAGED, bool AX12>
 __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &cfg, const EnvArrays &ea, int env, const StepIO &io,
                                            WarpScratch<STAGED> &ws) {
