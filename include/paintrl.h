@@ -16,7 +16,9 @@
  *     owns every I/O buffer (contiguous, 16-byte aligned) and the stream.
  *   - *_dev calls are asynchronous on the given stream and never synchronise; *_host calls copy
  *     host<->device inside the call and return after the stream has drained.
- *   - a handle is not thread-safe; different handles (one per GPU) are independent.
+ *   - a handle is not thread-safe; different handles (one per GPU) are independent.  All calls on one
+ *     handle must be issued on ONE stream (or on streams the caller orders): the two kernels of a step hand
+ *     over per environment through device flags.
  *   - there is NO CPU fallback: without a CUDA device paintrl_create fails with PAINTRL_E_CUDA.
  */
 #ifndef PAINTRL_H_
@@ -28,7 +30,8 @@
 extern "C" {
 #endif
 
-#define PAINTRL_ABI_VERSION 1
+#define PAINTRL_ABI_VERSION 2
+#define PAINTRL_STATE_SCALARS 12   /* doubles per environment in the `scalars` of paintrl_get_state / paintrl_set_state */
 
 enum {
     PAINTRL_OK = 0,
@@ -183,8 +186,14 @@ int paintrl_step_host(PaintrlHandle h, const void *actions_host, double *obs_hos
  * status_dev: int16[n, n_texels] first-channel value per front texel in part-pack order
  *             (== get_texture_image's R plane restricted to profile[front]);
  * pose_dev  : float64[n,3]; quat_dev: float64[n,4];
- * scalars_dev: float64[n,8] = total_reward, total_return, step_counter, terminate_counter,
- *             last_on_part, terminate, last_turning_angle, angle_diff.  Any pointer may be NULL. */
+ * scalars_dev: float64[n, PAINTRL_STATE_SCALARS] = total_reward, total_return, step_counter, terminate_counter,
+ *             last_on_part, terminate, last_turning_angle, angle_diff, has_overlap_reference,
+ *             overlap_reference_centre[3].  The last four carry Part._last_painted_pixels
+ *             (bullet_paint_wrapper.py:483, 575-576) exactly: that set is the ball query of the previous shot's
+ *             centre, so a state saved mid-episode and restored into another handle continues bit for bit,
+ *             OVERLAP_PENALTY included.  paintrl_set_state with a status plane but without scalars clears the
+ *             reference (as reset_part does, :708).  Any pointer may be NULL.
+ * env_ids must be in [0, num_envs) and unique; ids out of range are ignored by the device code. */
 int paintrl_get_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, int16_t *status_dev,
                       double *pose_dev, double *quat_dev, double *scalars_dev, void *stream);
 int paintrl_set_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n,
@@ -240,11 +249,13 @@ void paintrl_param_destroy(PaintrlParamHandle h);
 int32_t paintrl_param_obs_dim(PaintrlParamHandle h);
 /* ParamTestEnv.reset (:150-160); env_ids_dev NULL = all; obs_dev float64[n, obs_dim] or NULL */
 int paintrl_param_reset(PaintrlParamHandle h, const int32_t *env_ids_dev, int32_t n, double *obs_dev, void *stream);
-/* ParamTestEnv.step (:218-240): actions int64[num_envs] in 0..3 (anything else raises the bad-action flag of
- * paintrl_param_stats and leaves that world untouched; the reference raises IndexError) */
+/* ParamTestEnv.step (:218-240): actions int64[num_envs] in 0..3.  The reference raises IndexError for anything else
+ * (:173-174); here such a world is left untouched, its output row is written as (current observation, reward 0,
+ * penalty 0, done 1) and the bad-action flag of paintrl_param_stats is raised (reported once, then cleared) --
+ * the host mirror checks the actions before the launch and raises IndexError like the reference. */
 int paintrl_param_step(PaintrlParamHandle h, const int64_t *actions_dev, double *obs_dev, double *reward_dev,
                        double *penalty_dev, double *actual_dev, uint8_t *done_dev, double *next_obs_dev, void *stream);
-/* world / visit_table (:113-131) of the listed worlds as int32[n, size*size] (visit counts saturate at 255) */
+/* world / visit_table (:113-131) of the listed worlds as int32[n, size*size] (visit counts saturate at 65535) */
 int paintrl_param_tables(PaintrlParamHandle h, const int32_t *env_ids_dev, int32_t n, int32_t *world_dev,
                          int32_t *visit_dev, void *stream);
 int paintrl_param_stats(PaintrlParamHandle h, uint64_t *env_steps, uint64_t *episodes_ended,

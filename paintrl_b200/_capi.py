@@ -7,7 +7,8 @@ missing, and `paintrl_create` fails if there is no CUDA device.
 import ctypes
 import os
 
-PAINTRL_ABI_VERSION = 1
+PAINTRL_ABI_VERSION = 2
+PAINTRL_STATE_SCALARS = 12
 
 LIB_NAME = 'libpaintrl_b200.so'
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)

@@ -89,10 +89,34 @@ class BatchedPaintEnv(object):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _ids(self, env_ids):
+        """Device list of environment indices for the by-index entry points, validated on the host: in range and
+        unique (the kernels index states / planes with them; a duplicate would race, an out-of-range id corrupt
+        another environment -- the device code also ignores ids out of range).  Host-side lists cost nothing to
+        check; a CUDA tensor is checked with one small reduction."""
         if env_ids is None:
             return None, self.num_envs
-        ids = torch.as_tensor(env_ids, dtype=torch.int32, device=self.device).contiguous()
-        return ids, int(ids.numel())
+        if isinstance(env_ids, torch.Tensor) and env_ids.is_cuda:
+            ids = env_ids.to(device=self.device, dtype=torch.int32).reshape(-1).contiguous()
+            n = int(ids.numel())
+            if n == 0:
+                raise ValueError('env_ids is empty')
+            lo, hi = int(ids.min()), int(ids.max())
+            unique = n == 1 or int(torch.unique(ids).numel()) == n
+        else:
+            host = np.asarray(env_ids.cpu() if isinstance(env_ids, torch.Tensor) else env_ids).reshape(-1)
+            n = int(host.size)
+            if n == 0:
+                raise ValueError('env_ids is empty')
+            if host.dtype.kind not in 'iu':
+                raise ValueError('env_ids must be integers')
+            lo, hi = int(host.min()), int(host.max())
+            unique = n == 1 or np.unique(host).size == n
+            ids = torch.as_tensor(host.astype(np.int32), device=self.device).contiguous()
+        if lo < 0 or hi >= self.num_envs:
+            raise IndexError('env_ids out of range [0, %d): min %d, max %d' % (self.num_envs, lo, hi))
+        if not unique:
+            raise ValueError('env_ids must be unique')
+        return ids, n
 
     # ------------------------------------------------------------------ reference call mirror
     def reset(self, start_index=None, env_ids=None):
@@ -137,6 +161,8 @@ class BatchedPaintEnv(object):
         rs = None
         if reset_start_index is not None:
             rs = torch.as_tensor(reset_start_index, dtype=torch.int32, device=self.device).contiguous()
+            if rs.numel() != self.num_envs:
+                raise ValueError('reset_start_index must have one entry per environment (%d), got %d' % (self.num_envs, rs.numel()))
         _capi.check(self._lib.paintrl_step(
             self._h, _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.penalty), _ptr(self.actual),
             _ptr(self.done), _ptr(self.new_texels), _ptr(self.next_obs) if self.cfg.auto_reset else None,
@@ -213,16 +239,20 @@ class BatchedPaintEnv(object):
         st = torch.zeros(n, self.n_texels, dtype=torch.int16, device=dev) if status else None
         pose = torch.zeros(n, 3, dtype=torch.float64, device=dev)
         quat = torch.zeros(n, 4, dtype=torch.float64, device=dev)
-        scal = torch.zeros(n, 8, dtype=torch.float64, device=dev)
+        scal = torch.zeros(n, _capi.PAINTRL_STATE_SCALARS, dtype=torch.float64, device=dev)
         _capi.check(self._lib.paintrl_get_state(self._h, _ptr(ids), n, _ptr(st), _ptr(pose), _ptr(quat),
                                                 _ptr(scal), self._stream()))
         keys = ('total_reward', 'total_return', 'step_counter', 'term_counter', 'last_on_part',
-                'terminate', 'last_angle', 'angle_diff')
+                'terminate', 'last_angle', 'angle_diff', 'has_overlap_reference')
         out = {'status': st, 'pose': pose, 'quat': quat, 'scalars': scal}
         out.update({k: scal[:, i] for i, k in enumerate(keys)})
+        out['overlap_reference_centre'] = scal[:, 9:12]
         return out
 
     def set_state(self, env_ids=None, status=None, pose=None, quat=None, scalars=None):
+        """Import per-environment state (the tensors `get_state` returns).  `scalars` [n, 12] carries the overlap
+        reference (Part._last_painted_pixels as the last shot's centre), so a mid-episode checkpoint restored
+        into another engine continues bit for bit; a status plane without scalars clears that reference."""
         ids, n = self._ids(env_ids)
 
         def prep(t, dtype, shape):
@@ -235,7 +265,7 @@ class BatchedPaintEnv(object):
         st = prep(status, torch.int16, (n, self.n_texels))
         po = prep(pose, torch.float64, (n, 3))
         qu = prep(quat, torch.float64, (n, 4))
-        sc = prep(scalars, torch.float64, (n, 8))
+        sc = prep(scalars, torch.float64, (n, _capi.PAINTRL_STATE_SCALARS))
         _capi.check(self._lib.paintrl_set_state(self._h, _ptr(ids), n, _ptr(st), _ptr(po), _ptr(qu), _ptr(sc),
                                                 self._stream()))
 

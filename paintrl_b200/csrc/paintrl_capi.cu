@@ -74,7 +74,8 @@ struct PaintrlEngine {
     int16_t *thick = nullptr;        // [num_envs][n_slots] HSI thickness plane (HSI only)
     unsigned *grid_cnt = nullptr;    // [num_envs][n_gcells_pad] (grid observation only)
     unsigned long long *stats = nullptr;
-    unsigned *ready = nullptr;       // [num_envs] per-environment move -> paint hand-off flags (step sequence numbers)
+    unsigned *ready = nullptr;       // [num_envs] per-environment move -> paint hand-off flags: 1 = this step's move output is published;
+                                     // the paint warp clears it.  All steps of one handle must be issued on ONE stream (or ordered streams).
     // PAINTRL_CARVEOUT=<percent>: ask for the same L1 / shared-memory split for both step kernels, so that paint CTAs can
     // share an SM with the move kernel's last wave (CTAs of kernels with different carveouts cannot).  Off by default:
     // measured slower at C2 (the move phase loses L1 and issue slots to the co-resident paint warps).
@@ -688,7 +689,7 @@ int paintrl_param_create(const PaintrlParamConfig *cfg, int32_t num_envs, int32_
     w.auto_reset = cfg->auto_reset ? 1 : 0;
     w.init_reward_counter = (cfg->size - 2) * (cfg->size - 2);
     const size_t cells = (size_t)cfg->size * cfg->size * num_envs;
-    bool ok = e->arena.alloc((void **)&w.world, cells) == cudaSuccess && e->arena.alloc((void **)&w.visit, cells) == cudaSuccess &&
+    bool ok = e->arena.alloc((void **)&w.world, cells) == cudaSuccess && e->arena.alloc((void **)&w.visit, cells * sizeof(uint16_t)) == cudaSuccess &&
               e->arena.alloc((void **)&w.pos_i, sizeof(int) * num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&w.pos_j, sizeof(int) * num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&w.reward_counter, sizeof(int) * num_envs) == cudaSuccess &&
@@ -697,10 +698,11 @@ int paintrl_param_create(const PaintrlParamConfig *cfg, int32_t num_envs, int32_
               e->arena.alloc((void **)&w.stats, 2 * sizeof(unsigned long long)) == cudaSuccess &&
               e->arena.alloc((void **)&e->bad_action, sizeof(int)) == cudaSuccess;
     if (!ok) { delete e; return fail(PAINTRL_E_CUDA, "device allocation failed (grid world)"); }
-    cudaMemset(w.stats, 0, 2 * sizeof(unsigned long long));
-    cudaMemset(e->bad_action, 0, sizeof(int));
+    cudaError_t err = cudaMemset(w.stats, 0, 2 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemset(e->bad_action, 0, sizeof(int));
+    if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, cudaGetErrorString(err)); }
     param_reset_kernel<<<(num_envs + 127) / 128, 128>>>(w, nullptr, num_envs, nullptr);
-    cudaError_t err = cudaGetLastError();
+    err = cudaGetLastError();
     if (err == cudaSuccess) err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, cudaGetErrorString(err)); }
     *out = e;
@@ -760,6 +762,7 @@ int paintrl_param_stats(PaintrlParamHandle h, uint64_t *env_steps, uint64_t *epi
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(host, h->w.stats, sizeof(host), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(&bad, h->bad_action, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) CUDA_TRY(cudaMemset(h->bad_action, 0, sizeof(int)));      /* reported once, then cleared */
     if (env_steps) *env_steps = host[0];
     if (episodes_ended) *episodes_ended = host[1];
     if (kernel_launches) *kernel_launches = h->launches;
@@ -958,15 +961,18 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
               e->arena.alloc(&e->stage_actions, adim * num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&e->stage_out, (sizeof(double) * (2 * od + 3) + 1) * (size_t)num_envs) == cudaSuccess;
     if (!ok) { delete e; return fail(PAINTRL_E_CUDA, "device allocation failed (state / status planes)"); }
-    cudaMemset(e->states, 0, sizeof(EnvState) * (size_t)num_envs);
-    cudaMemset(e->moves, 0xff, sizeof(MoveOut) * (size_t)num_envs);   // miss_cache = none
-    cudaMemset(e->env_stats, 0, sizeof(EnvStat) * (size_t)num_envs);
-    cudaMemset(e->bits, 0, bits_bytes);
-    if (e->thick)   // the initial colour everywhere; resets only rewrite what an episode touched (clear_planes)
+    err = cudaMemset(e->states, 0, sizeof(EnvState) * (size_t)num_envs);
+    if (err == cudaSuccess) err = cudaMemset(e->moves, 0xff, sizeof(MoveOut) * (size_t)num_envs);   // miss_cache = none
+    if (err == cudaSuccess) err = cudaMemset(e->env_stats, 0, sizeof(EnvStat) * (size_t)num_envs);
+    if (err == cudaSuccess) err = cudaMemset(e->bits, 0, bits_bytes);
+    if (err == cudaSuccess && e->thick) {   // the initial colour everywhere; resets only rewrite what an episode touched (clear_planes)
         fill_thickness_kernel<<<1184, 256>>>(e->thick, thick_bytes / sizeof(int16_t), (int16_t)e->pk.status_init);
-    if (e->grid_cnt) cudaMemset(e->grid_cnt, 0, gcnt_bytes);
-    cudaMemset(e->stats, 0, 4 * sizeof(unsigned long long));
-    cudaMemset(e->ready, 0, sizeof(unsigned) * (size_t)num_envs);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess && e->grid_cnt) err = cudaMemset(e->grid_cnt, 0, gcnt_bytes);
+    if (err == cudaSuccess) err = cudaMemset(e->stats, 0, 4 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemset(e->ready, 0, sizeof(unsigned) * (size_t)num_envs);
+    if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, std::string("initialising device state: ") + cudaGetErrorString(err)); }
     // observation of a fresh environment at every start point, from environment 0's all-zero planes
     e->pk.reset_obs = reset_obs;
     reset_obs_kernel<<<(e->pk.n_starts + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32>>>(
@@ -1019,7 +1025,7 @@ static int reset_like(PaintrlHandle h, const int32_t *env_ids, int32_t n, const 
     if (!env_ids && n != h->num_envs) return fail(PAINTRL_E_INVALID, "env_ids == NULL requires n == num_envs");
     CUDA_TRY(cudaSetDevice(h->device));
     const int blocks = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    reset_kernel<<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), env_ids, n, start_idx,
+    reset_kernel<<<blocks, kWarpsPerBlock * 32, 0, as_stream(stream)>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, env_ids, n, start_idx,
                                                                          pos, normal, obs, mode);
     return launch_check(h, "reset_kernel");
 }
@@ -1090,14 +1096,15 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     lattr[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = lattr; lc.numAttrs = 1;
     const EnvArrays pea = env_arrays(h);
+    cudaError_t perr = cudaSuccess;
 #define PAINTRL_PAINT_W(C, ST, W)                                                                           \
     do {                                                                                                    \
         if (!h->carveout_set && h->carveout_percent >= 0) {                                                 \
             cudaFuncSetAttribute(paint_kernel<C, ST, true, W>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout_percent);  \
             cudaFuncSetAttribute(paint_kernel<C, ST, false, W>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout_percent); \
         }                                                                                                   \
-        if (ax12) cudaLaunchKernelEx(&lc, paint_kernel<C, ST, true, W>, h->pk, h->cfg, pea, h->num_envs, io);  \
-        else cudaLaunchKernelEx(&lc, paint_kernel<C, ST, false, W>, h->pk, h->cfg, pea, h->num_envs, io);      \
+        if (ax12) perr = cudaLaunchKernelEx(&lc, paint_kernel<C, ST, true, W>, h->pk, h->cfg, pea, h->num_envs, io);  \
+        else perr = cudaLaunchKernelEx(&lc, paint_kernel<C, ST, false, W>, h->pk, h->cfg, pea, h->num_envs, io);      \
     } while (0)
 #define PAINTRL_PAINT(C, ST)                                                                 \
     do {                                                                                     \
@@ -1112,7 +1119,16 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
 #undef PAINTRL_PAINT
 #undef PAINTRL_PAINT_W
     h->carveout_set = true;
-    return launch_check(h, "paint_kernel");
+    if (perr == cudaSuccess) perr = cudaGetLastError();
+    if (perr != cudaSuccess) {
+        // the move grid is already in flight and will raise the hand-off flags nobody consumes: clear them behind it,
+        // or the next step's paint warps would pass their acquire on stale move outputs
+        cudaGetLastError();
+        cudaMemsetAsync(h->ready, 0, sizeof(unsigned) * (size_t)h->num_envs, s);
+        return fail(PAINTRL_E_CUDA, std::string("paint_kernel: ") + cudaGetErrorString(perr));
+    }
+    h->launches++;
+    return PAINTRL_OK;
 }
 
 int paintrl_step_host(PaintrlHandle h, const void *actions_host, double *obs_host, double *reward_host,
@@ -1166,7 +1182,7 @@ int paintrl_get_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, in
     if (n <= 0 || n > h->num_envs || (!env_ids_dev && n != h->num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
     CUDA_TRY(cudaSetDevice(h->device));
     dim3 grid(std::max(1, std::min(64, (h->pk.n_texels + 255) / 256)), n);
-    get_state_kernel<<<grid, 256, 0, as_stream(stream)>>>(h->pk, env_arrays(h), env_ids_dev, n, status_dev, pose_dev, quat_dev,
+    get_state_kernel<<<grid, 256, 0, as_stream(stream)>>>(h->pk, env_arrays(h), h->num_envs, env_ids_dev, n, status_dev, pose_dev, quat_dev,
                                                           scalars_dev);
     return launch_check(h, "get_state_kernel");
 }
@@ -1176,11 +1192,11 @@ int paintrl_set_state(PaintrlHandle h, const int32_t *env_ids_dev, int32_t n, co
     if (!h) return fail(PAINTRL_E_INVALID, "null handle");
     if (n <= 0 || n > h->num_envs || (!env_ids_dev && n != h->num_envs)) return fail(PAINTRL_E_INVALID, "bad env count");
     CUDA_TRY(cudaSetDevice(h->device));
-    set_scalars_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(env_arrays(h), env_ids_dev, n, pose_dev, quat_dev,
+    set_scalars_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(env_arrays(h), h->num_envs, env_ids_dev, n, pose_dev, quat_dev,
                                                                         scalars_dev, status_dev ? 1 : 0);
     int rc = launch_check(h, "set_scalars_kernel");
     if (rc != PAINTRL_OK || !status_dev) return rc;
-    set_status_kernel<<<(n + 3) / 4, 128, 0, as_stream(stream)>>>(h->pk, env_arrays(h), env_ids_dev, n, status_dev);
+    set_status_kernel<<<(n + 3) / 4, 128, 0, as_stream(stream)>>>(h->pk, env_arrays(h), h->num_envs, env_ids_dev, n, status_dev);
     return launch_check(h, "set_status_kernel");
 }
 

@@ -68,6 +68,7 @@ constexpr double kHookDistance = 0.1;         // bullet_paint_wrapper.py:443
 constexpr int kHsiTargetMax = 25;             // bullet_paint_wrapper.py:388
 constexpr int kPainted = 255;                 // bullet_paint_wrapper.py:354, 496
 constexpr double kPi = 3.141592653589793;     // math.pi / np.pi
+constexpr int kStateScalars = 12;             // doubles per environment in paintrl_get_state / set_state `scalars` (ABI v2)
 constexpr int kMaxObs = 128;                  // largest observation vector (OBS_GRAD^2 or OBS_GRAD+2)
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxRows = 128;                // rows of the texel layout

@@ -1119,7 +1119,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
 
 // PaintGymEnv.reset / Robot.reset(pose) for the listed environments, with their first observation.
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, const int32_t *env_ids, int n, const int32_t *start_idx,
+reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const int32_t *env_ids, int n, const int32_t *start_idx,
              const double *set_pos, const double *set_normal, double *obs_out, int mode /*0 reset, 1 set_pose*/) {
     const Ax ax = make_ax<false>(pk.axis0, pk.axis1);
     __shared__ WarpScratch<false> scratch[kWarpsPerBlock];
@@ -1127,8 +1127,10 @@ reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, const int32_t *env_ids, in
     const int k = blockIdx.x * kWarpsPerBlock + warp;
     if (k >= n) return;
     const int env = env_ids ? env_ids[k] : k;
+    if ((unsigned)env >= (unsigned)num_envs) return;      // the host validates the list; never index out of bounds
     unsigned *gbits = bits_of(pk, ea, env), *grid_cnt = grid_cnt_of(pk, ea, env);
     int16_t *thick = thick_of(pk, ea, env);
+    if (lane == 0) ea.ready[env] = 0u;                    // a hand-off flag left behind by a failed step launch
     EnvState st;
     load_state(&ea.states[env], st);
     if (mode == 0) {
@@ -1164,10 +1166,11 @@ reset_obs_kernel(DevPack pk, DevConfig cfg, unsigned *zero_bits, const unsigned 
 }
 
 // ------------------------------------------------------------------------------ state access
-__global__ void get_state_kernel(DevPack pk, EnvArrays ea, const int32_t *env_ids, int n, int16_t *status_out,
+__global__ void get_state_kernel(DevPack pk, EnvArrays ea, int num_envs, const int32_t *env_ids, int n, int16_t *status_out,
                                  double *pose_out, double *quat_out, double *scalars_out) {
     const int k = blockIdx.y;
     const int env = env_ids ? env_ids[k] : k;
+    if ((unsigned)env >= (unsigned)num_envs) return;
     if (status_out) {
         const unsigned *bits = bits_of(pk, ea, env);
         const int16_t *thick = thick_of(pk, ea, env);
@@ -1184,45 +1187,55 @@ __global__ void get_state_kernel(DevPack pk, EnvArrays ea, const int32_t *env_id
         if (pose_out) for (int i = 0; i < 3; ++i) pose_out[3 * k + i] = st.pose[i];
         if (quat_out) for (int i = 0; i < 4; ++i) quat_out[4 * k + i] = st.quat[i];
         if (scalars_out) {
-            double *o = scalars_out + 8 * (size_t)k;
+            double *o = scalars_out + kStateScalars * (size_t)k;
             o[0] = st.total_reward; o[1] = st.total_return; o[2] = st.step_counter; o[3] = st.term_counter;
             o[4] = (st.flags & kFlagLastOnPart) ? 1.0 : 0.0; o[5] = (st.flags & kFlagTerminate) ? 1.0 : 0.0;
             o[6] = st.last_angle; o[7] = st.angle_diff;
+            // the overlap reference Part._last_painted_pixels (bullet_paint_wrapper.py:483, 575-576): the set is the
+            // ball query of the last shot's centre, so the centre (and whether there is one) carries it exactly
+            o[8] = (st.flags & kFlagHasLast) ? 1.0 : 0.0;
+            o[9] = st.last_center[0]; o[10] = st.last_center[1]; o[11] = st.last_center[2];
         }
     }
 }
 
 // Scalars / pose of set_state (one thread per listed environment).
-__global__ void set_scalars_kernel(EnvArrays ea, const int32_t *env_ids, int n, const double *pose_in, const double *quat_in,
+__global__ void set_scalars_kernel(EnvArrays ea, int num_envs, const int32_t *env_ids, int n, const double *pose_in, const double *quat_in,
                                    const double *scalars_in, int status_given) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int env = env_ids ? env_ids[k] : k;
+    if ((unsigned)env >= (unsigned)num_envs) return;
+    ea.ready[env] = 0u;
     EnvState &st = ea.states[env];
     if (pose_in) for (int i = 0; i < 3; ++i) st.pose[i] = pose_in[3 * k + i];
     if (quat_in) for (int i = 0; i < 4; ++i) st.quat[i] = quat_in[4 * k + i];
     if (scalars_in) {
-        const double *o = scalars_in + 8 * (size_t)k;
+        const double *o = scalars_in + kStateScalars * (size_t)k;
         st.total_reward = o[0]; st.total_return = o[1]; st.step_counter = (int)o[2]; st.term_counter = (int)o[3];
-        int f = st.flags & kFlagHasLast;
+        int f = 0;
         if (o[4] != 0.0) f |= kFlagLastOnPart;
         if (o[5] != 0.0) f |= kFlagTerminate;
+        if (o[8] != 0.0) f |= kFlagHasLast;               // the overlap reference travels with the scalars (ABI v2)
         st.flags = f;
         st.last_angle = o[6]; st.angle_diff = o[7];
+        st.last_center[0] = o[9]; st.last_center[1] = o[10]; st.last_center[2] = o[11];
+    } else if (status_given) {
+        // a status plane without scalars: no overlap reference came with it -- clear it, as reset_part does
+        // (bullet_paint_wrapper.py:708)
+        st.flags &= ~kFlagHasLast;
     }
-    // the overlap reference set cannot be expressed through this interface: clear it, as
-    // reset_part does (bullet_paint_wrapper.py:708)
-    if (status_given) st.flags &= ~kFlagHasLast;
 }
 
 // Status planes of set_state: one warp per listed environment rebuilds the flip bits, the
 // thickness plane (HSI) and the grid-cell counters.  In RGB mode a texel is painted (255) or not:
 // any other value reads back as the fresh colour.
-__global__ void set_status_kernel(DevPack pk, EnvArrays ea, const int32_t *env_ids, int n, const int16_t *status_in) {
+__global__ void set_status_kernel(DevPack pk, EnvArrays ea, int num_envs, const int32_t *env_ids, int n, const int16_t *status_in) {
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (k >= n) return;
     const int env = env_ids ? env_ids[k] : k;
+    if ((unsigned)env >= (unsigned)num_envs) return;
     unsigned *bits = bits_of(pk, ea, env), *grid_cnt = grid_cnt_of(pk, ea, env);
     int16_t *thick = thick_of(pk, ea, env);
     if (grid_cnt) for (int w = lane; w < pk.n_gcells_pad; w += 32) grid_cnt[w] = 0;

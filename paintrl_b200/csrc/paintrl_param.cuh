@@ -18,7 +18,7 @@ struct ParamWorld {
     int num_envs, size, episode_max_length, repeat_termination, obs_mode, obs_dim, auto_reset;
     int init_reward_counter;
     uint8_t *world;        // [size * size][num_envs]  world[(i, j)]  (param_test_env.py:122-130)
-    uint8_t *visit;        // [size * size][num_envs]  visit_table[(i, j)], saturating at 255
+    uint16_t *visit;       // [size * size][num_envs]  visit_table[(i, j)] (saturates at 65535: beyond any EPISODE_MAX_LENGTH in use)
     int *pos_i, *pos_j;    // [num_envs]
     int *reward_counter, *step_counter;
     uint8_t *flags;        // [num_envs] bit 0 violated_wall, bit 1 repeat_visit
@@ -83,18 +83,27 @@ __global__ void param_reset_kernel(ParamWorld w, const int32_t *env_ids, int n, 
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const int e = env_ids ? env_ids[k] : k;
+    if ((unsigned)e >= (unsigned)w.num_envs) return;
     param_reset_env(w, e);
     if (obs_out) param_observation(w, e, obs_out + (size_t)k * w.obs_dim);
 }
 
-// ParamTestEnv.step (param_test_env.py:218-240) for every environment.  *bad_action is raised for an action
-// outside 0..3 (the reference raises IndexError; the environment is left untouched).
+// ParamTestEnv.step (param_test_env.py:218-240) for every environment.  An action outside 0..3 (the reference raises
+// IndexError, :173-174) raises *bad_action and leaves that world untouched, but its output row is still written
+// -- current observation, zero reward / penalty, done = 1 -- so that a caller who skips the check never trains
+// on the previous step's stale transition.  The host mirror checks the actions (or the flag) and raises.
 __global__ void param_step_kernel(ParamWorld w, const long long *actions, double *obs, double *reward_out, double *penalty_out,
                                   double *actual_out, uint8_t *done_out, double *next_obs, int *bad_action) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= w.num_envs) return;
     const long long a = actions[e];
-    if (a < 0 || a > 3) { atomicExch(bad_action, 1); return; }
+    if (a < 0 || a > 3) {
+        atomicExch(bad_action, 1);
+        param_observation(w, e, obs + (size_t)e * w.obs_dim);
+        if (next_obs) param_observation(w, e, next_obs + (size_t)e * w.obs_dim);
+        reward_out[e] = 0.0; penalty_out[e] = 0.0; actual_out[e] = 0.0; done_out[e] = 1;
+        return;
+    }
     const int s = w.size;
     int i = w.pos_i[e], j = w.pos_j[e], rc = w.reward_counter[e];
     int flags = w.flags[e];
@@ -106,8 +115,8 @@ __global__ void param_step_kernel(ParamWorld w, const long long *actions, double
         j = min(max(j, 0), s - 1);
         flags |= 1;
     } else {
-        uint8_t *v = &w.visit[(size_t)(i * s + j) * w.num_envs + e];
-        if (*v < 255) *v += 1;
+        uint16_t *v = &w.visit[(size_t)(i * s + j) * w.num_envs + e];
+        if (*v < 65535) *v += 1;
         if (*v > 1) flags |= 2;
     }
     int reward = (flags & 1) ? 0 : param_immediate(w, e, i, j, rc);                // :213-216
@@ -134,6 +143,7 @@ __global__ void param_tables_kernel(ParamWorld w, const int32_t *env_ids, int n,
     const int k = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n || c >= w.size * w.size) return;
     const int e = env_ids ? env_ids[k] : k;
+    if ((unsigned)e >= (unsigned)w.num_envs) return;
     if (world_out) world_out[(size_t)k * w.size * w.size + c] = w.world[(size_t)c * w.num_envs + e];
     if (visit_out) visit_out[(size_t)k * w.size * w.size + c] = w.visit[(size_t)c * w.num_envs + e];
 }

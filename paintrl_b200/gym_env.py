@@ -319,8 +319,10 @@ class PaintVectorEnv(object):
 
     def vector_step(self, actions):
         obs, actual, done, reward, penalty = self.step_arrays(actions)
-        infos = [{'reward': float(reward[i]), 'penalty': float(penalty[i])} for i in range(self.num_envs)]
-        return [obs[i] for i in range(self.num_envs)], actual.tolist(), [bool(d) for d in done], infos
+        # the VectorEnv contract wants Python lists; build them with bulk conversions (tolist / row views), not one
+        # NumPy scalar access per environment -- at thousands of environments that loop, not the engine, set the pace
+        infos = [{'reward': r, 'penalty': p} for r, p in zip(reward.tolist(), penalty.tolist())]
+        return list(obs), actual.tolist(), done.tolist(), infos
 
     def get_unwrapped(self):
         return []

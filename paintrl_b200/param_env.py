@@ -66,9 +66,17 @@ class BatchedParamTestEnv(object):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _ids(self, env_ids):
+        """Validated device list of world indices (in range, unique), like BatchedPaintEnv._ids."""
         if env_ids is None:
             return None, self.num_envs
-        ids = torch.as_tensor(env_ids, dtype=torch.int32, device=self.device).contiguous()
+        host = np.asarray(env_ids.cpu() if isinstance(env_ids, torch.Tensor) else env_ids).reshape(-1)
+        if host.size == 0 or host.dtype.kind not in 'iu':
+            raise ValueError('env_ids must be a non-empty list of integers')
+        if int(host.min()) < 0 or int(host.max()) >= self.num_envs:
+            raise IndexError('env_ids out of range [0, %d)' % self.num_envs)
+        if np.unique(host).size != host.size:
+            raise ValueError('env_ids must be unique')
+        ids = torch.as_tensor(host.astype(np.int32), device=self.device).contiguous()
         return ids, int(ids.numel())
 
     def reset(self, env_ids=None):
@@ -80,11 +88,20 @@ class BatchedParamTestEnv(object):
             self.next_obs.copy_(out)
         return out
 
-    def step(self, actions):
-        """ParamTestEnv.step for every world (param_test_env.py:218-240): (obs, actual_reward, done, info)."""
+    def step(self, actions, check_actions=True):
+        """ParamTestEnv.step for every world (param_test_env.py:218-240): (obs, actual_reward, done, info).
+        An action outside 0..3 raises IndexError BEFORE anything is stepped, like the reference (:173-174); host
+        inputs are checked on the host, a CUDA tensor with one reduction (`check_actions=False` skips that
+        synchronisation: an offending world then reports done with zero reward and `stats()['bad_action_seen']`)."""
+        if check_actions and not (isinstance(actions, torch.Tensor) and actions.is_cuda):
+            host = np.asarray(actions.cpu() if isinstance(actions, torch.Tensor) else actions).reshape(-1)
+            if host.size and (int(host.min()) < 0 or int(host.max()) > 3):
+                raise IndexError('No such action!')
         a = torch.as_tensor(actions, device=self.device).to(torch.int64).contiguous()
         if a.numel() != self.num_envs:
             raise ValueError('expected %d actions' % self.num_envs)
+        if check_actions and isinstance(actions, torch.Tensor) and actions.is_cuda and bool(((a < 0) | (a > 3)).any()):
+            raise IndexError('No such action!')
         _capi.check(self._lib.paintrl_param_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.penalty),
                                                  _ptr(self.actual), _ptr(self.done), _ptr(self.next_obs), self._stream()))
         return self.obs, self.actual, self.done, {'reward': self.reward, 'penalty': self.penalty, 'next_obs': self.next_obs}
@@ -228,13 +245,17 @@ def spiral_actions(grid_size):
     three legs of grid_size - 3 steps, then legs shrinking by one every second turn."""
     direction, leg, legs_left = 0, grid_size - 3, 3
     yield None
-    while True:
+    while leg > 0:
         for _ in range(leg):
             yield direction % 4
         direction += 1
         legs_left -= 1
         if legs_left <= 0:
             legs_left, leg = 2, leg - 1
+    # the legs are used up: the reference's loop (param_test_env.py:326-340) never sees `current_counter == 0` again
+    # and keeps stepping in the direction it has just turned to until the episode ends (at a wall)
+    while True:
+        yield direction % 4
 
 
 def drive(env, actions):

@@ -108,16 +108,22 @@ class RolloutWorker(object):
         self.ep_reward = torch.zeros(B, dtype=torch.float64, device=dev)
         self.ep_penalty = torch.zeros(B, dtype=torch.float64, device=dev)
         self.ep_len = torch.zeros(B, dtype=torch.int64, device=dev)
+        # the observation the next fragment starts from: written by start() and at the end of every fragment,
+        # read at the top of every fragment -- inside the captured loop, so back-to-back collect() calls are
+        # always consistent (no separate advance() step to forget)
+        self._carry = torch.zeros(B, env.obs_dim, dtype=torch.float64, device=dev)
         self._started = False
 
     def start(self, start_index=None):
         """Reset every environment; the first observation of the first fragment."""
-        self.frag.obs[0].copy_(self.env.reset(start_index))
+        self._carry.copy_(self.env.reset(start_index))
+        self.frag.obs[0].copy_(self._carry)
         self.ep_reward.zero_(); self.ep_penalty.zero_(); self.ep_len.zero_()
         self._started = True
 
     def _run_steps(self):
         f, env, pol = self.frag, self.env, self.policy
+        f.obs[0].copy_(self._carry)
         for t in range(self.T):
             a, logp, value = pol.act(f.obs[t])
             f.actions[t].copy_(a)
@@ -126,6 +132,7 @@ class RolloutWorker(object):
             env.step_into(f.actions[t], f.term_obs[t], f.reward[t], f.penalty[t], f.actual[t], f.done[t],
                           next_obs=f.obs[t + 1], new_texels=f.new_texels[t])
         f.value[self.T].copy_(pol.forward(f.obs[self.T])[1])      # bootstrap value of the truncated episodes
+        self._carry.copy_(f.obs[self.T])
 
     def _capture(self):
         try:
@@ -175,16 +182,15 @@ class RolloutWorker(object):
         acc = torch.stack([done.sum().to(torch.float64), totals[0].sum(), totals[1].sum(), totals[0].sum() - totals[1].sum(),
                            f.new_texels.sum().to(torch.float64), totals[2].max()])
         host = acc.cpu()
-        next_first = f.obs[self.T].clone()
         stats = {'env_steps': float(self.T * env.num_envs), 'episodes': float(host[0]), 'sum_reward': float(host[1]),
                  'sum_penalty': float(host[2]), 'sum_return': float(host[3]), 'new_texels': float(host[4]),
                  'max_episode_len': float(host[5])}
-        self._next_first = next_first
         return f, stats
 
     def advance(self):
-        """Make the last observation of the collected fragment the first of the next one."""
-        self.frag.obs[0].copy_(self._next_first)
+        """Kept for callers of the first version: the hand-over of the last observation to the next fragment now
+        happens inside `collect()` itself (`_carry`), so this is a no-op."""
+        return None
 
 
 def gae(frag, gamma=0.99, lam=1.0):

@@ -31,7 +31,7 @@ def test_engine_replays_reference_trace(name, cuda_device):
             assert np.array_equal(env.reset().cpu().numpy()[1], next(first))
     w, v = env.tables()
     assert np.array_equal(w[2].cpu().numpy(), c['world'])
-    assert np.array_equal(np.minimum(v[2].cpu().numpy(), 255), np.minimum(c['visit'], 255))
+    assert np.array_equal(v[2].cpu().numpy(), c['visit'])
     st = env.stats()
     assert st['env_steps'] == 3 * len(c['actions']) and not st['bad_action_seen']
     env.close()
@@ -86,14 +86,52 @@ def test_batch_matches_oracle_with_auto_reset(mode, size, repeat, cuda_device):
     env.close()
 
 
-def test_bad_action_is_flagged_and_ignored(cuda_device):
+def test_bad_action_raises_like_the_reference(cuda_device):
+    """param_test_env.py:173-174 raises IndexError for an action outside 0..3: so does the batched mirror, before
+    any world is stepped, for host lists and for CUDA tensors.  With the check switched off the offending world
+    is left untouched but its output row is fresh (current observation, zero reward, done), the flag is
+    reported once and then cleared."""
     from paintrl_b200.param_env import BatchedParamTestEnv
     env = BatchedParamTestEnv(4, 8, device=cuda_device)
-    env.reset()
+    first = env.reset().clone()
     before = env.tables()[0].clone()
-    env.step(torch.tensor([0, 9, 1, -1]))
+    for bad in ([0, 9, 1, -1], torch.tensor([0, 4, 1, 2], device=cuda_device)):
+        with pytest.raises(IndexError):
+            env.step(bad)
+    assert torch.equal(env.tables()[0], before) and env.stats()['env_steps'] == 0
+    o, actual, done, info = env.step(torch.tensor([0, 9, 1, -1], device=cuda_device), check_actions=False)
     st = env.stats()
     assert st['bad_action_seen'] and st['env_steps'] == 2
+    assert not env.stats()['bad_action_seen']                 # cleared once reported
     after = env.tables()[0]
     assert torch.equal(before[1], after[1]) and torch.equal(before[3], after[3]) and not torch.equal(before[0], after[0])
+    assert done.cpu().tolist() == [0, 1, 0, 1] and actual.cpu().tolist()[1] == 0.0 and actual.cpu().tolist()[3] == 0.0
+    assert torch.equal(o[1], first[1]) and torch.equal(info['next_obs'][3], first[3])
     env.close()
+
+
+def test_env_ids_are_validated(cuda_device):
+    from paintrl_b200.param_env import BatchedParamTestEnv
+    env = BatchedParamTestEnv(4, 8, device=cuda_device)
+    for bad, exc in (([4], IndexError), ([-1], IndexError), ([1, 1], ValueError), ([], ValueError)):
+        with pytest.raises(exc):
+            env.reset(env_ids=bad)
+        with pytest.raises(exc):
+            env.tables(env_ids=bad)
+    assert env.reset(env_ids=[3, 0]).shape[0] == 2
+    env.close()
+
+
+def test_spiral_driver_terminates_on_any_world(cuda_device, capsys):
+    """The reference's spiral() keeps stepping in its last direction once the legs are used up
+    (param_test_env.py:326-340) until the episode ends at a wall; the generator does the same instead of
+    spinning without yielding (sizes where the legs run out before the world is consumed)."""
+    from paintrl_b200.param_env import ParamTestEnv, drive, spiral_actions
+    for size, max_len in ((5, 900), (9, 900), (22, 900)):
+        env = ParamTestEnv(size, max_len=max_len)
+        steps, _ = drive(env, spiral_actions(size))
+        assert 0 < steps <= max(max_len, (size - 2) ** 2)
+        env.close()
+    gen = spiral_actions(4)            # grid_size - 3 = 1: one-step legs, then none
+    next(gen)
+    assert [next(gen) for _ in range(8)] == [0, 1, 2, 3, 3, 3, 3, 3]

@@ -80,34 +80,62 @@ def test_unstaged_grid_and_discrete_observations():
 
 
 def test_state_round_trip():
-    """get_state -> set_state into other environments reproduces their future bit for bit (RGB status is the
-    painted bit).  set_state clears the overlap reference set (it cannot be expressed through the
-    interface), so the source environments re-import their own state as well."""
+    """Exact mid-episode checkpoint (ABI v2): get_state -> set_state into ANOTHER engine reproduces the future
+    bit for bit, OVERLAP_PENALTY included -- the scalars carry the overlap reference
+    (Part._last_painted_pixels, bullet_paint_wrapper.py:483, 575-576, as the last shot's centre), so the source
+    engine does not have to re-import its own state."""
     from paintrl_b200.batched_env import BatchedPaintEnv
-    cfg = EnvConfig(dict(BASE), auto_reset=False)
-    dev = torch.device('cuda:0')
-    a = BatchedPaintEnv(32, cfg, device=dev)
-    b = BatchedPaintEnv(32, cfg, device=dev)
-    rng = np.random.default_rng(11)
-    a.reset(rng.integers(0, a.n_starts, size=32).astype(np.int32))
-    b.reset(np.zeros(32, dtype=np.int32))
-    for _ in range(15):
-        a.step(rng.integers(0, 4, size=32))
-    st = a.get_state()
-    b.set_state(status=st['status'], pose=st['pose'], quat=st['quat'], scalars=st['scalars'])
-    a.set_state(status=st['status'], pose=st['pose'], quat=st['quat'], scalars=st['scalars'])   # same overlap-set clearing
-    st_b = b.get_state()
-    assert torch.equal(st['status'], st_b['status'])
-    assert torch.equal(st['pose'], st_b['pose']) and torch.equal(st['scalars'], st_b['scalars'])
-    assert torch.equal(a.job_status(), b.job_status())
-    for _ in range(10):
-        acts = rng.integers(0, 4, size=32)
-        oa, ra, da, _ = a.step(acts)
-        ob, rb, db, _ = b.step(acts)
-        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db)
-    assert torch.equal(a.get_state()['status'], b.get_state()['status'])
-    a.close()
-    b.close()
+    for color in ('RGB', 'HSI'):
+        cfg = EnvConfig(dict(BASE, OVERLAP_PENALTY=True, TURNING_PENALTY=True, COLOR_MODE=color, START_POINT_MODE='edge'), auto_reset=False)
+        dev = torch.device('cuda:0')
+        a = BatchedPaintEnv(32, cfg, device=dev)
+        b = BatchedPaintEnv(40, cfg, device=dev)
+        rng = np.random.default_rng(11)
+        a.reset(rng.integers(0, a.n_starts, size=32).astype(np.int32))
+        b.reset(np.zeros(40, dtype=np.int32))
+        for _ in range(15):
+            a.step(rng.integers(0, 4, size=32))
+        st = a.get_state()
+        assert st['scalars'].shape == (32, 12) and bool(st['has_overlap_reference'].all())
+        ids = np.arange(32, dtype=np.int32) + 8           # into other slots of another engine
+        b.set_state(env_ids=ids, status=st['status'], pose=st['pose'], quat=st['quat'], scalars=st['scalars'])
+        st_b = b.get_state(env_ids=ids)
+        assert torch.equal(st['status'], st_b['status'])
+        assert torch.equal(st['pose'], st_b['pose']) and torch.equal(st['scalars'], st_b['scalars'])
+        assert torch.equal(a.job_status(), b.job_status()[8:])
+        saw_overlap = False
+        for _ in range(10):
+            acts = rng.integers(0, 4, size=32)
+            oa, ra, da, ia = a.step(acts)
+            ob, rb, db, ib = b.step(np.concatenate([np.zeros(8, dtype=np.int64), acts]))
+            assert torch.equal(oa, ob[8:]) and torch.equal(ra, rb[8:]) and torch.equal(da, db[8:])
+            assert torch.equal(ia['penalty'], ib['penalty'][8:])
+            saw_overlap = saw_overlap or bool((ia['penalty'] > 0.2).any())
+        assert saw_overlap
+        assert torch.equal(a.get_state()['status'], b.get_state(env_ids=ids)['status'])
+        # a status plane WITHOUT scalars clears the overlap reference (reset_part, bullet_paint_wrapper.py:708)
+        b.set_state(env_ids=ids, status=st['status'])
+        assert not bool(b.get_state(env_ids=ids)['has_overlap_reference'].any())
+        a.close()
+        b.close()
+
+
+def test_env_ids_are_validated():
+    """Out-of-range, duplicate and empty id lists are refused on the host (the kernels index state with them);
+    a short reset_start_index is refused too."""
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    env = BatchedPaintEnv(16, dict(BASE), device=torch.device('cuda:0'), auto_reset=True)
+    env.reset(0)
+    for bad, exc in (([16], IndexError), ([-1], IndexError), ([3, 3], ValueError), ([], ValueError),
+                     (torch.tensor([2, 99], device='cuda:0'), IndexError), (torch.tensor([5, 5], device='cuda:0'), ValueError)):
+        with pytest.raises(exc):
+            env.reset(0, env_ids=bad)
+        with pytest.raises(exc):
+            env.get_state(env_ids=bad)
+    with pytest.raises(ValueError):
+        env.step(np.zeros(16, dtype=np.int64), reset_start_index=np.zeros(8, dtype=np.int32))
+    assert env.reset(1, env_ids=torch.tensor([15, 0], device='cuda:0')).shape == (2, env.obs_dim)
+    env.close()
 
 
 def test_step_rejects_bad_buffers():
