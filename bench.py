@@ -335,6 +335,17 @@ def measure(key, args, rank, local_rank, world_size, device, steps, warmup, e2e=
     start = torch.randint(0, env.n_starts, (n_env,), generator=gs, device=device, dtype=torch.int32)
     env.reset(start)
     flush = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=device)
+    drain = torch.empty(256 << 20, dtype=torch.uint8, device=device) if (flush is not None and args.flush_mode == 'write+read') else None
+
+    def flush_l2(i):
+        """Evict the environments' state from the 126 MB L2: write a 512 MiB buffer.  'write+read' then reads another
+        256 MiB buffer so that the L2 is left holding CLEAN foreign lines (the write alone leaves it full of dirty
+        lines, whose write-backs the timed step would pay for on every miss)."""
+        if flush is not None:
+            flush.fill_(i & 0xff)
+            if drain is not None:
+                drain_sink.add_(drain.view(torch.int64)[::8].sum())
+    drain_sink = torch.zeros((), dtype=torch.int64, device=device)
 
     # the parity sample of the timed run (rank 0): logged on the device between the event brackets
     rec = None
@@ -350,8 +361,7 @@ def measure(key, args, rank, local_rank, world_size, device, steps, warmup, e2e=
         torch.cuda.synchronize(device)
 
     for i in range(warmup):
-        if flush is not None:
-            flush.fill_(i & 0xff)
+        flush_l2(i)
         env.step(actions[i])
         if rec is not None:
             rec.record(actions[i])
@@ -364,8 +374,7 @@ def measure(key, args, rank, local_rank, world_size, device, steps, warmup, e2e=
     acc = torch.zeros(4, dtype=torch.float64, device=device)   # rollout statistics, accumulated outside the timed event pairs
     t_wall = time.perf_counter()
     for i in range(steps):
-        if flush is not None:
-            flush.fill_(i & 0xff)
+        flush_l2(i)
         starts[i].record()
         env.step(actions[warmup + i])
         stops[i].record()
@@ -378,6 +387,15 @@ def measure(key, args, rank, local_rank, world_size, device, steps, warmup, e2e=
     s1 = env.stats()
     step_ms = np.array([a.elapsed_time(b) for a, b in zip(starts, stops)])
     dev_ms = float(step_ms.sum())
+    # informational: the same steps back to back under ONE event pair (warm L2, no flush, no per-step events)
+    b2b = min(steps, 100)
+    eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eb0.record()
+    for i in range(b2b):
+        env.step(actions[warmup + i])
+    eb1.record()
+    torch.cuda.synchronize(device)
+    b2b_us = eb0.elapsed_time(eb1) * 1e3 / b2b
 
     # ---- end-to-end through the host-buffer API (pinned host actions in, results out, every step)
     e2e_s, act_bytes, d2h_bytes, e2e_api = 0.0, 0, 0, None
@@ -431,7 +449,10 @@ def measure(key, args, rank, local_rank, world_size, device, steps, warmup, e2e=
     res = {'key': key, 'workload': workload, 'cfg': cfg, 'n_env': n_env, 'total_envs': total_envs, 'steps': steps, 'warmup': warmup,
            'value': total_envs * steps / (dev_ms_max * 1e-3), 'ms_per_step': dev_ms_max / steps, 'clocks': clocks,
            'rollout_stats': rollout_stats, 'wall_s': wall_s, 'create_s': create_s, 'n_front': env.n_texels,
-           'gpu_launches': s1['kernel_launches'] - s0['kernel_launches']}
+           'gpu_launches': s1['kernel_launches'] - s0['kernel_launches'],
+           'step_us': {'mean': float(step_ms.mean() * 1e3), 'median': float(np.median(step_ms) * 1e3), 'p10': float(np.percentile(step_ms, 10) * 1e3),
+                       'p90': float(np.percentile(step_ms, 90) * 1e3), 'max': float(step_ms.max() * 1e3),
+                       'back_to_back_warm_l2': b2b_us}}
     if e2e:
         res['e2e'] = {'value': total_envs * e2e_steps / e2e_s_max, 'unit': UNIT, 'h2d_bytes_per_step': act_bytes,
                       'd2h_bytes_per_step': d2h_bytes, 'steps': e2e_steps, 'repeats': 5, 'statistic': 'median repeat', 'api': e2e_api}
@@ -455,6 +476,7 @@ def measure(key, args, rank, local_rank, world_size, device, steps, warmup, e2e=
                 'kernel_ms': kernel_ms, 'algorithmic_bytes_per_env_step': b_alg,
                 'footprint_union_texels_mean': u_mean, 'p_reset': p_reset,
                 'ray_full_scans_per_env_step': (s1['ray_full_scans'] - s0['ray_full_scans']) / max(1, steps_done),
+                'move_bailouts_per_env_step': (s1['move_bailouts'] - s0['move_bailouts']) / max(1, steps_done),
                 'bound_measured': None, 'issue_frac': None, 'dram_gbs_measured': None, 'dram_frac_measured': None,
                 'kernel_source_sha': sha, 'counters_source_sha': counters_sha,
                 'counters_current': bool(counters is not None and counters_sha == sha)}
@@ -490,7 +512,7 @@ def measure(key, args, rank, local_rank, world_size, device, steps, warmup, e2e=
                            'reward / penalty / next_obs every step, status planes after the last step' % chk['envs'])
             res['parity_check'] = chk
     env.close()
-    del env, actions, flush
+    del env, actions, flush, drain
     torch.cuda.empty_cache()
     return res
 
@@ -506,7 +528,7 @@ def compact(res):
     roof = res.get('roofline')
     if roof:
         out['roofline'] = {k: roof[k] for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic', 'kernel_ms', 'p_reset',
-                                                'footprint_union_texels_mean', 'algorithmic_bytes_per_env_step', 'bound_measured',
+                                                'footprint_union_texels_mean', 'algorithmic_bytes_per_env_step', 'move_bailouts_per_env_step', 'bound_measured',
                                                 'issue_frac', 'dram_gbs_measured', 'counters_current')}
     if 'parity_check' in res:
         out['parity_check'] = {k: res['parity_check'][k] for k in ('envs', 'steps', 'ok', 'exact', 'episodes', 'mismatch')}
@@ -523,6 +545,8 @@ def main():
     ap.add_argument('--envs', type=int, default=None, help='override environments per GPU')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-flush', action='store_true', help='keep the L2 warm between steps (not the headline)')
+    ap.add_argument('--flush-mode', default='write', choices=['write', 'write+read'],
+                    help="how the L2 is flushed between timed steps: a 512 MiB write, or that write followed by a 256 MiB read")
     ap.add_argument('--no-graph', action='store_true', help='--rollout: keep the eager per-step launch loop (no CUDA graph)')
     ap.add_argument('--no-extra', action='store_true', help='skip the other BASELINE configurations (extra.configs)')
     ap.add_argument('--no-parity', action='store_true', help='skip the oracle replay of the timed run')
@@ -579,10 +603,10 @@ def main():
             'warmup': warmup, 'ms_per_step': res['ms_per_step'], 'higher_is_better': True,
             'scaling': workload['scaling'], 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': config,
-            'timing': dict(res['state'], l2='warm (no flush)' if args.no_flush else 'flushed with a 512 MiB write between timed steps',
+            'timing': dict(res['state'], l2='warm (no flush)' if args.no_flush else ('flushed with a 512 MiB write between timed steps' + (' followed by a 256 MiB read (L2 left clean)' if args.flush_mode == 'write+read' else '')),
                            method='CUDA events per step on the launch stream, summed; max over ranks'),
             'clocks': res['clocks'], 'e2e': res['e2e'], 'gpu_launches': res['gpu_launches'], 'roofline': res['roofline'],
-            'rollout_stats': res['rollout_stats'], 'wall_s_timed_region': res['wall_s'],
+            'rollout_stats': res['rollout_stats'], 'wall_s_timed_region': res['wall_s'], 'step_us': res['step_us'],
         }
         if 'parity_check' in res:
             line['parity_check'] = res['parity_check']

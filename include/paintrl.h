@@ -212,6 +212,7 @@ typedef struct PaintrlStats {
     uint64_t footprint_texels;
     uint64_t kernel_launches;
     uint64_t ray_full_scans;   /* rays that needed the full plane list (5 rays per env-step) */
+    uint64_t move_bailouts;    /* env-steps whose move phase left the fast kernel and ran in the paint warp */
 } PaintrlStats;
 int paintrl_stats(PaintrlHandle h, PaintrlStats *out);
 

@@ -68,7 +68,7 @@ class PaintrlConfig(ctypes.Structure):
 class PaintrlStats(ctypes.Structure):
     _fields_ = [('env_steps', ctypes.c_uint64), ('episodes_ended', ctypes.c_uint64),
                 ('footprint_texels', ctypes.c_uint64), ('kernel_launches', ctypes.c_uint64),
-                ('ray_full_scans', ctypes.c_uint64)]
+                ('ray_full_scans', ctypes.c_uint64), ('move_bailouts', ctypes.c_uint64)]
 
 
 class PaintrlParamConfig(ctypes.Structure):

@@ -285,4 +285,4 @@ class BatchedPaintEnv(object):
         _capi.check(self._lib.paintrl_stats(self._h, ctypes.byref(s)))
         return {'env_steps': int(s.env_steps), 'episodes_ended': int(s.episodes_ended),
                 'footprint_texels': int(s.footprint_texels), 'kernel_launches': int(s.kernel_launches),
-                'ray_full_scans': int(s.ray_full_scans)}
+                'ray_full_scans': int(s.ray_full_scans), 'move_bailouts': int(s.move_bailouts)}

@@ -16,6 +16,10 @@
 
 using namespace paintrl;
 
+// Batches below this many environments per GPU take the one-kernel step (a warp runs move + paint of its environment
+// back to back); from here on the two-kernel step with 8-lane move groups wins (measured: profiles/).
+static const int kFusedBelowEnvs = 16384;
+
 namespace {
 
 thread_local std::string g_error;
@@ -91,6 +95,9 @@ struct PaintrlEngine {
     int move_lanes = 32;             // lanes per environment in move_kernel (8, 16 or 32)
     int move_warps = 4, paint_warps = 1;   // warps per block of the two step kernels (1, 2 or 4)
     int move_minb = 4;               // its __launch_bounds__ min blocks per SM (4: 128 registers, 7: 72)
+    void *cold_args = nullptr;       // device copy of {pk, cfg, env arrays} for the paint warps' generic-move call (ColdArgs)
+    int fused = -1;                  // PAINTRL_FUSED: 1 / 0 force the one-kernel / two-kernel step; -1: by batch size
+    bool move_fast = true;           // PAINTRL_MOVE_FAST=0: the generic move kernel instead of the lean fast-path one
     bool force_unstaged = false;     // PAINTRL_FORCE_UNSTAGED: run the global-memory bit-plane path (tests)
 };
 
@@ -841,6 +848,16 @@ int paintrl_debug_profile(unsigned long long *out64, int reset) {
 }
 
 /* Debug only: the last step's phase cycles per environment ([n][32] u32, slot 14 = the move counters). */
+int paintrl_debug_fast_reasons(unsigned long long *out8) {
+#ifdef PAINTRL_PROFILE
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out8, g_fast_reasons, 8 * sizeof(unsigned long long)) == cudaSuccess ? 1 : -1;
+#else
+    (void)out8;
+    return 0;
+#endif
+}
+
 int paintrl_debug_profile_env(unsigned *out, int n) {
 #ifdef PAINTRL_PROFILE
     cudaDeviceSynchronize();
@@ -942,6 +959,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     c.expected_avg_reward = cfg->max_possible_point / (double)(cfg->expected_episode_length * 100);
     c.hybrid_threshold = cfg->switch_threshold * cfg->max_possible_point / 100;
     c.auto_reset = cfg->auto_reset;
+    { const char *bm = getenv("PAINTRL_DEBUG_BAIL_MOD"); c.debug_bail_mod = bm ? std::max(0, atoi(bm)) : 0; }
     c.seed = cfg->seed;
 
     const size_t bits_bytes = (size_t)num_envs * e->pk.n_words_pad * sizeof(unsigned);
@@ -955,7 +973,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
               e->arena.alloc((void **)&e->bits, bits_bytes) == cudaSuccess &&
               (thick_bytes == 0 || e->arena.alloc((void **)&e->thick, thick_bytes) == cudaSuccess) &&
               (gcnt_bytes == 0 || e->arena.alloc((void **)&e->grid_cnt, gcnt_bytes) == cudaSuccess) &&
-              e->arena.alloc((void **)&e->stats, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              e->arena.alloc((void **)&e->stats, 8 * sizeof(unsigned long long)) == cudaSuccess &&
               e->arena.alloc((void **)&e->ready, sizeof(unsigned) * (size_t)num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&reset_obs, sizeof(double) * od * (size_t)e->pk.n_starts) == cudaSuccess &&
               e->arena.alloc(&e->stage_actions, adim * num_envs) == cudaSuccess &&
@@ -970,7 +988,7 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
         err = cudaGetLastError();
     }
     if (err == cudaSuccess && e->grid_cnt) err = cudaMemset(e->grid_cnt, 0, gcnt_bytes);
-    if (err == cudaSuccess) err = cudaMemset(e->stats, 0, 4 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemset(e->stats, 0, 8 * sizeof(unsigned long long));
     if (err == cudaSuccess) err = cudaMemset(e->ready, 0, sizeof(unsigned) * (size_t)num_envs);
     if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, std::string("initialising device state: ") + cudaGetErrorString(err)); }
     // observation of a fresh environment at every start point, from environment 0's all-zero planes
@@ -993,8 +1011,19 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
         e->paint_warps = (pwi == 4 || pwi == 2) ? pwi : 1;   // one warp per block: a finished environment frees its slot at once
         const char *co = getenv("PAINTRL_CARVEOUT");
         e->carveout_percent = co ? std::min(100, std::max(-1, atoi(co))) : -1;
+        const char *fu = getenv("PAINTRL_FUSED");
+        e->fused = fu ? (atoi(fu) != 0 ? 1 : 0) : -1;
+        const char *mf = getenv("PAINTRL_MOVE_FAST");
+        e->move_fast = !(mf && atoi(mf) == 0);
         const char *mb = getenv("PAINTRL_MOVE_MINB");
         e->move_minb = (mb && atoi(mb) >= 7) ? 7 : 4;     // 4: 128 registers, two waves at 4096 envs; 7: 72 registers (spills), one wave
+    }
+    {
+        ColdArgs ca;
+        ca.pk = e->pk; ca.cfg = e->cfg; ca.ea = env_arrays(e);
+        err = e->arena.alloc(&e->cold_args, sizeof(ColdArgs));
+        if (err == cudaSuccess) err = cudaMemcpy(e->cold_args, &ca, sizeof(ColdArgs), cudaMemcpyHostToDevice);
+        if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, std::string("uploading the kernel-argument copy: ") + cudaGetErrorString(err)); }
     }
     *out = e;
     return PAINTRL_OK;
@@ -1059,6 +1088,28 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     io.actual = actual_dev; io.done = done_dev; io.new_texels = new_texels_dev;
     io.next_obs = h->cfg.auto_reset ? next_obs_dev : nullptr;
     io.reset_start_idx = reset_start_idx_dev;
+    const bool use_fused = h->fused >= 0 ? h->fused == 1 : h->num_envs < kFusedBelowEnvs;
+    if (use_fused) {
+        // one launch, one warp per environment for the whole step (paintrl_kernels.cuh step_fused_kernel)
+        const bool staged_f = h->pk.n_words_pad <= kStageWords && !h->force_unstaged;
+        const bool ax12f = h->pk.axis0 == 1 && h->pk.axis1 == 2, disc = h->cfg.action_mode == 0;
+        const EnvArrays fea = env_arrays(h);
+        const ColdArgs *cold = (const ColdArgs *)h->cold_args;
+        cudaStream_t fs = as_stream(stream);
+#define PAINTRL_FUSED_K(C, ST, AX, DI) step_fused_kernel<C, ST, AX, DI><<<h->num_envs, 32, 0, fs>>>(h->pk, h->cfg, fea, h->num_envs, io, cold)
+#define PAINTRL_FUSED_AD(C, ST)                                                        \
+    do {                                                                               \
+        if (ax12f && disc) PAINTRL_FUSED_K(C, ST, true, true);                         \
+        else if (ax12f) PAINTRL_FUSED_K(C, ST, true, false);                           \
+        else if (disc) PAINTRL_FUSED_K(C, ST, false, true);                            \
+        else PAINTRL_FUSED_K(C, ST, false, false);                                     \
+    } while (0)
+        if (h->color == 0) { if (staged_f) PAINTRL_FUSED_AD(0, true); else PAINTRL_FUSED_AD(0, false); }
+        else { if (staged_f) PAINTRL_FUSED_AD(1, true); else PAINTRL_FUSED_AD(1, false); }
+#undef PAINTRL_FUSED_AD
+#undef PAINTRL_FUSED_K
+        return launch_check(h, "step_fused_kernel");
+    }
     {   // lanes per environment in the move phase: fewer when there are enough environments to fill the GPU
         const int threads = h->move_warps * 32;
         cudaStream_t ms = as_stream(stream);
@@ -1074,11 +1125,23 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
         if (ax12m) move_kernel<G, MINB, true><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);  \
         else move_kernel<G, MINB, false><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);       \
     } while (0)
-        if (h->move_minb == 7) {
+#define PAINTRL_MOVE_FAST(G)                                                                                               \
+    do {                                                                                                                   \
+        if (ax12m && discrete) move_fast_kernel<G, true, true><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);   \
+        else if (ax12m) move_fast_kernel<G, true, false><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);         \
+        else if (discrete) move_fast_kernel<G, false, true><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);      \
+        else move_fast_kernel<G, false, false><<<mblocks, threads, 0, ms>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);                   \
+    } while (0)
+        const bool discrete = h->cfg.action_mode == 0;
+        if (h->move_fast) {
+            // the lean kernel: rays decided by their move cell alone; the rest is handed to the paint warps (kReadyBailed)
+            if (L == 8) PAINTRL_MOVE_FAST(8); else if (L == 16) PAINTRL_MOVE_FAST(16); else PAINTRL_MOVE_FAST(32);
+        } else if (h->move_minb == 7) {
             if (L == 8) PAINTRL_MOVE(8, 7); else if (L == 16) PAINTRL_MOVE(16, 7); else PAINTRL_MOVE(32, 7);
         } else {
             if (L == 8) PAINTRL_MOVE(8, 4); else if (L == 16) PAINTRL_MOVE(16, 4); else PAINTRL_MOVE(32, 4);
         }
+#undef PAINTRL_MOVE_FAST
 #undef PAINTRL_MOVE
     }
     int rc = launch_check(h, "move_kernel");
@@ -1103,8 +1166,8 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
             cudaFuncSetAttribute(paint_kernel<C, ST, true, W>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout_percent);  \
             cudaFuncSetAttribute(paint_kernel<C, ST, false, W>, cudaFuncAttributePreferredSharedMemoryCarveout, h->carveout_percent); \
         }                                                                                                   \
-        if (ax12) perr = cudaLaunchKernelEx(&lc, paint_kernel<C, ST, true, W>, h->pk, h->cfg, pea, h->num_envs, io);  \
-        else perr = cudaLaunchKernelEx(&lc, paint_kernel<C, ST, false, W>, h->pk, h->cfg, pea, h->num_envs, io);      \
+        if (ax12) perr = cudaLaunchKernelEx(&lc, paint_kernel<C, ST, true, W>, h->pk, h->cfg, pea, h->num_envs, io, (const ColdArgs *)h->cold_args);  \
+        else perr = cudaLaunchKernelEx(&lc, paint_kernel<C, ST, false, W>, h->pk, h->cfg, pea, h->num_envs, io, (const ColdArgs *)h->cold_args);      \
     } while (0)
 #define PAINTRL_PAINT(C, ST)                                                                 \
     do {                                                                                     \
@@ -1211,7 +1274,7 @@ int paintrl_job_status(PaintrlHandle h, int32_t *painted_dev, void *stream) {
 int paintrl_stats(PaintrlHandle h, PaintrlStats *out) {
     if (!h || !out) return fail(PAINTRL_E_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    unsigned long long host[4];
+    unsigned long long host[5];
     CUDA_TRY(cudaMemset(h->stats, 0, sizeof(host)));
     stats_kernel<<<std::max(1, std::min(64, (h->num_envs + 255) / 256)), 256>>>(h->env_stats, h->num_envs, h->stats);
     CUDA_TRY(cudaGetLastError());
@@ -1224,6 +1287,7 @@ int paintrl_stats(PaintrlHandle h, PaintrlStats *out) {
                 host[2] & 0xffffffffull, host[2] >> 32, host[3]);
     out->env_steps = host[3];
     out->kernel_launches = h->launches;
+    out->move_bailouts = host[4];
     return PAINTRL_OK;
 }
 

@@ -106,8 +106,10 @@ struct alignas(128) MoveOut {
 static_assert(sizeof(MoveOut) == 128, "MoveOut must be one 128-byte line");
 
 // Per-environment counters behind paintrl_stats (summed on request; no atomics on the step path).
-struct alignas(32) EnvStat {
+struct alignas(64) EnvStat {
     unsigned long long episodes_ended, footprint_texels, full_scans, env_steps;
+    unsigned long long move_bailouts;   // steps whose move phase the fast kernel handed to the paint warp
+    unsigned long long pad[3];
 };
 
 // Move grid over (axis0, axis1) (see build_move_cells in paintrl_capi.cu).  Every cell has an 8-byte
@@ -206,6 +208,7 @@ struct DevConfig {
     double expected_avg_reward;     // max_possible_point / (Expected_Episode_Length * 100)   (robot_gym_env.py:297)
     double hybrid_threshold;        // SWITCH_THRESHOLD * max_possible_point / 100            (robot_gym_env.py:302)
     int auto_reset;
+    int debug_bail_mod;             // PAINTRL_DEBUG_BAIL_MOD=n (tests): every n-th environment leaves the fast move kernel at once
     unsigned long long seed;
 };
 
@@ -429,6 +432,20 @@ __device__ __forceinline__ int near_violations(const double2 *planes, int n, con
     for (; i < n; i += G) {
         const double2 lo = __ldg(planes + 2 * i), hi2 = __ldg(planes + 2 * i + 1);
         double sd = fma(hi2.x, h.z, fma(lo.y, h.y, lo.x * h.x)) - hi2.y;
+        c += (sd > -kVerifyMargin) ? 1 : 0;
+    }
+    return grp_sum<G>(c, g);
+}
+
+// The same count with a plain loop (the fast move path's copy of the verify pass: rare there, and its registers must
+// not add to that kernel's budget).  Per plane the same expression as near_violations, so counts are comparable.
+template <int G>
+__device__ __noinline__ int near_violations_rolled(const double2 *planes, int n, Vec3 h, Grp g) {
+    int c = 0;
+#pragma unroll 1
+    for (int i = g.gl; i < n; i += G) {
+        const double2 lo = __ldg(planes + 2 * i), hi2 = __ldg(planes + 2 * i + 1);
+        const double sd = fma(hi2.x, h.z, fma(lo.y, h.y, lo.x * h.x)) - hi2.y;
         c += (sd > -kVerifyMargin) ? 1 : 0;
     }
     return grp_sum<G>(c, g);
@@ -698,8 +715,8 @@ __device__ __forceinline__ unsigned nearest_vertex_cell(const Vec3 &p, const Cel
 // point, accepted when it proves that no vertex outside the block can be nearer; otherwise (hull faces
 // bridging an opening of the part: the nearest vertex is far away) one coalesced brute-force pass over
 // all front vertices -- a bounded ~n/32 iterations instead of a growing ring search.
-template <int G>
-__device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const Ax &ax, const Vec3 &p, const Grp &g) {
+template <int G, typename VG>
+__device__ __forceinline__ unsigned nearest_vertex_grid(const VG &pk, const Ax &ax, const Vec3 &p, const Grp &g) {
     double q0 = comp(p, ax.a0), q1 = comp(p, ax.a1);
     int cx = (int)floor((q0 - pk.vg_o0) * pk.vg_inv);
     int cy = (int)floor((q1 - pk.vg_o1) * pk.vg_inv);
@@ -754,6 +771,38 @@ __device__ __forceinline__ unsigned nearest_vertex_grid(const DevPack &pk, const
     }
     if (bi == 0xFFFFFFFFu) return 0xFFFFFFFFu;
     return __ldg(&pk.vrec[bi]);
+}
+
+// The fast move path's copies of ray_test's / hook_triangle's slow steps: real calls (noinline) with every argument
+// by value, so that their registers and loops stay out of the calling kernel's budget.  They run for a few rays in
+// a hundred thousand (rays that graze a move-cell border or leave the part), but a step is as slow as its slowest
+// environment: sending such an environment through the whole generic move instead costs the step tens of microseconds.
+struct VertexGridArgs {       // the vertex-grid members of DevPack, same names (nearest_vertex_grid is generic over the holder)
+    int vg_nx, vg_ny;
+    double vg_o0, vg_o1, vg_cs, vg_inv;
+    const int *vg_start;
+    const double *vx, *vy, *vz;
+    const int *vid;
+    const unsigned *vrec;
+};
+__device__ __forceinline__ VertexGridArgs vertex_grid_args(const DevPack &pk) {
+    VertexGridArgs a;
+    a.vg_nx = pk.vg_nx; a.vg_ny = pk.vg_ny; a.vg_o0 = pk.vg_o0; a.vg_o1 = pk.vg_o1; a.vg_cs = pk.vg_cs; a.vg_inv = pk.vg_inv;
+    a.vg_start = pk.vg_start; a.vx = pk.vx; a.vy = pk.vy; a.vz = pk.vz; a.vid = pk.vid; a.vrec = pk.vrec;
+    return a;
+}
+template <int G>
+__device__ __noinline__ unsigned nearest_vertex_grid_call(VertexGridArgs a, int a0, int a1, Vec3 p, Grp g) {
+    Ax ax; ax.a0 = a0; ax.a1 = a1;
+    return nearest_vertex_grid<G>(a, ax, p, g);
+}
+struct SlabAll { double t_in, t_out; int outside; unsigned args; };
+template <int G>
+__device__ __noinline__ SlabAll slab_pass_all_call(const double2 *planes, int n, Vec3 frm, double d0, double d1, double d2, Grp g) {
+    SlabAll o;
+    const SlabResult r = slab_pass_all<G>(planes, n, frm, d0, d1, d2, g, &o.args);
+    o.t_in = r.t_in; o.t_out = r.t_out; o.outside = r.outside ? 1 : 0;
+    return o;
 }
 
 // Part._get_hook_point + _get_closest_bary (bullet_paint_wrapper.py:525-534, 508-523, 154-185):

@@ -886,12 +886,299 @@ move_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *a
     move_body<G, AX12>(pk, cfg, ea, env, actions);
 }
 
+// ------------------------------------------------------------------------------ move, fast path
+// The move phase as the batch overwhelmingly runs it: every ray is decided by its move cell's own plane list
+// -- a miss proven by the list (1), or an entry point inside the cell's region (2a) -- within kRayAttempts
+// cells, and the nearest vertex comes from the cell's candidates.  Everything else of ray_test / hook_triangle
+// (the verify pass (2b), the full plane scan (3), the miss-cache pair, the vertex-grid search) is NOT compiled
+// into this kernel: an environment that needs any of it leaves without having written anything and raises its
+// hand-off flag to kReadyBailed; the paint warp of that environment then runs the generic move_body itself
+// before it paints.  Same arithmetic, same order, same results as move_body on the path both share -- but
+// without the cold paths' live ranges the kernel fits the register budget of ONE wave at 4096 environments
+// (28 warps per SM), which the generic kernel (128 registers, 1.73 waves) does not.
+constexpr unsigned kReadyMoved = 1u, kReadyBailed = 2u;
+
+template <int G>
+__device__ __forceinline__ const double *hook_triangle_cell(const DevPack &pk, const Ax &ax, const Vec3 &point, const CellRef &ref, double2 vc0,
+                                                            double2 vc1, const Grp &g) {
+    // the hit's move cell lists every vertex that can be nearest; a hit outside every cell region (rare: accepted by
+    // the verify pass or found by the full scan) searches the vertex grid
+    const unsigned rec = ref.blob ? nearest_vertex_cell<G>(point, ref, vc0, vc1, g)
+                                  : nearest_vertex_grid_call<G>(vertex_grid_args(pk), ax.a0, ax.a1, point, g);
+    if (rec == 0xFFFFFFFFu) return nullptr;
+    const int deg = (int)(rec & 0xffu);
+    const double *base = pk.trirec + (size_t)(rec >> 8) * kTriRec;
+    if (deg <= 0) return nullptr;
+    int pick = -1;
+    double run_max = -INFINITY;
+    int run_arg = -1;
+    for (int b0 = 0; b0 < deg; b0 += G) {
+        const int k = b0 + g.gl;
+        bool inside = false;
+        double m = -INFINITY;
+        if (k < deg) {
+            const double2 *t = reinterpret_cast<const double2 *>(base + (size_t)k * kTriRec);
+            // the tail of the record (normal, quaternion, shot-centre offset) is read right after the pick:
+            // bring its sectors in with the head's
+            prefetch_l1(reinterpret_cast<const char *>(t) + 128);
+            const double2 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2), t3 = __ldg(t + 3), t4 = __ldg(t + 4),
+                          t5 = __ldg(t + 5), t6 = __ldg(t + 6);
+            const double v2x = point.x - t0.x, v2y = point.y - t0.y, v2z = point.z - t1.x;
+            const double d20 = npdot3(v2x, v2y, v2z, t1.y, t2.x, t2.y);
+            const double d21 = npdot3(v2x, v2y, v2z, t3.x, t3.y, t4.x);
+            const double d00 = t4.y, d01 = t5.x, d11 = t5.y, inv = t6.x;
+            double bv = (d11 * d20 - d01 * d21) * inv;
+            double bw = (d00 * d21 - d01 * d20) * inv;
+            double bu = 1.0 - bv - bw;
+            if (inv == 0.0) { bu = -1.0; bv = -1.0; bw = -1.0; }
+            inside = (0.0 <= bu && bu <= 1.0 && 0.0 <= bv && bv <= 1.0 && 0.0 <= bw && bw <= 1.0);
+            m = fmin(fmin(bu, bv), bw);
+        }
+        const unsigned in_mask = grp_ballot<G>(inside, g);
+        if (in_mask) { pick = b0 + __ffs(in_mask) - 1; break; }
+        const double cm = grp_max<G>(m, g);
+        if (cm >= run_max) {   // `>=`: a later triangle wins ties (bullet_paint_wrapper.py:520)
+            const unsigned eq = grp_ballot<G>(k < deg && m == cm, g);
+            run_max = cm;
+            run_arg = b0 + 31 - __clz(eq);
+        }
+    }
+    if (pick < 0) pick = (run_max >= -1.0) ? run_arg : 0;
+    return base + (size_t)pick * kTriRec;
+}
+
+// 0 miss, 1 hit (hit / ref / vc0 / vc1 set), 2 leave the fast path.  `miss_cache_ptr`: the environment's pair of hull
+// planes that decided its last full plane scan (MoveOut::miss_cache, maintained by the generic path): a ray no move
+// cell can decide -- the TCP has wandered off the part, its rays start outside the grid -- is usually proven a miss
+// by that pair (any subset of the planes may prove a miss), so such environments stay on the fast path too.
+#ifdef PAINTRL_PROFILE
+__device__ unsigned long long g_fast_reasons[8];   // why rays left the fast path: 1 outside the grid, 2 empty cell, 3 no entering plane, 4 attempts used up, 5 no vertex candidates
+#define PAINTRL_FAST_REASON(k) do { if (grp.gl == 0) atomicAdd(&g_fast_reasons[k], 1ull); } while (0)
+#else
+#define PAINTRL_FAST_REASON(k) do {} while (0)
+#endif
+template <int G>
+__device__ __forceinline__ int ray_fast(const DevPack &pk, const Ax &ax, const Vec3 &frm, const Vec3 &to, const Grp &grp, Vec3 &hit,
+                                        CellRef &ref, double2 &vc0, double2 &vc1, double pf0, double pf1, bool do_prefetch,
+                                        const unsigned *miss_cache_ptr) {
+    const double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
+    const int npax = 3 - ax.a0 - ax.a1;
+    Vec3 h = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
+    SlabResult r;
+    r.t_in = -INFINITY; r.t_out = INFINITY; r.outside = false;
+    bool candidate = false;
+    int why = 4;
+    const double2 *sub = nullptr;      // the plane list of the last cell tried
+    int n_sub = 0;
+#pragma unroll 1
+    for (int attempt = 0; attempt < kRayAttempts; ++attempt) {
+        const double g0 = comp(h, ax.a0), g1 = comp(h, ax.a1);
+        const int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
+        const int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
+        if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) { why = 1; break; }
+        const uint2 entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+        const int n_planes = (int)(entry.y & 0xffffu), n_verts = (int)(entry.y >> 16);
+        if (n_planes <= 0) { why = 2; break; }
+        const double2 *blob = pk.mc_blob + (size_t)entry.x * 2;
+        sub = blob + 4; n_sub = n_planes;
+        const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);
+        if (grp.gl < n_verts) {
+            vc0 = __ldg(blob + 2 * (2 + n_planes + grp.gl));
+            vc1 = __ldg(blob + 2 * (2 + n_planes + grp.gl) + 1);
+        }
+        if (do_prefetch && attempt == 0) {
+            const int px = (int)floor((g0 + pf0 - pk.mc_o0) * pk.mc_inv);
+            const int py = (int)floor((g1 + pf1 - pk.mc_o1) * pk.mc_inv);
+            if (px >= 0 && py >= 0 && px < pk.mc_nx && py < pk.mc_ny && (px != cx || py != cy)) {
+                const uint2 pe = __ldg(&pk.mc_entry[py * pk.mc_nx + px]);
+                const int sectors = 2 + (int)(pe.y & 0xffffu) + (int)(pe.y >> 16);
+                const char *pb = reinterpret_cast<const char *>(pk.mc_blob + (size_t)pe.x * 2);
+                if (G == 32) { if (grp.gl * 128 < sectors * 32) prefetch_l1(pb + grp.gl * 128); }
+                else for (int o = grp.gl * 128; o < sectors * 32; o += G * 128) prefetch_l1(pb + o);
+            }
+        }
+        r = slab_pass<G>(blob + 4, n_planes, frm, d0, d1, d2, grp);
+        if (r.outside || r.t_in > r.t_out || r.t_in > 1.0 || r.t_out < 0.0) return 0;   // (1)
+        candidate = false;
+        if (!(r.t_in > -INFINITY)) { why = 3; break; }
+        candidate = true;
+        h.x = frm.x + d0 * r.t_in; h.y = frm.y + d1 * r.t_in; h.z = frm.z + d2 * r.t_in;
+        if (in_cell_region(pk, h, comp(h, ax.a0), comp(h, ax.a1), comp(h, npax), cx, cy, abv, clv, hpv)) {   // (2a)
+            if (!(0.0 <= r.t_in)) return 0;        // with (1) passed this is the serial scan's hit test
+            if (n_verts <= 0) { PAINTRL_FAST_REASON(5); return 2; }
+            ref.blob = blob; ref.n_planes = n_planes; ref.n_verts = n_verts;
+            hit = h;
+            return 1;
+        }
+    }
+    // (1) again with the pair of planes that decided this environment's last full scan, as ray_test does
+    if (pair_proves_miss(pk, *miss_cache_ptr, r, candidate, frm, d0, d1, d2)) return 0;
+    if (candidate) {
+        // (2b) the entry point of the last list lies in the region of none of the cells tried (a ray grazing a sharp
+        // feature of the hull): one division-free pass over all hull planes decides whether that list was enough.
+        // Out-of-line, rolled: a handful of rays in a million come here, but a step is as slow as its slowest environment.
+        if (near_violations_rolled<G>(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, h, grp) ==
+            near_violations_rolled<G>(sub, n_sub, h, grp)) {
+            if (!(r.t_in <= r.t_out && 0.0 <= r.t_in && r.t_in <= 1.0)) return 0;
+            ref.blob = nullptr;          // the hit lies outside every cell region: its nearest vertex comes from the vertex grid
+            hit = h;
+            return 1;
+        }
+        why = 6;
+    }
+    PAINTRL_FAST_REASON(why);
+    (void)why;
+    return 2;
+}
+
+// FUSED (G == 32, called by the fused step kernel's warp): the record is read from and written to the warp's shared
+// scratch `sst` / `smv` instead of global memory and no flag is published; returns true when the environment left
+// the fast path (then nothing of `sst` has been changed).
+template <int G, bool AX12, bool DISCRETE, bool FUSED>
+__device__ __forceinline__ bool move_fast_body(const DevPack &pk, const DevConfig &cfg, const EnvArrays &ea, int env, const void *actions,
+                                               EnvState *sst, MoveOut *smv) {
+    const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
+    const int lane = threadIdx.x & 31;
+    const Grp grp = make_grp<G>(lane);
+    PAINTRL_TRACE_MARK(env, 0, grp.gl == 0);
+    PAINTRL_TRACE_SM(env, 6, grp.gl == 0);
+    EnvState *gst = FUSED ? sst : &ea.states[env];
+    Vec3 cur_p, cur_n;
+    double last_angle;
+    int term_counter = gst->term_counter, flags = gst->flags;
+    {
+        const double2 s0 = reinterpret_cast<const double2 *>(gst)[0], s1 = reinterpret_cast<const double2 *>(gst)[1],
+                      s2 = reinterpret_cast<const double2 *>(gst)[2];
+        const double q[4] = {s1.y, s2.x, s2.y, gst->quat[3]};
+        last_angle = gst->last_angle;
+        cur_p.x = s0.x; cur_p.y = s0.y; cur_p.z = s1.x;
+        cur_n = tcp_orn_norm(cur_p, q);
+    }
+    // ---- action -> direction (robot_gym_env.py:342-347, robot.py:390-398, 352-358), as in move_body
+    double u1, u2, new_angle;
+    if (DISCRETE) {
+        const long long a = reinterpret_cast<const long long *>(actions)[env];
+        const int ai = (int)min(max(a, 0ll), (long long)cfg.discrete_granularity);
+        u1 = __ldg(&cfg.discrete_table[3 * ai]);
+        u2 = __ldg(&cfg.discrete_table[3 * ai + 1]);
+        new_angle = __ldg(&cfg.discrete_table[3 * ai + 2]);
+    } else {
+        const double *a = reinterpret_cast<const double *>(actions) + (size_t)env * cfg.action_shape;
+        double a0 = a[0];
+        if (!(-1.0 <= a0 && a0 <= 1.0)) a0 = a0 < -1.0 ? -1.0 : 1.0;
+        if (cfg.action_shape == 1) {
+            const double phi = (a0 + 1.0) * kPi;
+            u1 = cos(phi);
+            u2 = sin(phi);
+        } else {
+            double a1v = a[1];
+            if (!(-1.0 <= a1v && a1v <= 1.0)) a1v = a1v < -1.0 ? -1.0 : 1.0;
+            const double phi = atan2(a1v, a0);
+            const double x = fabs(a0), y = fabs(a1v);
+            if (x == 0.0 && y == 0.0) { u1 = x; u2 = y; }
+            else { const double m = fmax(x, y); u1 = m * cos(phi); u2 = m * sin(phi); }
+        }
+        const double da1 = u1 * kStepSize, da2 = u2 * kStepSize;
+        new_angle = (da1 != 0.0) ? atan(fabs(da2 / da1)) : kPi / 2;
+    }
+    const double delta1 = (u1 * kStepSize) / kPaintPerAction, delta2 = (u2 * kStepSize) / kPaintPerAction;
+    const int counter_before = term_counter;
+    double quat[4];
+    MoveOut *mv = FUSED ? smv : &ea.moves[env];
+    double *centers = &mv->centers[0][0];
+#pragma unroll 1
+    for (int s = 0; s < kPaintPerAction; ++s) {
+        const double delta2_scaled = delta2 * pk.lwr;
+        Vec3 p = cur_p;
+        add_comp(p, ax.a0, delta1);
+        add_comp(p, ax.a1, delta2_scaled);
+        const Vec3 end = {p.x + cur_n.x, p.y + cur_n.y, p.z + cur_n.z};
+        Vec3 hit, pos, center;
+        CellRef ref;
+        double2 vc0 = make_double2(0.0, 0.0), vc1 = vc0;
+        const double *rec = nullptr;
+        const int code = ray_fast<G>(pk, ax, p, end, grp, hit, ref, vc0, vc1, delta1, delta2_scaled, s + 1 < kPaintPerAction,
+                                     &ea.moves[env].miss_cache);
+        if (code == 2) {
+            // not decidable on the fast path: nothing of this step has been published (the shot centres written so
+            // far are rewritten by the generic pass); the environment's paint warp takes the move over
+            if (!FUSED && grp.gl == 0)
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ea.ready + env), "r"(kReadyBailed) : "memory");
+            PAINTRL_TRACE_MARK(env, 1, grp.gl == 0);
+            return true;
+        }
+        if (code == 1) rec = hook_triangle_cell<G>(pk, ax, hit, ref, vc0, vc1, grp);
+        if (rec) {
+            const double2 *t = reinterpret_cast<const double2 *>(rec + 12);   // [12] inv, [13..15] n, [16..19] q, [20..22] off
+            const double2 t0 = __ldg(t), t1 = __ldg(t + 1), t2 = __ldg(t + 2), t3 = __ldg(t + 3), t4 = __ldg(t + 4),
+                          t5 = __ldg(t + 5);
+            const double nx = t0.y, ny = t1.x, nz = t1.y;
+            pos.x = hit.x + nx * kHookDistance;
+            pos.y = hit.y + ny * kHookDistance;
+            pos.z = hit.z + nz * kHookDistance;
+            quat[0] = t2.x; quat[1] = t2.y; quat[2] = t3.x; quat[3] = t3.y;
+            center.x = t4.x + pos.x; center.y = t4.y + pos.y; center.z = t5.x + pos.z;   // robot.py:277-278
+            cur_n.x = -nx; cur_n.y = -ny; cur_n.z = -nz;
+            flags |= kFlagLastOnPart;
+        } else {
+            quat_from_normal(cur_n, quat);                              // robot.py:313: the orientation of the kept normal
+            pos = transform_point(cur_p, quat, delta2, delta1, 0.0);    // robot.py:317 (sic)
+            center = transform_point(pos, quat, 0.0, 0.0, 0.1);         // robot.py:277-278
+            if (flags & kFlagLastOnPart) {                              // robot.py:292-300
+                flags &= ~kFlagLastOnPart;
+            } else {
+                term_counter += 1;
+                if (term_counter > kNotOnPartTerminateSteps) flags |= kFlagTerminate;
+            }
+        }
+        if (grp.gl == 0) { centers[3 * s] = center.x; centers[3 * s + 1] = center.y; centers[3 * s + 2] = center.z; }
+        cur_p = pos;
+    }
+    if (grp.gl == 0) {
+        reinterpret_cast<double2 *>(gst)[0] = make_double2(cur_p.x, cur_p.y);
+        reinterpret_cast<double2 *>(gst)[1] = make_double2(cur_p.z, quat[0]);
+        reinterpret_cast<double2 *>(gst)[2] = make_double2(quat[1], quat[2]);
+        gst->quat[3] = quat[3];
+        reinterpret_cast<double2 *>(&gst->last_angle)[0] = make_double2(new_angle, fabs(new_angle - last_angle));
+        gst->term_counter = term_counter;
+        gst->flags = flags;
+        mv->counts = term_counter - counter_before;
+        if (!FUSED) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ea.ready + env), "r"(kReadyMoved) : "memory");
+    }
+    PAINTRL_TRACE_MARK(env, 1, grp.gl == 0);
+    return false;
+}
+
+#ifndef PAINTRL_MOVE_FAST_MINB
+#define PAINTRL_MOVE_FAST_MINB 7
+#endif
+template <int G, bool AX12, bool DISCRETE>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PAINTRL_MOVE_FAST_MINB)
+move_fast_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const void *actions) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int env = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    if (env >= num_envs) return;
+    if (cfg.debug_bail_mod > 0 && env % cfg.debug_bail_mod == 0) {      // tests: exercise the hand-over to the paint warp
+        if ((threadIdx.x & (G - 1)) == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ea.ready + env), "r"(kReadyBailed) : "memory");
+        return;
+    }
+    move_fast_body<G, AX12, DISCRETE, false>(pk, cfg, ea, env, actions, nullptr, nullptr);
+}
+
+// The generic move of ONE environment, called by its paint warp when the fast move kernel bailed out.  Deliberately a
+// real call (noinline) on a copy of the kernel arguments in global memory: the cold path's registers and spills stay
+// out of the paint kernel's own allocation.
+struct ColdArgs { DevPack pk; DevConfig cfg; EnvArrays ea; };
+__device__ __noinline__ void move_generic_cold(const ColdArgs *ca, int env, const void *actions) {
+    move_body<32, false>(ca->pk, ca->cfg, ca->ea, env, actions);
+}
+
 // Everything after the move: stamp, score, observe, auto-reset.  (STAGED) the environment's flip bits
 // come in through a TMA bulk copy issued before the warp waits for its environment's hand-off flag and go
 // back the same way; the record and the move kernel's output follow the flag with L2 loads.
-template <int COLOR, bool STAGED, bool AX12>
+template <int COLOR, bool STAGED, bool AX12, bool FUSED = false, bool DISCRETE = false>
 __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &cfg, const EnvArrays &ea, int env, const StepIO &io,
-                                           WarpScratch<STAGED> &ws) {
+                                           WarpScratch<STAGED> &ws, const ColdArgs *cold) {
     const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
     typedef WarpScratch<STAGED> WS;
     const int lane = threadIdx.x & 31;
@@ -910,28 +1197,53 @@ __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &c
     // move kernel has started, and each warp waits only for ITS environment's move phase (acquire of the
     // flag the move warp released) -- not for the whole grid: a slow environment of the move phase delays
     // nobody else, and the paint phase fills the SMs the move kernel's last wave leaves idle.
-    if (lane == 0) {
-        const unsigned *flag = ea.ready + env;
-        unsigned v;
-        for (;;) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-            if (v != 0u) break;
-            __nanosleep(200);
+    int bailed = 0;
+    if (FUSED) {
+        // One warp runs the whole step of its environment: the record comes into the scratch, the fast move phase
+        // works on that copy (the bit-plane copy issued above lands meanwhile), the paint phase continues on it.
+        if (lane < 8) reinterpret_cast<double2 *>(&ws.st)[lane] = __ldcg(reinterpret_cast<const double2 *>(&ea.states[env]) + lane);
+        __syncwarp();
+        if (cfg.debug_bail_mod > 0 && env % cfg.debug_bail_mod == 0) bailed = 1;      // tests: force the generic path
+        else bailed = move_fast_body<32, AX12, DISCRETE, true>(pk, cfg, ea, env, io.actions, &ws.st, &ws.mv) ? 1 : 0;
+        __syncwarp();
+    } else {
+        // Launched with programmatic stream serialization: this grid's CTAs start as soon as every CTA of the
+        // move kernel has started, and each warp waits only for ITS environment's move phase (acquire of the
+        // flag the move warp released) -- not for the whole grid.
+        if (lane == 0) {
+            const unsigned *flag = ea.ready + env;
+            unsigned v;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                if (v != 0u) break;
+                __nanosleep(200);
+            }
+            // consume: the next step's move kernel (which starts after this grid has completed) raises it again.
+            // No sequence number in the kernel arguments, so a captured step can be replayed from a CUDA graph.
+            ea.ready[env] = 0u;
+            bailed = (v == kReadyBailed);
         }
-        // consume: the next step's move kernel (which starts after this grid has completed) raises it again.
-        // No sequence number in the kernel arguments, so a captured step can be replayed from a CUDA graph.
-        ea.ready[env] = 0u;
+        bailed = __shfl_sync(kFull, bailed, 0);
+    }
+    if (bailed) {
+        // the fast move phase could not decide one of this environment's rays from its move cell alone and wrote
+        // nothing: run the generic move here (verify pass / full plane scan / vertex-grid search), then paint
+        move_generic_cold(cold, env, io.actions);
+        __threadfence();
+        if (lane == 0) ea.ready[env] = 0u;      // move_body published 1: consumed
     }
     __syncwarp();
     PAINTRL_TRACE_MARK(env, 3, lane == 0);
-    // the record and the move output: L2 loads (another SM wrote them while this grid was already running)
-    if (lane < 16) {
-        const double2 *src = lane < 8 ? reinterpret_cast<const double2 *>(&ea.states[env]) + lane
-                                      : reinterpret_cast<const double2 *>(&ea.moves[env]) + (lane - 8);
-        double2 *dst = lane < 8 ? reinterpret_cast<double2 *>(&ws.st) + lane : reinterpret_cast<double2 *>(&ws.mv) + (lane - 8);
-        *dst = __ldcg(src);
+    if (!FUSED || bailed) {
+        // the record and the move output: L2 loads (another SM wrote them while this grid was already running)
+        if (lane < 16) {
+            const double2 *src = lane < 8 ? reinterpret_cast<const double2 *>(&ea.states[env]) + lane
+                                          : reinterpret_cast<const double2 *>(&ea.moves[env]) + (lane - 8);
+            double2 *dst = lane < 8 ? reinterpret_cast<double2 *>(&ws.st) + lane : reinterpret_cast<double2 *>(&ws.mv) + (lane - 8);
+            *dst = __ldcg(src);
+        }
+        __syncwarp();
     }
-    __syncwarp();
     if (STAGED) mbar_wait(&ws.bar, 0);
     PAINTRL_TRACE_MARK(env, 4, lane == 0);
     PAINTRL_PROF(16, lane == 0);
@@ -1071,6 +1383,7 @@ __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &c
         if (ws.mv.counts >> 8)   // full plane scans in the low half of the counter, verify passes in the high half
             atomicAdd(&es->full_scans, (unsigned long long)((ws.mv.counts >> 8) & 0xff) | ((unsigned long long)((ws.mv.counts >> 16) & 0xff) << 32));
         atomicAdd(&es->env_steps, 1ull);
+        if (bailed) atomicAdd(&es->move_bailouts, 1ull);
         // the record
         st.last_center[0] = ws.mv.centers[NS - 1][0];
         st.last_center[1] = ws.mv.centers[NS - 1][1];
@@ -1109,12 +1422,23 @@ __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &c
 #endif
 template <int COLOR, bool STAGED, bool AX12, int WPB>
 __global__ void __launch_bounds__(WPB * 32, (STAGED ? PAINTRL_PAINT_OCC : 16) / WPB)
-paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io) {
+paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io, const ColdArgs *cold) {
     __shared__ WarpScratch<STAGED> scratch[WPB];
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * WPB + warp;
     if (env >= num_envs) return;
-    paint_body<COLOR, STAGED, AX12>(pk, cfg, ea, env, io, scratch[warp]);
+    paint_body<COLOR, STAGED, AX12>(pk, cfg, ea, env, io, scratch[warp], cold);
+}
+
+// The whole step of one environment in one warp (batches that cannot fill the GPU twice over: the two-kernel step
+// pays the move grid's drain before the paint grid's warps get their slots; here a warp goes straight on).
+template <int COLOR, bool STAGED, bool AX12, bool DISCRETE>
+__global__ void __launch_bounds__(32, STAGED ? PAINTRL_PAINT_OCC : 16)
+step_fused_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io, const ColdArgs *cold) {
+    __shared__ WarpScratch<STAGED> scratch[1];
+    const int env = blockIdx.x;
+    if (env >= num_envs) return;
+    paint_body<COLOR, STAGED, AX12, true, DISCRETE>(pk, cfg, ea, env, io, scratch[0], cold);
 }
 
 // PaintGymEnv.reset / Robot.reset(pose) for the listed environments, with their first observation.
@@ -1274,12 +1598,13 @@ __global__ void job_status_kernel(DevPack pk, EnvArrays ea, int num_envs, int32_
 }
 
 // paintrl_stats: sum of the per-environment counters.
-__global__ void stats_kernel(const EnvStat *es, int num_envs, unsigned long long *out /*[4], zeroed*/) {
-    unsigned long long a = 0, b = 0, c = 0, d = 0;
+__global__ void stats_kernel(const EnvStat *es, int num_envs, unsigned long long *out /*[5], zeroed*/) {
+    unsigned long long a = 0, b = 0, c = 0, d = 0, f = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < num_envs; i += gridDim.x * blockDim.x) {
         a += es[i].episodes_ended; b += es[i].footprint_texels; c += es[i].full_scans; d += es[i].env_steps;
+        f += es[i].move_bailouts;
     }
-    atomicAdd(&out[0], a); atomicAdd(&out[1], b); atomicAdd(&out[2], c); atomicAdd(&out[3], d);
+    atomicAdd(&out[0], a); atomicAdd(&out[1], b); atomicAdd(&out[2], c); atomicAdd(&out[3], d); atomicAdd(&out[4], f);
 }
 
 }  // namespace paintrl

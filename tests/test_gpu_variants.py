@@ -38,9 +38,12 @@ def _replay(extra, kw, num_envs, steps, env_vars):
     rng = np.random.default_rng(7)
     start = rng.integers(0, env.n_starts, size=num_envs).astype(np.int32)
     assert np.array_equal(env.reset(start).cpu().numpy(), ora.reset(start))
-    exact = cfg.color_mode == 'RGB'
+    exact = cfg.color_mode == 'RGB' and cfg.action_mode == 'discrete'
     for t in range(steps):
-        acts = rng.integers(0, cfg.discrete_granularity, size=num_envs)
+        if cfg.action_mode == 'discrete':
+            acts = rng.integers(0, cfg.discrete_granularity, size=num_envs)
+        else:
+            acts = rng.uniform(-1, 1, size=(num_envs, cfg.action_dim))
         nxt = rng.integers(0, env.n_starts, size=num_envs).astype(np.int32)
         obs, actual, done, info = env.step(acts, reset_start_index=nxt)
         o_obs, o_rew, o_pen, o_act, o_done = ora.step(acts)
@@ -65,7 +68,37 @@ def _replay(extra, kw, num_envs, steps, env_vars):
 
 @pytest.mark.parametrize('lanes', [8, 16, 32])
 def test_move_kernel_lane_groups(lanes):
-    _replay(dict(BASE), {}, 96, 60, {'PAINTRL_MOVE_LANES': str(lanes)})
+    _replay(dict(BASE), {}, 96, 60, {'PAINTRL_MOVE_LANES': str(lanes), 'PAINTRL_FUSED': '0'})
+
+
+def test_generic_move_kernel():
+    """PAINTRL_MOVE_FAST=0: the generic move kernel (all ray / vertex paths compiled in) instead of the lean one."""
+    _replay(dict(BASE, START_POINT_MODE='edge'), {}, 96, 60, {'PAINTRL_MOVE_FAST': '0', 'PAINTRL_FUSED': '0'})
+
+
+@pytest.mark.parametrize('fused', ['0', '1'])
+@pytest.mark.parametrize('kw', [dict(), dict(action_mode='continuous', action_shape=2, obs_mode='grid', obs_grad=4),
+                                dict(action_mode='continuous', action_shape=1, obs_mode='section', obs_grad=8)])
+def test_one_kernel_and_two_kernel_steps(fused, kw):
+    """The step as one launch (a warp runs the move and the paint phase of its environment back to back; default
+    below 16384 environments) and as two launches (move grid + paint grid with per-environment hand-off flags),
+    forced either way on the same small batch."""
+    _replay(dict(BASE, START_POINT_MODE='all', OVERLAP_PENALTY=True), kw, 80, 50, {'PAINTRL_FUSED': fused})
+
+
+def test_one_kernel_step_unstaged_hsi():
+    _replay(dict(BASE, Part_NO=1, COLOR_MODE='HSI', OVERLAP_PENALTY=True), {}, 64, 40, {'PAINTRL_FUSED': '1', 'PAINTRL_FORCE_UNSTAGED': '1'})
+
+
+@pytest.mark.parametrize('lanes', ['8', '32', 'fused'])
+@pytest.mark.parametrize('color', ['RGB', 'HSI'])
+def test_fast_move_kernel_hands_over_to_the_paint_warp(lanes, color):
+    """Every third environment is forced off the fast move kernel: its paint warp runs the generic move itself
+    (the path rays take that their move cell cannot decide).  Results stay bit-exact."""
+    extra = dict(BASE, COLOR_MODE=color, START_POINT_MODE='edge', OVERLAP_PENALTY=True)
+    env_vars = {'PAINTRL_DEBUG_BAIL_MOD': '3', 'PAINTRL_FUSED': '1'} if lanes == 'fused' else {
+        'PAINTRL_DEBUG_BAIL_MOD': '3', 'PAINTRL_MOVE_LANES': lanes, 'PAINTRL_FUSED': '0'}
+    _replay(extra, {}, 100, 50, env_vars)
 
 
 @pytest.mark.parametrize('color', ['RGB', 'HSI'])
