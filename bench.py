@@ -159,6 +159,24 @@ def physical_gpu_index(local_index):
     return local_index
 
 
+def pin_to_gpu_numa_node(index):
+    """Keep this rank's host thread on the CPUs NVML reports as local to its GPU (the e2e leg is a host loop per rank:
+    eight of them on one box should not wander across sockets).  Returns the number of CPUs in the mask, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        return None
+    return None
+
+
 def workload_pack(workload, cfg, rasterizer='oracle'):
     """The part pack of a workload for the CPU legs (texels of synthetic textures from the oracle's own rasteriser)."""
     from paintrl_b200.partpack import PartPack
@@ -571,6 +589,7 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device('cuda', local_rank)
     sharding.init_process_group()
+    numa_cpus = pin_to_gpu_numa_node(physical_gpu_index(local_rank)) if world_size > 1 else None
 
     parity_envs = 0 if args.no_parity else 128
     res = measure(args.workload, args, rank, local_rank, world_size, device, args.steps, warmup, e2e=True,
@@ -605,7 +624,7 @@ def main():
             'config': config,
             'timing': dict(res['state'], l2='warm (no flush)' if args.no_flush else ('flushed with a 512 MiB write between timed steps' + (' followed by a 256 MiB read (L2 left clean)' if args.flush_mode == 'write+read' else '')),
                            method='CUDA events per step on the launch stream, summed; max over ranks'),
-            'clocks': res['clocks'], 'e2e': res['e2e'], 'gpu_launches': res['gpu_launches'], 'roofline': res['roofline'],
+            'clocks': res['clocks'], 'e2e': dict(res['e2e'], host_thread_cpus=numa_cpus), 'gpu_launches': res['gpu_launches'], 'roofline': res['roofline'],
             'rollout_stats': res['rollout_stats'], 'wall_s_timed_region': res['wall_s'], 'step_us': res['step_us'],
         }
         if 'parity_check' in res:

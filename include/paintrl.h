@@ -181,6 +181,18 @@ int paintrl_step_host(PaintrlHandle h, const void *actions_host, double *obs_hos
                       double *reward_host, double *penalty_host, double *actual_host,
                       uint8_t *done_host, double *next_obs_host, void *stream);
 
+/* The same host-buffer step, split in two so that consecutive steps overlap: `submit` queues the host->device copy of
+ * the actions (on a copy stream of the library's own), the step (on `stream`) and the device->host copy of the results
+ * (on a second copy stream) and returns at once; `wait` blocks until the results of that slot have landed.  Two slots
+ * (0 and 1) with separate device staging: step t + 1 may be submitted on the other slot before step t is waited for --
+ * its copy-in and kernels then run while step t's results travel and the host wakes up.  Steps execute in submission
+ * order.  The host buffers of a slot (actions included) belong to the library between submit and wait; pinned memory
+ * is needed for the copies to be asynchronous.  A slot resubmitted without a wait first waits for its own copy-out. */
+int paintrl_step_host_submit(PaintrlHandle h, int32_t slot, const void *actions_host, double *obs_host,
+                             double *reward_host, double *penalty_host, double *actual_host,
+                             uint8_t *done_host, double *next_obs_host, void *stream);
+int paintrl_step_host_wait(PaintrlHandle h, int32_t slot);
+
 /* State access (the reference keeps it in Part.texels / Robot._pose,_orn / PaintGymEnv counters,
  * robot_gym_env.py:219-221, robot.py:201-218, bullet_paint_wrapper.py:467,483).
  * status_dev: int16[n, n_texels] first-channel value per front texel in part-pack order

@@ -93,6 +93,8 @@ SIGNATURES = {
     'paintrl_set_pose': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP]),
     'paintrl_step': (ctypes.c_int, [_VP] * 11),
     'paintrl_step_host': (ctypes.c_int, [_VP] * 9),
+    'paintrl_step_host_submit': (ctypes.c_int, [_VP, _I32] + [_VP] * 8),
+    'paintrl_step_host_wait': (ctypes.c_int, [_VP, _I32]),
     'paintrl_get_state': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
     'paintrl_set_state': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP, _VP]),
     'paintrl_job_status': (ctypes.c_int, [_VP, _VP, _VP]),

@@ -214,6 +214,37 @@ class BatchedPaintEnv(object):
             _capi.check(rc)
         return out
 
+    def step_host_submit(self, actions, out, slot=0):
+        """First half of `step_host` (paintrl_step_host_submit): queue the copy-in of `actions`, the step and the
+        copy-out into `out` (from `host_buffers`) on staging slot 0 or 1 and return at once.  `actions` must stay
+        untouched (and should be pinned) until `step_host_wait(slot)`.  Submitting step t + 1 on the other slot
+        before waiting for step t overlaps its copy-in and kernels with step t's copy-out and the host's wake-up."""
+        discrete = self.cfg.action_mode == 'discrete'
+        want = np.int64 if discrete else np.float64
+        a = actions
+        if not (isinstance(a, np.ndarray) and a.dtype == want and a.flags.c_contiguous):
+            a = np.ascontiguousarray(actions, dtype=want)
+        if a.size != (self.num_envs if discrete else self.num_envs * self.action_dim):
+            raise ValueError('expected %d actions' % self.num_envs)
+        ptrs = out.get('_ptrs')
+        if ptrs is None:
+            nxt = out.get('next_obs')
+            ptrs = tuple(out[k].ctypes.data for k in ('obs', 'reward', 'penalty', 'actual', 'done')) + (
+                nxt.ctypes.data if nxt is not None else None,)
+        self._inflight = getattr(self, '_inflight', {})
+        self._inflight[slot] = (a, out)          # keep the buffers alive until the wait
+        rc = self._lib.paintrl_step_host_submit(self._h, int(slot), a.ctypes.data, ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4],
+                                                ptrs[5], torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            _capi.check(rc)
+
+    def step_host_wait(self, slot=0):
+        """Second half: block until the results of `slot` have landed in its host buffers; returns them."""
+        rc = self._lib.paintrl_step_host_wait(self._h, int(slot))
+        if rc != 0:
+            _capi.check(rc)
+        return self._inflight.pop(slot)[1]
+
     def host_buffers(self, pinned=True, next_obs=True):
         """Host result buffers for `step_host`: views into ONE (pinned) allocation laid out
         obs | reward | penalty | actual | [next_obs] | done, the order `paintrl_step_host` stages its

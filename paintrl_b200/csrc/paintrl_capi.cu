@@ -90,6 +90,13 @@ struct PaintrlEngine {
     // paintrl_step_host: one contiguous block, laid out per call as obs | reward | penalty | actual | [next_obs] | done,
     // so that host buffers carved from one allocation in that order come back with a single copy
     unsigned char *stage_out = nullptr;
+    // paintrl_step_host_submit / _wait: two staging slots, a copy-in and a copy-out stream of the library's own, so that
+    // step t + 1's host->device copy and launch overlap step t's device->host copy and the host's wake-up
+    void *slot_actions[2] = {nullptr, nullptr};
+    unsigned char *slot_out[2] = {nullptr, nullptr};
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_step[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    bool slot_pending[2] = {false, false};
     unsigned long long launches = 0;
     double move_cell_planes_mean = 0.0, move_cell_verts_mean = 0.0;
     int move_lanes = 32;             // lanes per environment in move_kernel (8, 16 or 32)
@@ -977,6 +984,10 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
               e->arena.alloc((void **)&e->ready, sizeof(unsigned) * (size_t)num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&reset_obs, sizeof(double) * od * (size_t)e->pk.n_starts) == cudaSuccess &&
               e->arena.alloc(&e->stage_actions, adim * num_envs) == cudaSuccess &&
+              e->arena.alloc(&e->slot_actions[0], adim * num_envs) == cudaSuccess &&
+              e->arena.alloc(&e->slot_actions[1], adim * num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&e->slot_out[0], (sizeof(double) * (2 * od + 3) + 1) * (size_t)num_envs) == cudaSuccess &&
+              e->arena.alloc((void **)&e->slot_out[1], (sizeof(double) * (2 * od + 3) + 1) * (size_t)num_envs) == cudaSuccess &&
               e->arena.alloc((void **)&e->stage_out, (sizeof(double) * (2 * od + 3) + 1) * (size_t)num_envs) == cudaSuccess;
     if (!ok) { delete e; return fail(PAINTRL_E_CUDA, "device allocation failed (state / status planes)"); }
     err = cudaMemset(e->states, 0, sizeof(EnvState) * (size_t)num_envs);
@@ -1018,6 +1029,14 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
         const char *mb = getenv("PAINTRL_MOVE_MINB");
         e->move_minb = (mb && atoi(mb) >= 7) ? 7 : 4;     // 4: 128 registers, two waves at 4096 envs; 7: 72 registers (spills), one wave
     }
+    err = cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && err == cudaSuccess; ++k) {
+        err = cudaEventCreateWithFlags(&e->ev_in[k], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_step[k], cudaEventDisableTiming);
+        if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming);
+    }
+    if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, std::string("creating the copy streams: ") + cudaGetErrorString(err)); }
     {
         ColdArgs ca;
         ca.pk = e->pk; ca.cfg = e->cfg; ca.ea = env_arrays(e);
@@ -1033,6 +1052,13 @@ void paintrl_destroy(PaintrlHandle h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    for (int k = 0; k < 2; ++k) {
+        if (h->ev_in[k]) cudaEventDestroy(h->ev_in[k]);
+        if (h->ev_step[k]) cudaEventDestroy(h->ev_step[k]);
+        if (h->ev_done[k]) cudaEventDestroy(h->ev_done[k]);
+    }
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     delete h;
 }
 
@@ -1236,6 +1262,71 @@ int paintrl_step_host(PaintrlHandle h, const void *actions_host, double *obs_hos
     if (want_next && !dev_next) push(next_obs_host, d_obs, obytes);   // no auto-reset: the next observation is this one
     for (int i = 0; i < ns; ++i) CUDA_TRY(cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    return PAINTRL_OK;
+}
+
+int paintrl_step_host_submit(PaintrlHandle h, int32_t slot, const void *actions_host, double *obs_host, double *reward_host,
+                             double *penalty_host, double *actual_host, uint8_t *done_host, double *next_obs_host, void *stream) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (slot < 0 || slot > 1) return fail(PAINTRL_E_INVALID, "slot must be 0 or 1");
+    if (!actions_host || !obs_host || !reward_host || !penalty_host || !actual_host || !done_host)
+        return fail(PAINTRL_E_INVALID, "null I/O buffer");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = as_stream(stream);
+    const size_t nenv = (size_t)h->num_envs;
+    const size_t abytes = (h->cfg.action_mode == 0 ? sizeof(long long) : sizeof(double) * h->cfg.action_shape) * nenv;
+    const size_t obytes = sizeof(double) * h->cfg.obs_dim * nenv;
+    const bool want_next = next_obs_host != nullptr, dev_next = want_next && h->cfg.auto_reset;
+    // a slot that is submitted again before it was waited for: its previous copy-out must have drained first
+    if (h->slot_pending[slot]) {
+        CUDA_TRY(cudaStreamWaitEvent(h->copy_in, h->ev_done[slot], 0));
+        CUDA_TRY(cudaStreamWaitEvent(s, h->ev_done[slot], 0));
+    }
+    // copy-in stream: the actions, then the step on the caller's stream behind it
+    CUDA_TRY(cudaMemcpyAsync(h->slot_actions[slot], actions_host, abytes, cudaMemcpyHostToDevice, h->copy_in));
+    CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->copy_in));
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_in[slot], 0));
+    unsigned char *d = h->slot_out[slot];
+    double *d_obs = reinterpret_cast<double *>(d);
+    double *d_sc = reinterpret_cast<double *>(d + obytes);
+    double *d_next = dev_next ? reinterpret_cast<double *>(d + obytes + 3 * sizeof(double) * nenv) : nullptr;
+    uint8_t *d_done = d + obytes + 3 * sizeof(double) * nenv + (dev_next ? obytes : 0);
+    int rc = paintrl_step(h, h->slot_actions[slot], d_obs, d_sc, d_sc + nenv, d_sc + 2 * nenv, d_done, nullptr, d_next, nullptr, stream);
+    if (rc != PAINTRL_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_step[slot], s));
+    // copy-out stream: the results, as one copy when the host buffers are carved from one allocation in staging order
+    CUDA_TRY(cudaStreamWaitEvent(h->copy_out, h->ev_step[slot], 0));
+    struct Seg { void *dst; const void *src; size_t n; };
+    Seg segs[7] = {};
+    int ns = 0;
+    auto push = [&](void *dst, const void *src, size_t n) {
+        if (ns > 0 && (const char *)segs[ns - 1].src + segs[ns - 1].n == (const char *)src &&
+            (char *)segs[ns - 1].dst + segs[ns - 1].n == (char *)dst) {
+            segs[ns - 1].n += n;
+        } else {
+            segs[ns].dst = dst; segs[ns].src = src; segs[ns].n = n; ++ns;
+        }
+    };
+    push(obs_host, d_obs, obytes);
+    push(reward_host, d_sc, sizeof(double) * nenv);
+    push(penalty_host, d_sc + nenv, sizeof(double) * nenv);
+    push(actual_host, d_sc + 2 * nenv, sizeof(double) * nenv);
+    if (dev_next) push(next_obs_host, d_next, obytes);
+    push(done_host, d_done, nenv);
+    if (want_next && !dev_next) push(next_obs_host, d_obs, obytes);
+    for (int i = 0; i < ns; ++i) CUDA_TRY(cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].n, cudaMemcpyDeviceToHost, h->copy_out));
+    CUDA_TRY(cudaEventRecord(h->ev_done[slot], h->copy_out));
+    h->slot_pending[slot] = true;
+    return PAINTRL_OK;
+}
+
+int paintrl_step_host_wait(PaintrlHandle h, int32_t slot) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (slot < 0 || slot > 1) return fail(PAINTRL_E_INVALID, "slot must be 0 or 1");
+    if (!h->slot_pending[slot]) return fail(PAINTRL_E_STATE, "nothing was submitted on this slot");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->ev_done[slot]));
+    h->slot_pending[slot] = false;
     return PAINTRL_OK;
 }
 

@@ -269,3 +269,43 @@ def test_subset_reset_leaves_the_other_environments_alone(cuda_device):
     assert np.array_equal(env.get_state()['status'].cpu().numpy(), ora.status())
     env.close()
     ora.close()
+
+
+@pytest.mark.parametrize('auto_reset', [True, False])
+def test_pipelined_host_steps_match_synchronous_ones(cuda_device, auto_reset):
+    """paintrl_step_host_submit / _wait on two staging slots: step t + 1 is submitted before step t is waited for
+    (its copy-in and kernels overlap step t's copy-out); every result equals the synchronous paintrl_step_host's."""
+    from paintrl_b200 import _capi
+    from paintrl_b200.batched_env import BatchedPaintEnv
+    n, T = 200, 60
+    cfg = dict(BASE, START_POINT_MODE='edge', OVERLAP_PENALTY=True)
+    a = BatchedPaintEnv(n, cfg, device=cuda_device, auto_reset=auto_reset, seed=21)
+    b = BatchedPaintEnv(n, cfg, device=cuda_device, auto_reset=auto_reset, seed=21)
+    start = (np.arange(n) % a.n_starts).astype(np.int32)
+    a.reset(start)
+    b.reset(start)
+    rng = np.random.default_rng(31)
+    acts = torch.from_numpy(rng.integers(0, 4, size=(T, n))).pin_memory().numpy()
+    outs = [a.host_buffers(pinned=True), a.host_buffers(pinned=True)]
+    ref = b.host_buffers(pinned=True)
+    with pytest.raises(_capi.PaintrlError):
+        a.step_host_wait(0)                          # nothing submitted yet
+    a.step_host_submit(acts[0], outs[0], slot=0)
+    for t in range(T):
+        if t + 1 < T:
+            a.step_host_submit(acts[t + 1], outs[(t + 1) & 1], slot=(t + 1) & 1)
+        got = a.step_host_wait(slot=t & 1)
+        b.step_host(acts[t], ref)
+        for k in ('obs', 'reward', 'penalty', 'actual', 'done', 'next_obs'):
+            assert np.array_equal(got[k], ref[k]), (t, k)
+    # a slot submitted twice without a wait in between drains its first copy-out before it is reused
+    a.step_host_submit(acts[0], outs[0], slot=0)
+    a.step_host_submit(acts[1], outs[0], slot=0)
+    got = a.step_host_wait(0)
+    b.step_host(acts[0], ref)
+    b.step_host(acts[1], ref)
+    for k in ('obs', 'actual', 'done'):
+        assert np.array_equal(got[k], ref[k]), k
+    assert np.array_equal(a.get_state()['status'].cpu().numpy(), b.get_state()['status'].cpu().numpy())
+    a.close()
+    b.close()
