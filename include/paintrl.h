@@ -274,6 +274,33 @@ int paintrl_param_tables(PaintrlParamHandle h, const int32_t *env_ids_dev, int32
 int paintrl_param_stats(PaintrlParamHandle h, uint64_t *env_steps, uint64_t *episodes_ended,
                         uint64_t *kernel_launches, int32_t *bad_action_seen);
 
+/*
+ * The rollout policy of the reference's PPO script (paint_ppo.py:179-183: fully connected obs -> 256 -> 128 ->
+ * {logits | mean, value}, tanh, value branch sharing the hidden layers) evaluated and sampled for a whole batch in
+ * ONE kernel launch per environment step (layer 2 on the tcgen05 tensor cores, BF16 inputs, FP32 accumulation):
+ * observations come straight from paintrl_step's obs buffer, actions go straight into the next paintrl_step.
+ * Weights are host pointers, row-major FP32: w1 [obs_dim][256], b1 [256], w2 [256][128], b2 [128],
+ * w3 [128][n_out + 1] (last column = value head), b3 [n_out + 1].  obs_dim <= 32, n_out <= 15.
+ */
+typedef struct PaintrlPolicyConfig {
+    int32_t abi_version;
+    int32_t obs_dim;
+    int32_t n_out;          /* discrete: number of actions (logits); continuous: action dimensions (means) */
+    int32_t discrete;       /* 1: Gumbel-max sample of the logits (int64 actions); 0: tanh(mean) + unit Gaussian (float64) */
+    int32_t capacity;       /* largest batch (one random-number counter per environment) */
+    uint64_t seed;
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+} PaintrlPolicyConfig;
+typedef struct PaintrlPolicyEngine *PaintrlPolicyHandle;
+
+int paintrl_policy_create(const PaintrlPolicyConfig *cfg, int32_t device, PaintrlPolicyHandle *out);
+void paintrl_policy_destroy(PaintrlPolicyHandle h);
+/* obs_dev float64 [batch, obs_dim]; actions_dev int64 [batch] (discrete) or float64 [batch, n_out]; logp_dev /
+ * value_dev float32 [batch]; logits_dev float32 [batch, n_out + 1] or NULL (logits | means, then the value).
+ * sample = 0 evaluates value (and logits) only -- the bootstrap value at the end of a fragment -- and draws nothing. */
+int paintrl_policy_act(PaintrlPolicyHandle h, const double *obs_dev, int32_t batch, void *actions_dev, float *logp_dev,
+                       float *value_dev, float *logits_dev, int32_t sample, void *stream);
+
 const char *paintrl_last_error(void);
 int32_t paintrl_abi_version(void);
 

@@ -76,6 +76,11 @@ class PaintrlParamConfig(ctypes.Structure):
                 ('termination_by_repeat', ctypes.c_int32), ('obs_mode', ctypes.c_int32), ('auto_reset', ctypes.c_int32)]
 
 
+class PaintrlPolicyConfig(ctypes.Structure):
+    _fields_ = [('abi_version', ctypes.c_int32), ('obs_dim', ctypes.c_int32), ('n_out', ctypes.c_int32), ('discrete', ctypes.c_int32),
+                ('capacity', ctypes.c_int32), ('seed', ctypes.c_uint64)] + [(k, ctypes.POINTER(ctypes.c_float)) for k in ('w1', 'b1', 'w2', 'b2', 'w3', 'b3')]
+
+
 # name -> (restype, argtypes); every symbol include/paintrl.h declares
 _VP = ctypes.c_void_p
 _I32 = ctypes.c_int32
@@ -108,6 +113,9 @@ SIGNATURES = {
     'paintrl_param_tables': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _VP]),
     'paintrl_param_stats': (ctypes.c_int, [_VP, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64),
                                            ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(_I32)]),
+    'paintrl_policy_create': (ctypes.c_int, [ctypes.POINTER(PaintrlPolicyConfig), _I32, ctypes.POINTER(_VP)]),
+    'paintrl_policy_destroy': (None, [_VP]),
+    'paintrl_policy_act': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _VP, _VP, _I32, _VP]),
     'paintrl_last_error': (ctypes.c_char_p, []),
     'paintrl_abi_version': (_I32, []),
 }

@@ -13,6 +13,7 @@
 #include "paintrl_kernels.cuh"
 #include "paintrl_raster.cuh"
 #include "paintrl_param.cuh"
+#include "paintrl_policy.cuh"
 
 using namespace paintrl;
 
@@ -833,6 +834,79 @@ int paintrl_rasterize_texels(const double *tri_a, const double *tri_b, const dou
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(texel_ij_out, d_ij, sizeof(int) * 2 * pix.size(), cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(texel_pos_out, d_pos, sizeof(double) * 3 * pix.size(), cudaMemcpyDeviceToHost));
+    return PAINTRL_OK;
+}
+
+/* ---- the rollout policy (paint_ppo.py:179-183), see paintrl_policy.cuh ---- */
+struct PaintrlPolicyEngine {
+    int device = 0;
+    int capacity = 0;
+    PolicyParams pp{};
+    DeviceArena arena;
+    unsigned long long launches = 0;
+};
+
+int paintrl_policy_create(const PaintrlPolicyConfig *cfg, int32_t device, PaintrlPolicyHandle *out) {
+    if (!cfg || !out) return fail(PAINTRL_E_INVALID, "null argument");
+    if (cfg->abi_version != PAINTRL_ABI_VERSION) return fail(PAINTRL_E_INVALID, "ABI version mismatch");
+    if (cfg->obs_dim <= 0 || cfg->obs_dim > kPolMaxObs) return fail(PAINTRL_E_INVALID, "the policy kernel takes observations of 1..32 entries");
+    if (cfg->n_out <= 0 || cfg->n_out + 1 > kPolMaxOut) return fail(PAINTRL_E_INVALID, "the policy kernel takes 1..15 action outputs");
+    if (cfg->capacity <= 0) return fail(PAINTRL_E_INVALID, "capacity must be positive");
+    if (!cfg->w1 || !cfg->b1 || !cfg->w2 || !cfg->b2 || !cfg->w3 || !cfg->b3) return fail(PAINTRL_E_INVALID, "null weight pointer");
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return fail(PAINTRL_E_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(err));
+    if (device < 0 || device >= count) return fail(PAINTRL_E_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    PaintrlPolicyEngine *e = new PaintrlPolicyEngine();
+    e->device = device;
+    e->capacity = cfg->capacity;
+    PolicyParams &pp = e->pp;
+    pp.obs_dim = cfg->obs_dim; pp.n_out = cfg->n_out; pp.discrete = cfg->discrete ? 1 : 0; pp.seed = cfg->seed;
+    const int nout1 = cfg->n_out + 1;
+    std::vector<float> w1(cfg->w1, cfg->w1 + (size_t)cfg->obs_dim * kPolH1), b1(cfg->b1, cfg->b1 + kPolH1), b2(cfg->b2, cfg->b2 + kPolH2),
+        w3(cfg->w3, cfg->w3 + (size_t)kPolH2 * nout1), b3(cfg->b3, cfg->b3 + nout1);
+    // W2 [256 in][128 out] FP32 -> BF16 B operand [n = out][k = in] in the tensor core's canonical K-major layout
+    std::vector<__nv_bfloat16> w2p((size_t)kPolH1 * kPolH2);
+    for (int n = 0; n < kPolH2; ++n)
+        for (int k = 0; k < kPolH1; ++k) {
+            const size_t byte = (size_t)(k / 8) * (kPolH2 / 8) * 128 + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
+            w2p[byte / 2] = __float2bfloat16_rn(cfg->w2[(size_t)k * kPolH2 + n]);
+        }
+    bool ok = e->arena.upload(w1, &pp.w1) == cudaSuccess && e->arena.upload(b1, &pp.b1) == cudaSuccess &&
+              e->arena.upload(w2p, &pp.w2_packed) == cudaSuccess && e->arena.upload(b2, &pp.b2) == cudaSuccess &&
+              e->arena.upload(w3, &pp.w3) == cudaSuccess && e->arena.upload(b3, &pp.b3) == cudaSuccess &&
+              e->arena.alloc((void **)&pp.counters, sizeof(unsigned) * (size_t)cfg->capacity) == cudaSuccess;
+    if (ok) ok = cudaMemset(pp.counters, 0, sizeof(unsigned) * (size_t)cfg->capacity) == cudaSuccess;
+    if (ok) ok = cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmemBytes) == cudaSuccess;
+    if (!ok) { delete e; cudaGetLastError(); return fail(PAINTRL_E_CUDA, "setting up the policy engine failed (allocation / shared memory opt-in)"); }
+    *out = e;
+    return PAINTRL_OK;
+}
+
+void paintrl_policy_destroy(PaintrlPolicyHandle h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    delete h;
+}
+
+int paintrl_policy_act(PaintrlPolicyHandle h, const double *obs_dev, int32_t batch, void *actions_dev, float *logp_dev, float *value_dev,
+                       float *logits_dev, int32_t sample, void *stream) {
+    if (!h) return fail(PAINTRL_E_INVALID, "null handle");
+    if (!obs_dev || !value_dev || (sample && (!actions_dev || !logp_dev))) return fail(PAINTRL_E_INVALID, "null I/O buffer");
+    if (batch <= 0 || batch > h->capacity) return fail(PAINTRL_E_INVALID, "batch exceeds the policy engine's capacity");
+    CUDA_TRY(cudaSetDevice(h->device));
+    PolicyIO io;
+    io.obs = obs_dev; io.batch = batch;
+    io.act_discrete = h->pp.discrete ? reinterpret_cast<long long *>(actions_dev) : nullptr;
+    io.act_continuous = h->pp.discrete ? nullptr : reinterpret_cast<double *>(actions_dev);
+    io.logp = logp_dev; io.value = value_dev; io.logits = logits_dev; io.sample = sample ? 1 : 0;
+    policy_act_kernel<<<(batch + kPolRows - 1) / kPolRows, kPolThreads, kPolSmemBytes, as_stream(stream)>>>(h->pp, io);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(PAINTRL_E_CUDA, std::string("policy_act_kernel: ") + cudaGetErrorString(err));
+    h->launches++;
     return PAINTRL_OK;
 }
 

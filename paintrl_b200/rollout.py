@@ -10,13 +10,56 @@ the environments live on -- observations and actions never visit the host.
 
 One process per GPU owns a shard of the environments (`sharding.shard_range`); the step path has no
 collective; `iteration_stats` reduces the per-iteration statistics with one small all-reduce.
-The policy is a plain torch MLP (library GEMMs): it is the consumer of the hot path, not part of it.
+The policy runs as ONE kernel of this repository per environment step (`paintrl_policy_act`, csrc/paintrl_policy.cuh:
+layer 2 on the tcgen05 tensor cores, sampling included); a plain torch evaluation of the same weights is kept as the
+FP32 reference the tests compare against and as the path for shapes the kernel does not take (obs_dim > 32).
 """
+import ctypes
 import math
 
+import numpy as np
 import torch
 
-from . import sharding
+from . import _capi, sharding
+
+
+def _fptr(t):
+    return t.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+class NativePolicy(object):
+    """`paintrl_policy_*` (include/paintrl.h): the MLP of paint_ppo.py:179-183 evaluated and sampled in one launch."""
+
+    def __init__(self, obs_dim, n_out, discrete, weights, capacity, device, seed=0):
+        self._lib = _capi.lib()
+        self.device = torch.device(device)
+        self.obs_dim, self.n_out, self.discrete, self.capacity, self.seed = int(obs_dim), int(n_out), bool(discrete), int(capacity), int(seed)
+        host = [np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float32) for w in weights]    # w1 b1 w2 b2 w3 b3
+        cfg = _capi.PaintrlPolicyConfig(_capi.PAINTRL_ABI_VERSION, self.obs_dim, self.n_out, int(self.discrete), self.capacity, self.seed,
+                                        *[_fptr(a) for a in host])
+        handle = ctypes.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _capi.check(self._lib.paintrl_policy_create(ctypes.byref(cfg), index, ctypes.byref(handle)))
+        self._h = handle
+
+    def close(self):
+        if getattr(self, '_h', None):
+            self._lib.paintrl_policy_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def act_into(self, obs, actions, logp, value, logits=None, sample=True):
+        """obs float64 [B, obs_dim] -> actions (int64 [B] | float64 [B, n_out]), logp / value float32 [B], all contiguous
+        CUDA tensors of this device, written in place by one kernel launch on the current stream."""
+        B = obs.shape[0]
+        p = lambda t: None if t is None else ctypes.c_void_p(t.data_ptr())
+        _capi.check(self._lib.paintrl_policy_act(self._h, p(obs), B, p(actions), p(logp), p(value), p(logits), int(bool(sample)),
+                                                 ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
 
 class MlpPolicy(object):
@@ -45,6 +88,27 @@ class MlpPolicy(object):
         self.device = device
         self.gen = torch.Generator(device=device)
         self.gen.manual_seed(seed + 1)
+        self.obs_dim, self.seed = obs_dim, seed
+        self.native = None
+
+    def weights(self):
+        (w1, b1), (w2, b2) = self.layers
+        return [w1, b1, w2, b2, self.head_w, self.head_b]
+
+    def enable_native(self, capacity):
+        """Evaluate and sample with the repository's own kernel (one launch per step) for batches up to `capacity`.
+        Returns False when the shape is outside what the kernel takes (the torch path stays)."""
+        if self.native is not None and self.native.capacity >= capacity:
+            return True
+        if not (self.obs_dim <= 32 and self.n_out + 1 <= 16 and len(self.layers) == 2 and
+                tuple(self.layers[0][0].shape) == (self.obs_dim, 256) and tuple(self.layers[1][0].shape) == (256, 128)):
+            return False
+        self.native = NativePolicy(self.obs_dim, self.n_out, self.discrete, self.weights(), capacity, self.device, seed=self.seed)
+        return True
+
+    def describe(self):
+        return ('one paintrl_policy_act kernel per step: layer 2 on tcgen05 tensor cores (BF16 x BF16 -> FP32), FP32 elsewhere'
+                if self.native is not None else 'torch addmm (TF32) + elementwise kernels')
 
     def forward(self, obs):
         """obs [B, obs_dim] (any float dtype) -> (logits or means [B, n_out], value [B]) in FP32."""
@@ -91,7 +155,7 @@ class RolloutFragment(object):
 class RolloutWorker(object):
     """Collects fragments from a `BatchedPaintEnv` created with `auto_reset=True`."""
 
-    def __init__(self, env, policy, fragment_length=100, use_cuda_graph=False):
+    def __init__(self, env, policy, fragment_length=100, use_cuda_graph=False, use_native_policy=True):
         """`use_cuda_graph`: after one eager fragment, capture the whole T-step loop (policy kernels and the
         two step kernels per step, ~25 launches each) into one CUDA graph and replay it per fragment -- the
         fragment buffers are persistent, so every address in the loop is static.  Small batches are
@@ -99,6 +163,8 @@ class RolloutWorker(object):
         if not env.cfg.auto_reset:
             raise ValueError('RolloutWorker needs an environment created with auto_reset=True')
         self.env, self.policy, self.T = env, policy, int(fragment_length)
+        if use_native_policy and hasattr(policy, 'enable_native'):
+            policy.enable_native(env.num_envs)
         self.use_cuda_graph = bool(use_cuda_graph)
         self._graph, self._eager_fragments, self.graph_error = None, 0, None
         shape = () if env.cfg.action_mode == 'discrete' else (env.action_dim,)
@@ -124,14 +190,22 @@ class RolloutWorker(object):
     def _run_steps(self):
         f, env, pol = self.frag, self.env, self.policy
         f.obs[0].copy_(self._carry)
+        native = pol.native
         for t in range(self.T):
-            a, logp, value = pol.act(f.obs[t])
-            f.actions[t].copy_(a)
-            f.logp[t].copy_(logp)
-            f.value[t].copy_(value)
+            if native is not None:
+                # one launch: obs[t] -> actions[t], logp[t], value[t] written in place (no torch kernels in the loop)
+                native.act_into(f.obs[t], f.actions[t], f.logp[t], f.value[t])
+            else:
+                a, logp, value = pol.act(f.obs[t])
+                f.actions[t].copy_(a)
+                f.logp[t].copy_(logp)
+                f.value[t].copy_(value)
             env.step_into(f.actions[t], f.term_obs[t], f.reward[t], f.penalty[t], f.actual[t], f.done[t],
                           next_obs=f.obs[t + 1], new_texels=f.new_texels[t])
-        f.value[self.T].copy_(pol.forward(f.obs[self.T])[1])      # bootstrap value of the truncated episodes
+        if native is not None:
+            native.act_into(f.obs[self.T], None, None, f.value[self.T], sample=False)     # bootstrap value of the truncated episodes
+        else:
+            f.value[self.T].copy_(pol.forward(f.obs[self.T])[1])
         self._carry.copy_(f.obs[self.T])
 
     def _capture(self):
