@@ -62,6 +62,10 @@ WORKLOADS = {
                extra=dict(BASE, START_POINT_MODE='all'),
                kw=dict(action_mode='continuous', action_shape=2, obs_mode='grid', obs_grad=4),
                texture=(2048, 2048), envs_per_gpu=8192, scaling='weak'),
+    # Robot.PAINT_METHOD = 'normal' -- a fan of 124 rays per shot instead of the ball query
+    'c2_normal': dict(name='C2 settings with the normal paint method (robot.py:172, 414-417: 124-ray beam fan per shot, nearest texel per hit), '
+                           'door panel x4096 envs/GPU',
+                      extra=dict(BASE), kw=dict(paint_method='normal'), envs_per_gpu=4096, scaling='weak'),
     # configs[4] env side: 65536 envs sharded over the GPUs (strong scaling)
     'c5': dict(name='C5 door panel, 65536 envs sharded over N GPUs, C2 settings',
                extra=dict(BASE), kw={}, envs_total=65536, scaling='strong'),
@@ -600,7 +604,7 @@ def main():
     # ---- the other BASELINE configurations, fewer steps each (N > 1: only the strong-scaling C5)
     extras = {}
     if not args.no_extra and args.workload == 'c2' and args.envs is None:
-        keys = ['c3', 'c3_late', 'c4', 'c5'] if world_size == 1 else ['c5']
+        keys = ['c3', 'c3_late', 'c4', 'c5', 'c2_normal'] if world_size == 1 else ['c5']
         xsteps = max(10, min(args.steps, 60))
         for k in keys:
             try:

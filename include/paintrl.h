@@ -46,6 +46,8 @@ enum { PAINTRL_OBS_SECTION = 0, PAINTRL_OBS_GRID = 1, PAINTRL_OBS_SIMPLE = 2, PA
 /* robot_gym_env.py:134-157 extra_config */
 enum { PAINTRL_COLOR_RGB = 0, PAINTRL_COLOR_HSI = 1 };
 enum { PAINTRL_TERM_LATE = 0, PAINTRL_TERM_EARLY = 1, PAINTRL_TERM_HYBRID = 2 };
+/* robot.py:172 Robot.PAINT_METHOD */
+enum { PAINTRL_PAINT_FAST = 0, PAINTRL_PAINT_NORMAL = 1 };
 
 /*
  * Constant per-part tables, all host pointers, row-major, FP64
@@ -91,6 +93,12 @@ typedef struct PaintrlPartPack {
     const double *start_normal;   /* [n_starts,3] */
 
     int32_t status_init;          /* first-channel value of a fresh front texel: 191 RGB / 255 HSI (:586) */
+
+    /* PAINTRL_PAINT_NORMAL only (may be NULL otherwise): for every front texel, the texel that the reference's
+     * cKDTree.query(k = 1) (bullet_paint_wrapper.py:565) returns among the texels sharing its exact 3-D position (UV
+     * seams map a few texels to the same point: 109 groups on the door).  Which twin the kd-tree reports is fixed
+     * by the tree's leaf order, not by the query, so it is a constant table; identity for unique positions. */
+    const int32_t *texel_nn_rep;  /* [n_texels] */
 } PaintrlPartPack;
 
 /* Everything PaintGymEnv reads at construction (robot_gym_env.py:126-157, 240-252). */
@@ -120,6 +128,15 @@ typedef struct PaintrlConfig {
      *    then reset and the first observation of the new episode goes to `next_obs`.          */
     int32_t auto_reset;
     uint64_t seed;                  /* start-index stream for auto-reset (uniform over n_starts) */
+    /* Robot.PAINT_METHOD (robot.py:172, 414-417).  PAINTRL_PAINT_FAST: every shot is the ball query of its centre
+     * (Part.fast_paint, bullet_paint_wrapper.py:568-570) -- the reference's default.  PAINTRL_PAINT_NORMAL: every shot
+     * casts the beam fan `beam_plain` from the TCP (Robot._paint / _generate_paint_beams, robot.py:251-258, 280-285)
+     * and paints the texel nearest to each hit (Part.paint, bullet_paint_wrapper.py:562-566).
+     * beam_plain: host float64 [n_beams, 3], the ray end points in the TCP frame (Robot._paint_plain: the uniform
+     * disc of robot.py:23-36 for RGB, the beta-distributed rings of :39-69 for HSI; both at z = 0.2). */
+    int32_t paint_method;
+    int32_t n_beams;
+    const double *beam_plain;
 } PaintrlConfig;
 
 typedef struct PaintrlEngine *PaintrlHandle;

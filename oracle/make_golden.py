@@ -356,8 +356,12 @@ def _save(name, ref, rec, kw, note):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     cfg = dict(extra_config=ref.extra_config, note=note, n_start_points=len(ref.env._start_points),
                part=PART_NAMES[ref.extra_config['Part_NO']], **kw)
+    extra = {}
+    if kw.get('paint_method') == 'normal':
+        # Robot._paint_plain as the reference built it (robot.py:244-249; the HSI table draws from `random`)
+        extra['beam_plain'] = np.array(ref.env.robot._paint_plain, dtype=np.float64).reshape(-1, 3)
     np.savez_compressed(os.path.join(GOLDEN_DIR, name + '.npz'), config=json.dumps(cfg),
-                        **_pack_episodes(rec.episodes))
+                        **_pack_episodes(rec.episodes), **extra)
     return name
 
 
@@ -509,6 +513,34 @@ def g9_door_discrete20_grid10():
     for e in range(4):
         rec.run_episode(0, _random_discrete(rng, 20), 150)
     return _save('g9_door_discrete20_grid10', ref, rec, kw, 'discrete-20, grid-10, hybrid')
+
+
+@job
+def g11_door_normal_rgb():
+    """Robot.PAINT_METHOD = 'normal' (robot.py:172, 414-417): door, RGB, beam fan per shot, overlap penalty."""
+    kw = dict(action_mode='discrete', action_shape=1, discrete_granularity=4, obs_mode='section',
+              obs_grad=4, rollout=False, paint_method='normal')
+    ref, rec = _make({'Part_NO': 0, 'START_POINT_MODE': 'anchor', 'OVERLAP_PENALTY': True}, **kw)
+    rng = np.random.default_rng(11)
+    rec.run_episode(0, _zigzag_policy_simple({'up': True, 'h': 0}), 40)
+    for e in range(3):
+        rec.run_episode(1 + e, _random_discrete(rng, 4), 40)
+    return _save('g11_door_normal_rgb', ref, rec, kw, 'normal paint method, RGB, 4 episodes of <= 40 steps')
+
+
+@job
+def g12_sheet_normal_hsi():
+    """Normal paint method with the HSI handler (beta-distributed beam rings, one subtraction per beam hit): sheet,
+    both penalties, continuous 2-D actions."""
+    kw = dict(action_mode='continuous', action_shape=2, obs_mode='section', obs_grad=4, rollout=False, paint_method='normal')
+    ref, rec = _make({'Part_NO': 1, 'START_POINT_MODE': 'anchor', 'COLOR_MODE': 'HSI', 'TURNING_PENALTY': True,
+                      'OVERLAP_PENALTY': True}, **kw)
+    rng = np.random.default_rng(12)
+    seq = ([[0, 1]] * 8 + [[0, -1]] * 8) * 2
+    rec.run_episode(0, lambda obs, t: seq[t] if t < len(seq) else None, 40)
+    for e in range(2):
+        rec.run_episode(1 + e, _random_box(rng, 2), 30)
+    return _save('g12_sheet_normal_hsi', ref, rec, kw, 'normal paint method, HSI, repeated coats + random walks')
 
 
 def _run(name):

@@ -105,8 +105,8 @@ class OracleBatch(object):
         self.pack, self.cfg, self.num_envs = pack, cfg, int(num_envs)
         self.threads = int(threads or os.cpu_count() or 1)
         self._h = lib()
-        self._cpack, self._keep_pack = pack.to_c(cfg.start_point_mode, cfg.color_mode)
-        self._ccfg, self._keep_cfg = cfg.to_c(pack.max_points)
+        self._cpack, self._keep_pack = pack.to_c(cfg.start_point_mode, cfg.color_mode, with_nn_rep=cfg.paint_method == 'normal')
+        self._ccfg, self._keep_cfg = cfg.to_c(pack.max_points, density=pack.meta.get('density'))
         self.envs = []
         for _ in range(self.num_envs):
             e = self._h.oracle_create(ctypes.byref(self._cpack), ctypes.byref(self._ccfg))

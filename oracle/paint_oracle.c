@@ -60,6 +60,7 @@ typedef struct OracleEnv {
     uint8_t *affected;         /* scratch */
     uint8_t *possible;         /* scratch: robot.py:401 possible_pixels */
     double *dist;              /* scratch: HSI distances */
+    int32_t *beam_texel;       /* scratch (normal paint): nearest texel of every beam that hit, in beam order */
     /* Robot state (robot.py:201-218, 235-242) */
     double pose[3], orn[4];
     int terminate, terminate_counter, last_on_part;
@@ -420,6 +421,68 @@ static double fast_paint(OracleEnv *e, const double *center, int *n_valid_out) {
     return succeed;
 }
 
+/* Robot._paint (robot.py:280-285) + Part.paint / _paint (bullet_paint_wrapper.py:562-566, 572-577): the beam fan of
+ * the TCP (robot.py:251-258: every point of Robot._paint_plain, given in the TCP frame, is a ray end point), the hits
+ * on the part (shim S1 rayTestBatch), the texel nearest to each hit (cKDTree.query, k = 1: brute force here), and the
+ * colour handlers on that list -- duplicates included: RGB repaints are no-ops (:358-365), HSI subtracts once per
+ * occurrence while the texel is still above 0 (:411-434).  Uses e->pose / e->orn of the current sub-step. */
+static double normal_paint(OracleEnv *e, const double *center, int *n_valid_out) {
+    const PaintrlPartPack *p = &e->pack;
+    const int n = e->n;
+    int n_hits = 0;
+    for (int b = 0; b < e->cfg.n_beams; ++b) {
+        double dst[3], hit[3];
+        transform_point(e->pose, e->orn, e->cfg.beam_plain + 3 * b, dst);   /* _get_tcp_point_in_world */
+        if (!ray_test(p, e->pose, dst, hit)) continue;
+        int best = -1;
+        double best_d = INFINITY;
+        for (int i = 0; i < n; ++i) {
+            const double *c = p->texel_pos + 3 * i;
+            double dx = c[0] - hit[0], dy = c[1] - hit[1], dz = c[2] - hit[2];
+            double d = dx * dx + dy * dy + dz * dz;
+            if (d < best_d) { best_d = d; best = i; }
+        }
+        if (p->texel_nn_rep) best = p->texel_nn_rep[best];    /* twins at the same position: the kd-tree's pick */
+        e->beam_texel[n_hits++] = best;
+    }
+    *n_valid_out = 0;
+    if (n_hits == 0) return 0;                 /* Part.paint: `if not points: return [], 0` -- the last set is kept */
+    memset(e->affected, 0, (size_t)n);
+    double succeed = 0;
+    if (e->cfg.color_mode == PAINTRL_COLOR_RGB) {
+        for (int k = 0; k < n_hits; ++k) {
+            int i = e->beam_texel[k];
+            if (e->status[i] != PAINTED) { e->status[i] = PAINTED; succeed += 1; }
+            e->affected[i] = 1;
+        }
+    } else {
+        double rmax = 0;
+        for (int k = 0; k < n_hits; ++k) {
+            const double *c = p->texel_pos + 3 * e->beam_texel[k];
+            double ex = fabs(center[0] - c[0]), ey = fabs(center[1] - c[1]), ez = fabs(center[2] - c[2]);
+            double dist = sqrt((ex * ex + ey * ey) + ez * ez);
+            e->dist[k] = dist;
+            if (k == 0 || dist > rmax) rmax = dist;
+        }
+        if (rmax == 0) e->anomalies += 1;      /* 0 / 0: the reference would raise on int(nan) */
+        for (int k = 0; k < n_hits; ++k) {
+            int i = e->beam_texel[k];
+            double ratio = e->dist[k] / rmax;
+            int quantity = (int)(HSI_TARGET_MAX * pow(1 - pow(ratio, 2.0), 1.0)) + 1;
+            e->affected[i] = 1;
+            if (e->status[i] <= 0) continue;
+            e->status[i] = (int16_t)(e->status[i] - quantity);
+            succeed += quantity / 255.0;
+        }
+    }
+    int n_valid = 0;
+    for (int i = 0; i < n; ++i)
+        if (e->affected[i] && !e->last_affected[i]) { e->possible[i] = 1; n_valid++; }
+    memcpy(e->last_affected, e->affected, (size_t)n);
+    *n_valid_out = n_valid;
+    return succeed;
+}
+
 /* ---------------------------------------------------------------------------------- API */
 OracleEnv *oracle_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg) {
     OracleEnv *e = (OracleEnv *)calloc(1, sizeof(OracleEnv));
@@ -438,14 +501,16 @@ OracleEnv *oracle_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg) 
     e->last_affected = (uint8_t *)calloc(e->n, 1);
     e->affected = (uint8_t *)calloc(e->n, 1);
     e->possible = (uint8_t *)calloc(e->n, 1);
-    e->dist = (double *)calloc(e->n, sizeof(double));
+    e->dist = (double *)calloc((size_t)(e->n > cfg->n_beams ? e->n : cfg->n_beams) + 1, sizeof(double));
+    e->beam_texel = (int32_t *)calloc((size_t)(cfg->n_beams > 0 ? cfg->n_beams : 1), sizeof(int32_t));
+    if (cfg->paint_method == PAINTRL_PAINT_NORMAL && (cfg->n_beams <= 0 || !cfg->beam_plain)) { free(e); return NULL; }
     if (cfg->obs_mode == PAINTRL_OBS_GRID && !build_grid_cells(e)) { free(e); return NULL; }
     return e;
 }
 
 void oracle_destroy(OracleEnv *e) {
     if (!e) return;
-    free(e->status); free(e->last_affected); free(e->affected); free(e->possible); free(e->dist);
+    free(e->status); free(e->last_affected); free(e->affected); free(e->possible); free(e->dist); free(e->beam_texel);
     free(e->grid_cell); free(e->grid_total);
     free(e);
 }
@@ -523,7 +588,8 @@ void oracle_step(OracleEnv *e, double u1, double u2, double *obs, double *reward
         double center[3];
         transform_point(e->pose, e->orn, shot, center);     /* _get_shot_center :277-278 */
         int n_valid;
-        succeeded_counter += fast_paint(e, center, &n_valid);
+        succeeded_counter += e->cfg.paint_method == PAINTRL_PAINT_NORMAL ? normal_paint(e, center, &n_valid)   /* robot.py:414-417 */
+                                                                        : fast_paint(e, center, &n_valid);
         extended += n_valid;
     }
     int pixel_counter = 0;

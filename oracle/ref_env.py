@@ -90,8 +90,9 @@ class ReferenceEnv(object):
 
     def __init__(self, extra_config=None, action_mode='discrete', action_shape=1,
                  discrete_granularity=4, obs_mode='section', obs_grad=4, rollout=False,
-                 quiet=True):
+                 quiet=True, paint_method='fast'):
         self.bpw, self.rob, self.rge = load_reference_modules()
+        self.rob.Robot.PAINT_METHOD = paint_method          # robot.py:172 (a class constant edited in source upstream)
         cfg = dict(DEFAULT_EXTRA_CONFIG)
         if extra_config:
             cfg.update(extra_config)

@@ -40,6 +40,7 @@ class PaintrlPartPack(ctypes.Structure):
         ('n_starts', ctypes.c_int32),
         ('start_pos', c_double_p), ('start_normal', c_double_p),
         ('status_init', ctypes.c_int32),
+        ('texel_nn_rep', c_int32_p),
     ]
 
 
@@ -62,6 +63,9 @@ class PaintrlConfig(ctypes.Structure):
         ('max_possible_point', ctypes.c_double),
         ('auto_reset', ctypes.c_int32),
         ('seed', ctypes.c_uint64),
+        ('paint_method', ctypes.c_int32),
+        ('n_beams', ctypes.c_int32),
+        ('beam_plain', c_double_p),
     ]
 
 

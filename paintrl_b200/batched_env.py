@@ -43,8 +43,8 @@ class BatchedPaintEnv(object):
         self.pack = pack if pack is not None else PartPack.for_part(self.cfg.part_no, *texture_size, device=dev_index)
         self.num_envs = int(num_envs)
         self._lib = _capi.lib()
-        cpack, keep_pack = self.pack.to_c(self.cfg.start_point_mode, self.cfg.color_mode)
-        ccfg, keep_cfg = self.cfg.to_c(self.pack.max_points)
+        cpack, keep_pack = self.pack.to_c(self.cfg.start_point_mode, self.cfg.color_mode, with_nn_rep=self.cfg.paint_method == 'normal')
+        ccfg, keep_cfg = self.cfg.to_c(self.pack.max_points, density=self.pack.meta.get('density'))
         handle = ctypes.c_void_p()
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         with torch.cuda.device(index):

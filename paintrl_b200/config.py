@@ -82,12 +82,56 @@ def discrete_table(n):
     return table
 
 
+def uniform_paint_plain(point_density):
+    """Robot._paint_plain for RGB: `_get_uniformed_plain(density)` (robot.py:14-36) -- the grid points of pitch
+    1.8 / sqrt(density) inside a disc of radius 0.1 at z = 0.2 in the TCP frame.  The two running coordinates are
+    accumulated with repeated float additions exactly like the reference's while loops, so the table is bit-identical."""
+    projection_distance = 0.2
+    ratio = projection_distance / 0.5
+    radius = 0.25 * ratio
+    resolution = 1.8 / math.sqrt(point_density)
+    points = []
+    i = -radius
+    while i <= radius:
+        j = -radius
+        while j <= radius:
+            if math.sqrt(math.pow(i, 2) + math.pow(j, 2)) <= radius:
+                points.append((i, j, projection_distance))
+            j += resolution
+        i += resolution
+    return np.array(points, dtype=np.float64).reshape(-1, 3)
+
+
+def beta_paint_plain(beta, point_density, rng=None):
+    """Robot._paint_plain for HSI: `_get_beta_plain(beta, density)` (robot.py:39-69) -- rings of width
+    1.8 / sqrt(density) up to radius 0.1, ring i holding round(450 * w_i / sum w) points with
+    w_i = (1 - (i / circles)^2)^(beta - 1), each at a radius drawn uniformly inside its ring (the reference draws from
+    the process-global `random.uniform`; pass `rng` -- anything with `.uniform(a, b)` -- for a reproducible table)."""
+    import random as _random
+    rng = rng or _random
+    radius = 0.25 * (0.2 / 0.5)
+    resolution = 1.8 / math.sqrt(point_density)
+    circles = math.ceil(radius / resolution)
+    weights = {i: (1 - (i / circles) ** 2) ** (beta - 1) for i in range(1, circles + 1)}
+    total = sum(weights.values())
+    counts = {i: round(450 * w / total) for i, w in weights.items()}
+    points = []
+    for i in range(1, circles + 1):
+        lower, upper = (i - 1) * resolution, i * resolution
+        step = 2 * math.pi / counts[i] if counts[i] else 0
+        for j in range(counts[i]):
+            r = rng.uniform(lower, upper)
+            theta = j * step
+            points.append((r * np.cos(theta), r * np.sin(theta), 0.2))
+    return np.array(points, dtype=np.float64).reshape(-1, 3)
+
+
 class EnvConfig(object):
     """One immutable configuration of the batched environment."""
 
     def __init__(self, extra_config=None, action_mode='discrete', action_shape=1,
                  discrete_granularity=4, obs_mode='section', obs_grad=4, auto_reset=False, seed=0,
-                 max_possible_point=None):
+                 max_possible_point=None, paint_method='fast', beam_plain=None):
         cfg = DEFAULT_EXTRA_CONFIG if extra_config is None else extra_config
         # every key is required, like robot_gym_env.py:240-252
         self.render_width = cfg['RENDER_WIDTH']
@@ -117,7 +161,23 @@ class EnvConfig(object):
         self.auto_reset = bool(auto_reset)
         self.seed = int(seed)
         self.max_possible_point = max_possible_point
+        # Robot.PAINT_METHOD (robot.py:172): 'fast' (ball query per shot) or 'normal' (beam fan per shot).  `beam_plain`
+        # [n, 3] is Robot._paint_plain; None derives it from the part's texel density at engine construction
+        # (robot_gym_env.py:284-285: uniform disc for RGB, beta rings -- seeded with `seed` -- for HSI)
+        if paint_method not in ('fast', 'normal'):
+            raise ValueError('PAINT_METHOD %r' % (paint_method,))
+        self.paint_method = paint_method
+        self.beam_plain = None if beam_plain is None else np.ascontiguousarray(beam_plain, dtype=np.float64).reshape(-1, 3)
         self.extra_config = dict(cfg)
+
+    def paint_plain(self, density):
+        """Robot.set_up_paint_params (robot.py:244-249): the beam table for this colour mode."""
+        if self.beam_plain is not None:
+            return self.beam_plain
+        if self.color_mode == 'RGB':
+            return uniform_paint_plain(density)
+        import random as _random
+        return beta_paint_plain(2, density, rng=_random.Random(self.seed))
 
     @property
     def obs_dim(self):
@@ -127,8 +187,9 @@ class EnvConfig(object):
     def action_dim(self):
         return self.action_shape if self.action_mode == 'continuous' else 1
 
-    def to_c(self, max_possible_point):
-        """Build the `PaintrlConfig` struct; returns (struct, keepalive)."""
+    def to_c(self, max_possible_point, density=None):
+        """Build the `PaintrlConfig` struct; returns (struct, keepalive).  `density`: the part's texel density
+        (Part.get_side_density, bullet_paint_wrapper.py:830-839), needed to derive the beam table in normal mode."""
         c = _capi.PaintrlConfig()
         c.abi_version = _capi.PAINTRL_ABI_VERSION
         c.action_mode = 0 if self.action_mode == 'discrete' else 1
@@ -149,4 +210,16 @@ class EnvConfig(object):
         c.max_possible_point = float(mpp)
         c.auto_reset = int(self.auto_reset)
         c.seed = self.seed
-        return c, [table]
+        keep = [table]
+        c.paint_method = 0
+        c.n_beams = 0
+        c.beam_plain = None
+        if self.paint_method == 'normal':
+            if self.beam_plain is None and not density:
+                raise ValueError('PAINT_METHOD normal needs a beam table or the part\'s texel density')
+            plain = np.ascontiguousarray(self.paint_plain(density), dtype=np.float64)
+            c.paint_method = 1
+            c.n_beams = int(plain.shape[0])
+            c.beam_plain = plain.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+            keep.append(plain)
+        return c, keep

@@ -79,6 +79,9 @@ struct PaintrlEngine {
     int16_t *thick = nullptr;        // [num_envs][n_slots] HSI thickness plane (HSI only)
     unsigned *grid_cnt = nullptr;    // [num_envs][n_gcells_pad] (grid observation only)
     unsigned long long *stats = nullptr;
+    ShotPoses *shots = nullptr;      // [num_envs] normal paint method: pose / orientation of the step's five shots
+    unsigned *last_mask = nullptr;   // [num_envs][n_words_pad] normal paint method: texels of the previous shot
+    bool paint_normal = false;
     unsigned *ready = nullptr;       // [num_envs] per-environment move -> paint hand-off flags: 1 = this step's move output is published;
                                      // the paint warp clears it.  All steps of one handle must be issued on ONE stream (or ordered streams).
     // PAINTRL_CARVEOUT=<percent>: ask for the same L1 / shared-memory split for both step kernels, so that paint CTAs can
@@ -545,6 +548,19 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
     CUDA_TRY(e->arena.upload(word_info, &pk.word_info));
     CUDA_TRY(e->arena.upload(slot_to_pack, &pk.slot_to_pack));
     CUDA_TRY(e->arena.upload(pack_to_slot, &pk.pack_to_slot));
+    {   // normal paint method: the kd-tree's twin among texels at one position (PaintrlPartPack::texel_nn_rep), per slot
+        std::vector<int> rep(pk.n_slots, 0);
+        for (int j = 0; j < pk.n_slots; ++j) {
+            const int t = slot_to_pack[j];
+            int r = t;
+            if (t >= 0 && pack->texel_nn_rep) {
+                r = pack->texel_nn_rep[t];
+                if (r < 0 || r >= n) return fail(PAINTRL_E_INVALID, "texel_nn_rep out of range");
+            }
+            rep[j] = t >= 0 ? pack_to_slot[r] : j;
+        }
+        CUDA_TRY(e->arena.upload(rep, &pk.nn_rep_slot));
+    }
 
     // ---- grid-observation cells (bullet_paint_wrapper.py:1072-1112)
     std::vector<uint16_t> gcell(pk.n_slots, 0);
@@ -657,6 +673,8 @@ EnvArrays env_arrays(PaintrlEngine *e) {
     ea.thick = e->thick;
     ea.grid_cnt = e->grid_cnt;
     ea.ready = e->ready;
+    ea.shots = e->shots;
+    ea.last_mask = e->last_mask;
     return ea;
 }
 
@@ -1040,6 +1058,17 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     c.expected_avg_reward = cfg->max_possible_point / (double)(cfg->expected_episode_length * 100);
     c.hybrid_threshold = cfg->switch_threshold * cfg->max_possible_point / 100;
     c.auto_reset = cfg->auto_reset;
+    c.paint_method = cfg->paint_method == PAINTRL_PAINT_NORMAL ? 1 : 0;
+    c.n_beams = 0;
+    c.beam_plain = nullptr;
+    if (c.paint_method == 1) {
+        if (cfg->n_beams <= 0 || cfg->n_beams > kMaxBeams || !cfg->beam_plain) { delete e; return fail(PAINTRL_E_INVALID, "the normal paint method needs a beam table of 1..512 rays"); }
+        if (e->pk.n_words_pad > kStageWords) { delete e; return fail(PAINTRL_E_INVALID, "the normal paint method supports textures of up to 16384 front texels"); }
+        std::vector<double> plain(cfg->beam_plain, cfg->beam_plain + 3 * (size_t)cfg->n_beams);
+        if (e->arena.upload(plain, &c.beam_plain) != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, "upload beam table"); }
+        c.n_beams = cfg->n_beams;
+        e->paint_normal = true;
+    }
     { const char *bm = getenv("PAINTRL_DEBUG_BAIL_MOD"); c.debug_bail_mod = bm ? std::max(0, atoi(bm)) : 0; }
     c.seed = cfg->seed;
 
@@ -1056,6 +1085,8 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
               (gcnt_bytes == 0 || e->arena.alloc((void **)&e->grid_cnt, gcnt_bytes) == cudaSuccess) &&
               e->arena.alloc((void **)&e->stats, 8 * sizeof(unsigned long long)) == cudaSuccess &&
               e->arena.alloc((void **)&e->ready, sizeof(unsigned) * (size_t)num_envs) == cudaSuccess &&
+              (!e->paint_normal || (e->arena.alloc((void **)&e->shots, sizeof(ShotPoses) * (size_t)num_envs) == cudaSuccess &&
+                                    e->arena.alloc((void **)&e->last_mask, bits_bytes) == cudaSuccess)) &&
               e->arena.alloc((void **)&reset_obs, sizeof(double) * od * (size_t)e->pk.n_starts) == cudaSuccess &&
               e->arena.alloc(&e->stage_actions, adim * num_envs) == cudaSuccess &&
               e->arena.alloc(&e->slot_actions[0], adim * num_envs) == cudaSuccess &&
@@ -1075,6 +1106,8 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
     if (err == cudaSuccess && e->grid_cnt) err = cudaMemset(e->grid_cnt, 0, gcnt_bytes);
     if (err == cudaSuccess) err = cudaMemset(e->stats, 0, 8 * sizeof(unsigned long long));
     if (err == cudaSuccess) err = cudaMemset(e->ready, 0, sizeof(unsigned) * (size_t)num_envs);
+    if (err == cudaSuccess && e->paint_normal) err = cudaMemset(e->shots, 0, sizeof(ShotPoses) * (size_t)num_envs);
+    if (err == cudaSuccess && e->paint_normal) err = cudaMemset(e->last_mask, 0, bits_bytes);
     if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, std::string("initialising device state: ") + cudaGetErrorString(err)); }
     // observation of a fresh environment at every start point, from environment 0's all-zero planes
     e->pk.reset_obs = reset_obs;
@@ -1188,6 +1221,24 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
     io.actual = actual_dev; io.done = done_dev; io.new_texels = new_texels_dev;
     io.next_obs = h->cfg.auto_reset ? next_obs_dev : nullptr;
     io.reset_start_idx = reset_start_idx_dev;
+    if (h->paint_normal) {
+        // Robot.PAINT_METHOD == 'normal': the generic move kernel (it also hands over the shots' poses), then the beam-fan
+        // paint kernel, one warp per environment
+        cudaStream_t ns = as_stream(stream);
+        const int threads = 128;
+        move_kernel<32, 4, false><<<(h->num_envs * 32 + threads - 1) / threads, threads, 0, ns>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, actions_dev);
+        int rc = launch_check(h, "move_kernel");
+        if (rc != PAINTRL_OK) return rc;
+        if (h->color == 0) paint_normal_kernel<0><<<h->num_envs, 32, 0, ns>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io, (const ColdArgs *)h->cold_args);
+        else paint_normal_kernel<1><<<h->num_envs, 32, 0, ns>>>(h->pk, h->cfg, env_arrays(h), h->num_envs, io, (const ColdArgs *)h->cold_args);
+        cudaError_t nerr = cudaGetLastError();
+        if (nerr != cudaSuccess) {
+            cudaMemsetAsync(h->ready, 0, sizeof(unsigned) * (size_t)h->num_envs, ns);
+            return fail(PAINTRL_E_CUDA, std::string("paint_normal_kernel: ") + cudaGetErrorString(nerr));
+        }
+        h->launches++;
+        return PAINTRL_OK;
+    }
     const bool use_fused = h->fused >= 0 ? h->fused == 1 : h->num_envs < kFusedBelowEnvs;
     if (use_fused) {
         // one launch, one warp per environment for the whole step (paintrl_kernels.cuh step_fused_kernel)

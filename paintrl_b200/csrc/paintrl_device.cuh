@@ -105,6 +105,14 @@ struct alignas(128) MoveOut {
 };
 static_assert(sizeof(MoveOut) == 128, "MoveOut must be one 128-byte line");
 
+// Normal paint method: what the move kernel hands over per shot besides the centre -- the TCP pose and orientation
+// the beam fan is cast from (Robot._generate_paint_beams, robot.py:251-258).
+struct alignas(32) ShotPoses {
+    double pos[kPaintPerAction][3];
+    double quat[kPaintPerAction][4];
+    double pad;
+};
+
 // Per-environment counters behind paintrl_stats (summed on request; no atomics on the step path).
 struct alignas(64) EnvStat {
     unsigned long long episodes_ended, footprint_texels, full_scans, env_steps;
@@ -183,6 +191,7 @@ struct DevPack {
     const uint16_t *gcell;        // [n_slots] grid-observation cell (grid mode only)
     const int *slot_to_pack;      // [n_slots] part-pack texel index, -1 for pad slots
     const int *pack_to_slot;      // [n_texels]
+    const int *nn_rep_slot;       // [n_slots] normal paint: the slot cKDTree.query reports among texels at this slot's exact position
     // grid observation (bullet_paint_wrapper.py:1072-1112)
     int n_gcells, n_gcells_pad;
     const int *gtotal;            // [obs_grad^2]
@@ -208,6 +217,9 @@ struct DevConfig {
     double expected_avg_reward;     // max_possible_point / (Expected_Episode_Length * 100)   (robot_gym_env.py:297)
     double hybrid_threshold;        // SWITCH_THRESHOLD * max_possible_point / 100            (robot_gym_env.py:302)
     int auto_reset;
+    int paint_method;               // 0 fast (ball query per shot), 1 normal (beam fan per shot; robot.py:172, 414-417)
+    int n_beams;
+    const double *beam_plain;       // [n_beams][3] Robot._paint_plain, ray end points in the TCP frame
     int debug_bail_mod;             // PAINTRL_DEBUG_BAIL_MOD=n (tests): every n-th environment leaves the fast move kernel at once
     unsigned long long seed;
 };

@@ -44,6 +44,8 @@ struct EnvArrays {
     int16_t *thick;        // [num_envs][n_slots]      HSI thickness (HSI only)
     unsigned *grid_cnt;    // [num_envs][n_gcells_pad] flipped texels per grid-observation cell (grid mode only)
     unsigned *ready;       // [num_envs] 1 once the step's move phase of the environment has been published (paint consumes it)
+    ShotPoses *shots;      // [num_envs] normal paint method only: pose / orientation of the five shots
+    unsigned *last_mask;   // [num_envs][n_words_pad] normal paint method only: Part._last_painted_pixels as a slot mask
 };
 
 // Words of the per-environment bit-plane a warp stages in shared memory (one TMA bulk copy in,
@@ -748,6 +750,230 @@ __device__ __forceinline__ void stamp(const DevPack &pk, const Ax &ax, const BIT
     __syncwarp();
 }
 
+// ------------------------------------------------------------------------------ stamp, normal paint method
+// Robot._paint (robot.py:280-285) + Part.paint (bullet_paint_wrapper.py:562-566): per shot a fan of n_beams rays from
+// the TCP (Robot._paint_plain in the TCP frame, robot.py:251-258), the hits on the hull, the texel nearest to every hit
+// (cKDTree.query, k = 1) and the colour handlers on that list -- duplicates included.  One lane per beam.
+//   * ray: the move cell under the beam's expected entry point supplies a short plane list; the entry point lying in
+//     that cell's region proves the list sufficient (ray_test's argument (2a)); otherwise all planes are scanned.
+//     Max / min over planes are order-independent, so the hit is the serial scan's bit for bit.
+//   * nearest texel: the 3 x (2R + 1) block of texel rows / cells around the hit, exact FP64 squared distances,
+//     accepted when the best beats the distance to the block's border (every other texel is farther); else a wider
+//     block, else all slots.  Texels sharing one position resolve to the kd-tree's twin (nn_rep_slot).
+constexpr int kMaxBeams = 512;
+
+struct alignas(16) NormalScratch {
+    double pos[kPaintPerAction][3];
+    double quat[kPaintPerAction][4];
+    unsigned shot_mask[kStageWords];       // texels the current shot touched
+    unsigned possible[kStageWords];        // union over the step's shots of (affected \ last affected)
+    uint16_t beam_slot[kMaxBeams];         // nearest texel (slot) per beam, 0xFFFF = the beam missed
+    double beam_q[kMaxBeams];              // HSI: distance of that texel to the shot centre
+};
+
+__device__ __forceinline__ void slab_serial(const double2 *planes, int n, const Vec3 &frm, double d0, double d1, double d2, double &t_in,
+                                            double &t_out, bool &outside) {
+    t_in = -INFINITY; t_out = INFINITY; outside = false;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+        const double2 lo = __ldg(planes + 2 * i), hi2 = __ldg(planes + 2 * i + 1);
+        const double den = (lo.x * d0 + lo.y * d1) + hi2.x * d2;
+        const double num = hi2.y - ((lo.x * frm.x + lo.y * frm.y) + hi2.x * frm.z);
+        if (den == 0.0) {
+            if (num < 0.0) outside = true;
+        } else {
+            const double t = num / den;
+            if (den < 0.0) t_in = fmax(t_in, t);
+            else t_out = fmin(t_out, t);
+        }
+    }
+}
+
+// shim S1 rayTestBatch for one beam, by one lane
+__device__ __forceinline__ bool beam_ray(const DevPack &pk, int a0, int a1, Vec3 frm, Vec3 to, Vec3 &hit) {
+    const double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
+    const int npax = 3 - a0 - a1;
+    // the TCP hovers kHookDistance above the surface and the fan's plane lies 0.2 ahead: expect the entry half way
+    Vec3 h = {frm.x + d0 * 0.5, frm.y + d1 * 0.5, frm.z + d2 * 0.5};
+    double t_in, t_out;
+    bool outside;
+#pragma unroll 1
+    for (int attempt = 0; attempt < kRayAttempts; ++attempt) {
+        const double g0 = comp(h, a0), g1 = comp(h, a1);
+        const int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
+        const int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
+        if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) break;
+        const uint2 entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+        const int n_planes = (int)(entry.y & 0xffffu);
+        if (n_planes <= 0) break;
+        const double2 *blob = pk.mc_blob + (size_t)entry.x * 2;
+        const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);
+        slab_serial(blob + 4, n_planes, frm, d0, d1, d2, t_in, t_out, outside);
+        if (outside || t_in > t_out || t_in > 1.0 || t_out < 0.0) return false;          // a miss proven by the subset
+        if (!(t_in > -INFINITY)) break;
+        h.x = frm.x + d0 * t_in; h.y = frm.y + d1 * t_in; h.z = frm.z + d2 * t_in;
+        if (in_cell_region(pk, h, comp(h, a0), comp(h, a1), comp(h, npax), cx, cy, abv, clv, hpv)) {
+            if (!(0.0 <= t_in)) return false;
+            hit = h;
+            return true;
+        }
+    }
+    slab_serial(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, frm, d0, d1, d2, t_in, t_out, outside);
+    if (outside || !(t_in <= t_out && 0.0 <= t_in && t_in <= 1.0)) return false;
+    hit.x = frm.x + d0 * t_in; hit.y = frm.y + d1 * t_in; hit.z = frm.z + d2 * t_in;
+    return true;
+}
+
+// cKDTree.query(point, k = 1) over the front texel positions, by one lane: returns the slot
+__device__ __forceinline__ int nearest_texel(const DevPack &pk, int a0, int a1, Vec3 p) {
+    const double *kx = pk.tx, *ky = pk.ty, *kz = pk.tz;
+    const double q0 = comp(p, a0), q1 = comp(p, a1);
+    const int r0 = min(max((int)floor((q1 - pk.row_o1) * pk.row_inv), 0), pk.n_rows - 1);
+    const int c0 = min(max((int)floor((q0 - pk.cx_o0) * pk.cx_inv), 0), pk.ncx - 1);
+    const double cw = 1.0 / pk.cx_inv;
+    double best = INFINITY;
+    int arg = -1;
+#pragma unroll 1
+    for (int R = 1; R <= 9; R += 4) {                 // half-widths 1, 5, 9 cells; then everything
+        const int ra = max(r0 - 1, 0), rb = min(r0 + 1, pk.n_rows - 1);
+        const int ca = max(c0 - R, 0), cb = min(c0 + R, pk.ncx - 1);
+        best = INFINITY; arg = -1;
+        for (int r = ra; r <= rb; ++r) {
+            const int *cs = pk.cell_start + (size_t)r * (pk.ncx + 1);
+            const int i0 = __ldg(cs + ca), i1 = __ldg(cs + cb + 1);
+            const int base = __ldg(&pk.row_word0[r]) * 32;
+            for (int i = i0; i < i1; ++i) {
+                const int j = base + i;
+                const double dx = __ldg(&kx[j]) - p.x, dy = __ldg(&ky[j]) - p.y, dz = __ldg(&kz[j]) - p.z;
+                const double d = dx * dx + dy * dy + dz * dz;
+                if (d < best) { best = d; arg = j; }
+            }
+        }
+        // every texel outside the block lies beyond the block's border in the principal plane
+        double m = INFINITY;
+        if (ca > 0) m = fmin(m, q0 - (pk.cx_o0 + ca * cw));
+        if (cb < pk.ncx - 1) m = fmin(m, (pk.cx_o0 + (cb + 1) * cw) - q0);
+        if (ra > 0) m = fmin(m, q1 - (pk.row_o1 + ra * pk.row_h));
+        if (rb < pk.n_rows - 1) m = fmin(m, (pk.row_o1 + (rb + 1) * pk.row_h) - q1);
+        m -= 1e-9;
+        if (arg >= 0 && (m == INFINITY || (m > 0.0 && best < m * m))) return __ldg(&pk.nn_rep_slot[arg]);
+    }
+    best = INFINITY; arg = -1;
+    for (int r = 0; r < pk.n_rows; ++r) {
+        const int base = __ldg(&pk.row_word0[r]) * 32, cnt = __ldg(&pk.row_count[r]);
+        for (int i = 0; i < cnt; ++i) {
+            const int j = base + i;
+            const double dx = __ldg(&kx[j]) - p.x, dy = __ldg(&ky[j]) - p.y, dz = __ldg(&kz[j]) - p.z;
+            const double d = dx * dx + dy * dy + dz * dz;
+            if (d < best) { best = d; arg = j; }
+        }
+    }
+    return arg >= 0 ? __ldg(&pk.nn_rep_slot[arg]) : -1;
+}
+
+// Returns (warp-uniform) like stamp(): newly painted texels (RGB) / thickness units removed (HSI), |union of valid
+// pixels| over the five shots (robot.py:423-425), whether a flip bit changed.  `last` = the environment's mask of the
+// previous shot's texels in global memory (read and rewritten word by word; an all-miss shot leaves it alone:
+// Part.paint returns early, bullet_paint_wrapper.py:563-564).
+template <int COLOR, typename WS, typename BITS>
+__device__ __forceinline__ void stamp_normal(const DevPack &pk, const DevConfig &cfg, const Ax &ax, const BITS &bits, int16_t *thick,
+                                             unsigned *grid_cnt, unsigned *last, int lane, WS &ws, NormalScratch &ns, int &n_new_out,
+                                             int &n_possible_out, bool &dirty_out) {
+    const int nw = pk.n_words;
+    for (int w = lane; w < nw; w += 32) ns.possible[w] = 0u;
+    int n_new = 0;
+    unsigned any = 0;
+    const bool init_painted = (pk.status_init == kPainted);
+#pragma unroll 1
+    for (int s = 0; s < NS; ++s) {
+        for (int w = lane; w < nw; w += 32) ns.shot_mask[w] = 0u;
+        __syncwarp();
+        const Vec3 pose = {ns.pos[s][0], ns.pos[s][1], ns.pos[s][2]};
+        const Vec3 center = {ws.mv.centers[s][0], ws.mv.centers[s][1], ws.mv.centers[s][2]};
+        int hits = 0;
+        for (int b = lane; b < cfg.n_beams; b += 32) {
+            const Vec3 dst = transform_point(pose, ns.quat[s], __ldg(&cfg.beam_plain[3 * b]), __ldg(&cfg.beam_plain[3 * b + 1]),
+                                             __ldg(&cfg.beam_plain[3 * b + 2]));
+            Vec3 hit;
+            int slot = -1;
+            if (beam_ray(pk, ax.a0, ax.a1, pose, dst, hit)) slot = nearest_texel(pk, ax.a0, ax.a1, hit);
+            ns.beam_slot[b] = slot >= 0 ? (uint16_t)slot : (uint16_t)0xFFFF;
+            if (slot >= 0) {
+                hits++;
+                atomicOr(&ns.shot_mask[slot >> 5], 1u << (slot & 31));
+                if (COLOR == 1) {     // minkowski_distance(texel, centre) (bullet_paint_wrapper.py:421-423)
+                    const double ex = fabs(center.x - __ldg(&pk.tx[slot])), ey = fabs(center.y - __ldg(&pk.ty[slot])),
+                                 ez = fabs(center.z - __ldg(&pk.tz[slot]));
+                    ns.beam_q[b] = sqrt((ex * ex + ey * ey) + ez * ez);
+                }
+            }
+        }
+        hits = __reduce_add_sync(kFull, hits);
+        __syncwarp();
+        if (hits == 0) continue;                       // `if not points: return [], 0`
+        double rmax = 0.0;
+        if (COLOR == 1) {
+            double m = -1.0;
+            for (int b = lane; b < cfg.n_beams; b += 32)
+                if (ns.beam_slot[b] != 0xFFFF) m = fmax(m, ns.beam_q[b]);
+            rmax = warp_max(m);
+        }
+        for (int w = lane; w < nw; w += 32) {
+            const unsigned m = ns.shot_mask[w];
+            const unsigned prev = last[w];
+            last[w] = m;                               // _last_painted_pixels = affected_pixels (:576)
+            ns.possible[w] |= m & ~prev;               // valid_pixels (:575)
+            if (m == 0u) continue;
+            const unsigned old = bits.ld(w);
+            unsigned flipped = 0u;
+            if (COLOR == 0) {                          // RGBColorHandler.change_pixels (:367-375): repaints count 0
+                const unsigned painted_before = init_painted ? ~old : old;
+                flipped = m & ~painted_before;
+                n_new += __popc(flipped);
+            } else {                                   // HSIColorHandler.change_pixels (:420-434), once per beam hit
+                unsigned mm = m;
+                while (mm) {
+                    const int bit = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    const int slot = w * 32 + bit;
+                    int times = 0;
+                    double dist = 0.0;
+                    for (int b = 0; b < cfg.n_beams; ++b)
+                        if (ns.beam_slot[b] == (uint16_t)slot) { times++; dist = ns.beam_q[b]; }
+                    const double ratio = dist / rmax;
+                    const int quantity = (int)(kHsiTargetMax * (1.0 - ratio * ratio)) + 1;
+                    const int v0 = (int)__ldcg(&thick[slot]);
+                    int v = v0;
+                    for (int k = 0; k < times && v > 0; ++k) { v -= quantity; n_new += quantity; }
+                    if (v != v0) {
+                        __stcg(&thick[slot], (int16_t)v);
+                        if (v0 == kPainted) flipped |= 1u << bit;     // values only decrease: 255 is left once
+                    }
+                }
+            }
+            if (flipped) {
+                bits.st(w, old | flipped);
+                any |= flipped;
+                if (grid_cnt) {
+                    unsigned f = flipped;
+                    while (f) {
+                        const int bit = __ffs(f) - 1;
+                        f &= f - 1;
+                        atomicAdd(grid_cnt + __ldg(&pk.gcell[w * 32 + bit]), 1u);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    int n_possible = 0;
+    for (int w = lane; w < nw; w += 32) n_possible += __popc(ns.possible[w]);
+    n_new_out = __reduce_add_sync(kFull, n_new);
+    n_possible_out = __reduce_add_sync(kFull, n_possible);
+    dirty_out = __any_sync(kFull, any != 0u);
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------ kernels
 // Robot._get_actions (robot.py:302-329): action -> direction, five guided sub-steps.
 // G lanes per environment (the plane / vertex / triangle lists of a sub-step are short).
@@ -849,6 +1075,11 @@ __device__ __forceinline__ void move_body(const DevPack &pk, const DevConfig &cf
             }
         }
         if (grp.gl == 0) { centers[3 * s] = center.x; centers[3 * s + 1] = center.y; centers[3 * s + 2] = center.z; }
+        if (ea.shots && grp.gl == 0) {      // normal paint method: the beam fan of shot s is cast from this pose
+            ShotPoses *sp = &ea.shots[env];
+            sp->pos[s][0] = pos.x; sp->pos[s][1] = pos.y; sp->pos[s][2] = pos.z;
+            sp->quat[s][0] = quat[0]; sp->quat[s][1] = quat[1]; sp->quat[s][2] = quat[2]; sp->quat[s][3] = quat[3];
+        }
         cur_p = pos;
         PAINTRL_PROF(12, grp.gl == 0);
     }
@@ -1176,9 +1407,9 @@ __device__ __noinline__ void move_generic_cold(const ColdArgs *ca, int env, cons
 // Everything after the move: stamp, score, observe, auto-reset.  (STAGED) the environment's flip bits
 // come in through a TMA bulk copy issued before the warp waits for its environment's hand-off flag and go
 // back the same way; the record and the move kernel's output follow the flag with L2 loads.
-template <int COLOR, bool STAGED, bool AX12, bool FUSED = false, bool DISCRETE = false>
+template <int COLOR, bool STAGED, bool AX12, bool FUSED = false, bool DISCRETE = false, bool NORMAL = false>
 __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &cfg, const EnvArrays &ea, int env, const StepIO &io,
-                                           WarpScratch<STAGED> &ws, const ColdArgs *cold) {
+                                           WarpScratch<STAGED> &ws, const ColdArgs *cold, NormalScratch *ns = nullptr) {
     const Ax ax = make_ax<AX12>(pk.axis0, pk.axis1);
     typedef WarpScratch<STAGED> WS;
     const int lane = threadIdx.x & 31;
@@ -1268,7 +1499,15 @@ __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &c
     const bool has_last = (st.flags & kFlagHasLast) != 0;
     int n_new, n_possible;
     bool dirty;
-    stamp<COLOR, STAGED>(pk, ax, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible, dirty PAINTRL_PROF_PASS);
+    if (NORMAL) {
+        // Robot.PAINT_METHOD == 'normal' (robot.py:414-417): the five beam fans instead of the five ball queries
+        const double *src = reinterpret_cast<const double *>(&ea.shots[env]);
+        for (int i = lane; i < kPaintPerAction * 7; i += 32) (&ns->pos[0][0])[i] = __ldcg(src + i);
+        __syncwarp();
+        stamp_normal<COLOR>(pk, cfg, ax, bits, thick, grid_cnt, ea.last_mask + (size_t)env * pk.n_words_pad, lane, ws, *ns, n_new, n_possible, dirty);
+    } else {
+        stamp<COLOR, STAGED>(pk, ax, bits, thick, grid_cnt, has_last, lane, ws, n_new, n_possible, dirty PAINTRL_PROF_PASS);
+    }
     PAINTRL_PROF(19, lane == 0);
 
     // ---- robot.py:425-433, robot_gym_env.py:321-340 (every lane ends up with the same scalars).
@@ -1399,6 +1638,8 @@ __device__ __forceinline__ void paint_body(const DevPack &pk, const DevConfig &c
         int idx = io.reset_start_idx ? io.reset_start_idx[env] : auto_start_index(pk, cfg, env, st.episode);
         idx = min(max(idx, 0), pk.n_starts - 1);
         clear_planes(pk, bits, gbits, thick, grid_cnt, lane);
+        if (ea.last_mask)
+            for (int w = lane; w < pk.n_words_pad; w += 32) ea.last_mask[(size_t)env * pk.n_words_pad + w] = 0u;
         __syncwarp();
         if (lane == 0) state_reset(pk, st, idx);
         if (next_obs) {
@@ -1428,6 +1669,17 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io, c
     const int env = blockIdx.x * WPB + warp;
     if (env >= num_envs) return;
     paint_body<COLOR, STAGED, AX12>(pk, cfg, ea, env, io, scratch[warp], cold);
+}
+
+// Paint kernel of the normal paint method (staged plane, generic axes; one warp per block).
+template <int COLOR>
+__global__ void __launch_bounds__(32, 8)
+paint_normal_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io, const ColdArgs *cold) {
+    __shared__ WarpScratch<true> scratch[1];
+    __shared__ NormalScratch nscratch[1];
+    const int env = blockIdx.x;
+    if (env >= num_envs) return;
+    paint_body<COLOR, true, false, false, false, true>(pk, cfg, ea, env, io, scratch[0], cold, &nscratch[0]);
 }
 
 // The whole step of one environment in one warp (batches that cannot fill the GPU twice over: the two-kernel step
@@ -1461,6 +1713,8 @@ reset_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, const int32_
         int idx = start_idx ? start_idx[k] : auto_start_index(pk, cfg, env, st.episode);
         idx = min(max(idx, 0), pk.n_starts - 1);
         clear_planes(pk, Bits<false>{gbits, nullptr}, gbits, thick, grid_cnt, lane);
+        if (ea.last_mask)
+            for (int w = lane; w < pk.n_words_pad; w += 32) ea.last_mask[(size_t)env * pk.n_words_pad + w] = 0u;
         state_reset(pk, st, idx);
     } else {
         robot_reset(st, set_pos + 3 * k, set_normal + 3 * k);
@@ -1563,6 +1817,8 @@ __global__ void set_status_kernel(DevPack pk, EnvArrays ea, int num_envs, const 
     unsigned *bits = bits_of(pk, ea, env), *grid_cnt = grid_cnt_of(pk, ea, env);
     int16_t *thick = thick_of(pk, ea, env);
     if (grid_cnt) for (int w = lane; w < pk.n_gcells_pad; w += 32) grid_cnt[w] = 0;
+    // normal paint method: the previous shot's texel set is not part of the exported state -- start from none
+    if (ea.last_mask) for (int w = lane; w < pk.n_words_pad; w += 32) ea.last_mask[(size_t)env * pk.n_words_pad + w] = 0u;
     __syncwarp();
     const bool init_painted = (pk.status_init == kPainted);
     const int16_t *src = status_in + (size_t)k * pk.n_texels;

@@ -130,6 +130,8 @@ class PaintGymEnv(_GymEnv):
     DISCRETE_GRANULARITY = 4
     OBS_MODE = 'section'
     OBS_GRAD = 4
+    # Robot.PAINT_METHOD (robot.py:172): 'fast' -- the reference's setting -- or 'normal' (beam fan per shot)
+    PAINT_METHOD = 'fast'
     EXTRA_CONFIG = dict(DEFAULT_EXTRA_CONFIG)
 
     action_space = spaces.Discrete(DISCRETE_GRANULARITY)
@@ -182,7 +184,8 @@ class PaintGymEnv(_GymEnv):
         self._rollout = rollout
         granularity = self.action_space.n if self.ACTION_MODE != 'continuous' else self.DISCRETE_GRANULARITY
         self._cfg = EnvConfig(extra_config, action_mode=self.ACTION_MODE, action_shape=self.ACTION_SHAPE,
-                              discrete_granularity=granularity, obs_mode=self.OBS_MODE, obs_grad=self.OBS_GRAD)
+                              discrete_granularity=granularity, obs_mode=self.OBS_MODE, obs_grad=self.OBS_GRAD,
+                              paint_method=self.PAINT_METHOD)
         self._setup_extra_config(extra_config)
         from .batched_env import BatchedPaintEnv      # raises without CUDA: no CPU fallback
         self._engine = BatchedPaintEnv(1, self._cfg, device=self.DEVICE)
@@ -287,11 +290,12 @@ class PaintVectorEnv(object):
     """
 
     def __init__(self, num_envs, extra_config=None, action_mode='discrete', action_shape=1,
-                 discrete_granularity=4, obs_mode='section', obs_grad=4, device=None, rollout=False, seed=0):
+                 discrete_granularity=4, obs_mode='section', obs_grad=4, device=None, rollout=False, seed=0,
+                 paint_method='fast'):
         from .batched_env import BatchedPaintEnv
         self._cfg = EnvConfig(extra_config, action_mode=action_mode, action_shape=action_shape,
                               discrete_granularity=discrete_granularity, obs_mode=obs_mode, obs_grad=obs_grad,
-                              auto_reset=False, seed=seed)
+                              auto_reset=False, seed=seed, paint_method=paint_method)
         self._engine = BatchedPaintEnv(num_envs, self._cfg, device=device)
         self.num_envs = int(num_envs)
         self._rollout = rollout

@@ -184,8 +184,29 @@ class PartPack(object):
         tex = self.compose_texture(status, color_mode)
         return (tex & 0xff).astype(np.uint8).reshape(self.width, self.height, 3)
 
+    def nn_representatives(self):
+        """For the normal paint method (Part.paint, bullet_paint_wrapper.py:562-566): per front texel, the member of its
+        group of texels with the SAME 3-D position that the reference's `cKDTree(pixel_positions).query(point, k=1)`
+        reports.  The kd-tree scans a leaf in its own index order and keeps the first of equal distances, so the twin
+        it returns is a constant of the tree -- read here from a tree built the way the reference builds it
+        (bullet_paint_wrapper.py:619-620, default parameters).  Identity where positions are unique."""
+        cached = getattr(self, '_nn_rep', None)
+        if cached is not None:
+            return cached
+        rep = np.arange(self.n_texels, dtype=np.int32)
+        uniq, inverse, counts = np.unique(self.front_pos, axis=0, return_inverse=True, return_counts=True)
+        groups = np.flatnonzero(counts > 1)
+        if groups.size:
+            from scipy.spatial import cKDTree
+            tree = cKDTree(self.front_pos)
+            winners = tree.query(uniq[groups], k=1)[1]
+            for g, w in zip(groups, winners):
+                rep[np.flatnonzero(inverse.reshape(-1) == g)] = w
+        self._nn_rep = rep
+        return rep
+
     # ------------------------------------------------------------------------------ C view
-    def to_c(self, start_mode, color_mode):
+    def to_c(self, start_mode, color_mode, with_nn_rep=False):
         """Build the `PaintrlPartPack` struct; returns (struct, keepalive)."""
         starts = self.start_points(start_mode)
         start_pos = np.ascontiguousarray(starts[:, 0, :])
@@ -228,4 +249,5 @@ class PartPack(object):
         p.start_pos = dptr(start_pos)
         p.start_normal = dptr(start_normal)
         p.status_init = self.status_init(color_mode)
+        p.texel_nn_rep = iptr(self.nn_representatives()) if with_nn_rep else None
         return p, keep

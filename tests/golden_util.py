@@ -27,7 +27,8 @@ class Golden(object):
         self.cfg = EnvConfig(extra, action_mode=self.config.get('action_mode', 'discrete'),
                              action_shape=self.config.get('action_shape', 1),
                              discrete_granularity=self.config.get('discrete_granularity', 4),
-                             obs_mode=self.config['obs_mode'], obs_grad=self.config['obs_grad'])
+                             obs_mode=self.config['obs_mode'], obs_grad=self.config['obs_grad'],
+                             paint_method=self.config.get('paint_method', 'fast'), beam_plain=self.data.get('beam_plain'))
         self.rollout = bool(self.config.get('rollout', False))
         self.pack = PartPack.for_part(extra['Part_NO'])
         self.lengths = self.data['lengths']

@@ -15,7 +15,7 @@ import pytest
 from golden_util import Golden, golden_names
 
 REL_TOL = 1e-5
-HSI_TRACES = {'g3_sheet_hsi_hybrid', 'g3b_sheet_hsi_late', 'g8_sheet_hsi_zigzag_continuous'}
+HSI_TRACES = {'g3_sheet_hsi_hybrid', 'g3b_sheet_hsi_late', 'g8_sheet_hsi_zigzag_continuous', 'g12_sheet_normal_hsi'}
 
 
 def _close(a, b, exact):
