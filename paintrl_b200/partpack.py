@@ -128,6 +128,22 @@ class PartPack(object):
                         self.meta.get('part_name'), self.width, self.height))
         return PartPack(meta, arrays)
 
+    def reordered_like(self, other):
+        """This pack with its front texels in `other`'s order (same texel set required).  The reference keeps the
+        texels in the iteration order of a CPython set (bullet_paint_wrapper.py:641); `loader.load_part` and the
+        rasteriser emit them sorted by (i, j).  The order carries no meaning for the step; this aligns two packs
+        of the same part for table-by-table comparison and for replaying traces recorded in the other order."""
+        mine = self.front_ij[:, 0].astype(np.int64) * self.height + self.front_ij[:, 1]
+        theirs = other.front_ij[:, 0].astype(np.int64) * other.height + other.front_ij[:, 1]
+        if mine.shape != theirs.shape or not np.array_equal(np.sort(mine), np.sort(theirs)):
+            raise ValueError('the packs do not hold the same front texels')
+        order = np.argsort(mine, kind='stable')[np.searchsorted(np.sort(mine), theirs)]
+        arrays = dict(self.arrays)
+        for key in ('front_ij', 'front_pos', 'texel_off', 'status_init_rgb', 'status_init_hsi', 'grid_cells_4', 'grid_cells_10'):
+            if key in arrays:
+                arrays[key] = np.ascontiguousarray(arrays[key][order])
+        return PartPack(self.meta, arrays)
+
     @property
     def n_texels(self):
         return self.front_pos.shape[0]
