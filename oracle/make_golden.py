@@ -32,9 +32,22 @@ MAX_POINTS = {0: 9148, 1: 14350, 5: 17000, 9: 9148}      # robot_gym_env.py:106-
 
 
 # ------------------------------------------------------------------------------ part packs
-def export_partpack(part_no):
+# the repository's own synthetic part (tests/data/make_synthetic_part.py), loaded by the reference like one of its own
+SYNTHETIC_ROOT = os.path.join(ROOT, 'tests', 'data')
+SYNTHETIC_PARTS = {100: ['bulge.urdf', 5200]}
+SYNTHETIC_PACK_DIR = os.path.join(ROOT, 'tests', 'golden')
+
+
+def export_partpack(part_no, pack_dir=None):
     from oracle.ref_env import ReferenceEnv
-    ref = ReferenceEnv({'Part_NO': part_no, 'START_POINT_MODE': 'anchor', 'COLOR_MODE': 'RGB'})
+    kw = {}
+    if part_no in SYNTHETIC_PARTS:
+        kw = dict(urdf_root=SYNTHETIC_ROOT, extra_parts=SYNTHETIC_PARTS)
+        PART_NAMES[part_no] = os.path.splitext(SYNTHETIC_PARTS[part_no][0])[0]
+        MAX_POINTS[part_no] = SYNTHETIC_PARTS[part_no][1]
+        pack_dir = pack_dir or SYNTHETIC_PACK_DIR
+    pack_dir = pack_dir or PACK_DIR
+    ref = ReferenceEnv({'Part_NO': part_no, 'START_POINT_MODE': 'anchor', 'COLOR_MODE': 'RGB'}, **kw)
     shim = sys.modules['pybullet']          # the S1 shim instance this env was built against
     part, bpw = ref.part, ref.bpw
     side = part.side
@@ -85,7 +98,10 @@ def export_partpack(part_no):
     # against the product's own derivation from positions)
     grid_cells = {}
     for g in (4, 10):
-        handler = bpw.GridObservation(part, g)
+        try:
+            handler = bpw.GridObservation(part, g)
+        except KeyError:        # door_lf: a texel left of its row's silhouette gives cell -1 (bullet_paint_wrapper.py:1085-1101)
+            continue
         cell_of = {}
         for i in range(g):
             for j in range(g):
@@ -98,12 +114,12 @@ def export_partpack(part_no):
     density = part.get_density()
 
     # HSI labelling differs only in the front colour (bullet_paint_wrapper.py:586)
-    ref_h = ReferenceEnv({'Part_NO': part_no, 'START_POINT_MODE': 'anchor', 'COLOR_MODE': 'HSI'})
+    ref_h = ReferenceEnv({'Part_NO': part_no, 'START_POINT_MODE': 'anchor', 'COLOR_MODE': 'HSI'}, **kw)
     assert ref_h.part.profile[ref_h.part.side] == profile
     init_hsi = np.array([int(v) for v in ref_h.part.init_texture], dtype=np.uint8)
     status_hsi = ref_h.front_status()
 
-    os.makedirs(PACK_DIR, exist_ok=True)
+    os.makedirs(pack_dir, exist_ok=True)
     name = '%s_%dx%d' % (PART_NAMES[part_no], part.texture_width, part.texture_height)
     meta = {
         'part_name': PART_NAMES[part_no], 'part_no': part_no, 'urdf': ref.env._part_name,
@@ -116,7 +132,7 @@ def export_partpack(part_no):
         'source': 'reference Part object under shims S1-S5 (oracle/make_golden.py)',
     }
     np.savez_compressed(
-        os.path.join(PACK_DIR, name + '.npz'),
+        os.path.join(pack_dir, name + '.npz'),
         meta=json.dumps(meta),
         ranges=np.array(part.ranges, dtype=np.float64),
         length_width_ratio=np.float64(part._length_width_ratio),
@@ -136,7 +152,7 @@ def export_partpack(part_no):
         grid_lo=grid_lo, grid_hi=grid_hi,
         start_fixed=starts['fixed'], start_anchor=starts['anchor'],
         start_edge=starts['edge'], start_all=starts['all'],
-        grid_cells_4=grid_cells[4], grid_cells_10=grid_cells[10],
+        **{'grid_cells_%d' % g: cells for g, cells in grid_cells.items()}
     )
     return name
 
@@ -551,7 +567,38 @@ def _run(name):
     return JOBS[name]()
 
 
+UNPACKED_PARTS = {2: 'door_lf', 3: 'door_lr', 4: 'door_rf', 6: 'roof', 7: 'bonnet', 8: 'door_rr_big'}   # max points 0: no stored pack
+
+
+def export_pack_digests(pack_dir=None):
+    """tests/golden/pack_digests.json: per-table sha256 of the packs the REFERENCE makes of the parts that have no
+    stored pack (`Part_Dict` max points 0); tests/test_loader.py holds the loader to them.  `pack_dir` reuses packs
+    minted earlier (about 1.5-4 minutes of reference load time per part otherwise)."""
+    import tempfile
+    for path in (os.path.join(ROOT, 'tests'), ROOT):
+        sys.path.insert(0, path)
+    from pack_util import pack_digest
+    from paintrl_b200.partpack import PartPack
+    pack_dir = pack_dir or tempfile.mkdtemp(prefix='refpacks_')
+    out = {}
+    for no, name in sorted(UNPACKED_PARTS.items()):
+        PART_NAMES[no], MAX_POINTS[no] = name, 0
+        import glob
+        found = glob.glob(os.path.join(pack_dir, name + '_[0-9]*x[0-9]*.npz'))
+        if not found:
+            if os.environ.get('PAINTRL_DIGESTS_EXISTING_ONLY'):
+                continue
+            found = [os.path.join(pack_dir, export_partpack(no, pack_dir=pack_dir) + '.npz')]
+        out[name] = pack_digest(PartPack.load(found[0]))
+    with open(os.path.join(GOLDEN_DIR, 'pack_digests.json'), 'w') as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    return 'pack_digests.json'
+
+
 def main(argv):
+    if argv and argv[0] == 'digests':
+        print('wrote', export_pack_digests(*argv[1:2]))
+        return
     names = argv or (['pack0', 'pack1'] + sorted(JOBS))
     if names == ['packs']:
         names = ['pack0', 'pack1']

@@ -90,9 +90,13 @@ class ReferenceEnv(object):
 
     def __init__(self, extra_config=None, action_mode='discrete', action_shape=1,
                  discrete_granularity=4, obs_mode='section', obs_grad=4, rollout=False,
-                 quiet=True, paint_method='fast'):
+                 quiet=True, paint_method='fast', urdf_root=None, extra_parts=None):
         self.bpw, self.rob, self.rge = load_reference_modules()
         self.rob.Robot.PAINT_METHOD = paint_method          # robot.py:172 (a class constant edited in source upstream)
+        if extra_parts:
+            # parts outside the reference's table (the repository's synthetic test part): Part_NO -> [urdf, max points],
+            # found under `urdf_root`/urdf/painting like the reference's own (robot_gym_env.py:106-117, 273)
+            self.rge.Part_Dict.update(extra_parts)
         cfg = dict(DEFAULT_EXTRA_CONFIG)
         if extra_config:
             cfg.update(extra_config)
@@ -129,7 +133,7 @@ class ReferenceEnv(object):
         self._forced_start = None
         self.rge.randint = logged_randint
         with self._silence():
-            self.env = cls(os.path.join(REFERENCE_ROOT, 'PaintRLEnv'), with_robot=False,
+            self.env = cls(urdf_root or os.path.join(REFERENCE_ROOT, 'PaintRLEnv'), with_robot=False,
                            renders=True, render_video=False, rollout=rollout, extra_config=cfg)
         self.part = self.bpw._urdf_cache[self.env._part_id]
         if cfg['COLOR_MODE'] != 'RGB':

@@ -29,7 +29,7 @@ class BatchedPaintEnv(object):
 
     def __init__(self, num_envs, extra_config=None, action_mode='discrete', action_shape=1,
                  discrete_granularity=4, obs_mode='section', obs_grad=4, device=None,
-                 auto_reset=False, seed=0, pack=None, texture_size=(240, 240), max_possible_point=None):
+                 auto_reset=False, seed=0, pack=None, texture_size=(240, 240), max_possible_point=None, urdf_root=None):
         if not torch.cuda.is_available():
             raise RuntimeError('paintrl_b200 needs a CUDA device: there is no CPU fallback')
         self.cfg = extra_config if isinstance(extra_config, EnvConfig) else EnvConfig(
@@ -40,7 +40,8 @@ class BatchedPaintEnv(object):
         if self.device.type != 'cuda':
             raise RuntimeError('paintrl_b200 runs on CUDA devices only')
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        self.pack = pack if pack is not None else PartPack.for_part(self.cfg.part_no, *texture_size, device=dev_index)
+        self.pack = pack if pack is not None else PartPack.for_part(self.cfg.part_no, *texture_size, device=dev_index,
+                                                                          urdf_root=urdf_root)
         self.num_envs = int(num_envs)
         self._lib = _capi.lib()
         cpack, keep_pack = self.pack.to_c(self.cfg.start_point_mode, self.cfg.color_mode, with_nn_rep=self.cfg.paint_method == 'normal')

@@ -188,7 +188,7 @@ class PaintGymEnv(_GymEnv):
                               paint_method=self.PAINT_METHOD)
         self._setup_extra_config(extra_config)
         from .batched_env import BatchedPaintEnv      # raises without CUDA: no CPU fallback
-        self._engine = BatchedPaintEnv(1, self._cfg, device=self.DEVICE)
+        self._engine = BatchedPaintEnv(1, self._cfg, device=self.DEVICE, urdf_root=urdf_root)
         self._host = self._engine.host_buffers(pinned=True)
         starts = self._engine.pack.start_points(self.START_POINT_MODE)
         self._start_points = [[list(map(float, s[0])), list(map(float, s[1]))] for s in starts]
@@ -291,12 +291,12 @@ class PaintVectorEnv(object):
 
     def __init__(self, num_envs, extra_config=None, action_mode='discrete', action_shape=1,
                  discrete_granularity=4, obs_mode='section', obs_grad=4, device=None, rollout=False, seed=0,
-                 paint_method='fast'):
+                 paint_method='fast', urdf_root=None):
         from .batched_env import BatchedPaintEnv
         self._cfg = EnvConfig(extra_config, action_mode=action_mode, action_shape=action_shape,
                               discrete_granularity=discrete_granularity, obs_mode=obs_mode, obs_grad=obs_grad,
                               auto_reset=False, seed=seed, paint_method=paint_method)
-        self._engine = BatchedPaintEnv(num_envs, self._cfg, device=device)
+        self._engine = BatchedPaintEnv(num_envs, self._cfg, device=device, urdf_root=urdf_root)
         self.num_envs = int(num_envs)
         self._rollout = rollout
         self._rng = np.random.RandomState(seed)

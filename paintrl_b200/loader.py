@@ -134,31 +134,29 @@ class Triangles(object):
     """Per-face constants of `BarycentricInterpolator` (bullet_paint_wrapper.py:123-146, 263-272) for all faces, as arrays."""
 
     def __init__(self, world, faces, front_normal):
-        n = len(faces)
-        self.a = np.zeros((n, 3)); self.b = np.zeros((n, 3)); self.c = np.zeros((n, 3))
-        self.v0 = np.zeros((n, 3)); self.v1 = np.zeros((n, 3))
-        self.d00 = np.zeros(n); self.d01 = np.zeros(n); self.d11 = np.zeros(n); self.inv_denom = np.zeros(n)
-        self.area = np.zeros(n)
-        self.normal = np.zeros((n, 3))
-        self.center = np.zeros((n, 3))
-        self.side = np.zeros(n, dtype=np.int64)
-        for t, (ia, ib, ic) in enumerate(faces):
-            a, b, c = world[ia], world[ib], world[ic]
-            v0, v1 = np.subtract(b, a), np.subtract(c, a)
-            d00, d01, d11 = np.dot(v0, v0), np.dot(v0, v1), np.dot(v1, v1)
-            denom = d00 * d11 - d01 * d01
-            self.a[t], self.b[t], self.c[t], self.v0[t], self.v1[t] = a, b, c, v0, v1
-            self.d00[t], self.d01[t], self.d11[t] = d00, d01, d11
-            self.inv_denom[t] = 1.0 / denom if denom != 0 else 0
-            self.area[t] = np.linalg.norm(np.cross(v0, v1)) / 2
-            # face normal from the corner order (:263-272): plain Python differences, NumPy cross and norm
-            u = [q - p for p, q in zip(a, b)]
-            w = [q - p for p, q in zip(a, c)]
-            nrm = np.cross(u, w)
-            length = np.linalg.norm(nrm)
-            self.normal[t] = [k / length for k in nrm]
-            self.center[t] = [(p + q + r) / 3 for p, q, r in zip(a, b, c)]
-            self.side[t] = classify_side(list(self.normal[t]), front_normal)
+        w = np.asarray(world, dtype=np.float64).reshape(-1, 3)
+        f = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+        n = len(f)
+        self.a, self.b, self.c = w[f[:, 0]], w[f[:, 1]], w[f[:, 2]]
+        self.v0, self.v1 = self.b - self.a, self.c - self.a            # np.subtract(b, a), np.subtract(c, a)
+
+        def dots(x, y):       # np.dot per pair of 3-vectors: OpenBLAS ddot contracts, a vectorised sum would not
+            return np.array([np.dot(x[t], y[t]) for t in range(n)], dtype=np.float64).reshape(n)
+
+        def cross(x, y):      # np.cross, element by element: products and differences rounded one by one
+            return np.stack([x[:, 1] * y[:, 2] - x[:, 2] * y[:, 1], x[:, 2] * y[:, 0] - x[:, 0] * y[:, 2],
+                             x[:, 0] * y[:, 1] - x[:, 1] * y[:, 0]], axis=1)
+
+        self.d00, self.d01, self.d11 = dots(self.v0, self.v0), dots(self.v0, self.v1), dots(self.v1, self.v1)
+        denom = self.d00 * self.d11 - self.d01 * self.d01
+        with np.errstate(divide='ignore', invalid='ignore'):
+            self.inv_denom = np.where(denom != 0, 1.0 / np.where(denom != 0, denom, 1.0), 0.0)
+            nrm = cross(self.v0, self.v1)
+            self.area = np.sqrt(dots(nrm, nrm)) / 2                    # np.linalg.norm(x) = sqrt(x.dot(x))
+            # face normal from the corner order (:263-272): the same differences, cross product and norm
+            self.normal = nrm / np.sqrt(dots(nrm, nrm))[:, None]
+        self.center = (self.a + self.b + self.c) / 3
+        self.side = np.array([classify_side(list(self.normal[t]), front_normal) for t in range(n)], dtype=np.int64).reshape(n)
         self.area_valid = self.area >= 1e-4          # BarycentricInterpolator.MIN_AREA
 
 
@@ -291,6 +289,7 @@ class Silhouette(object):
         self.lo = [0] * GRID_GRANULARITY
         self.hi = [0] * GRID_GRANULARITY
         self.scans = 0
+        self.sparse_rows = 0
         self._run()
 
     def _boundary(self, point, is_min):
@@ -337,6 +336,7 @@ class Silhouette(object):
                 continue
             index = cur + int(ahead[0])
             if index - cur <= 1:
+                self.sparse_rows += 1
                 new2 = step_max + 0.5 * step_size
                 new1 = data[order[index], ax1] if (i - 1) not in known else (known[i - 1][0] + known[i - 1][1]) / 2
                 for row in (left, right):
@@ -458,9 +458,9 @@ def correct_with_hull(tri, world, masked_data, side, front_normal, axes, ranges,
     simplices = ConvexHull(np.asarray(world, dtype=np.float64)).simplices
     keep = [s for s in simplices if int(np.sum(masked_data[s, 0] != PARKED[0])) >= 2]
     if not keep:
-        return
-    hull = Triangles([list(p) for p in world], keep, front_normal)
-    hull_normals = [list(hull.normal[k]) if hull.side[k] == side else [-c for c in hull.normal[k]] for k in range(len(keep))]
+        return 0
+    hull = Triangles(world, keep, front_normal)
+    hull_normals = np.where((hull.side == side)[:, None], hull.normal, -hull.normal)
     pa = np.asarray(world, dtype=np.float64)
     keep = np.asarray(keep)
     flat = Flat(pa[keep[:, 0]][:, list(axes)], pa[keep[:, 1]][:, list(axes)], pa[keep[:, 2]][:, list(axes)])
@@ -468,9 +468,12 @@ def correct_with_hull(tri, world, masked_data, side, front_normal, axes, ranges,
     n1, n2 = normalized_pose(tri.center[mine], axes, ranges, lo, hi)
     inner = mine[~((n1 <= 0.01) | (n1 >= 0.99) | (n2 <= 0.01) | (n2 >= 0.99))]
     above = flat.first_containing(tri.center[inner][:, list(axes)])
+    corrected = 0
     for t, k in zip(inner, above):
         if k >= 0 and included_angle_between(normals[t], hull_normals[k]) > np.pi / 6:
             normals[t] = hull_normals[k]
+            corrected += 1
+    return corrected
 
 
 def smooth_with_neighbours(tri, sides, normals):
@@ -481,7 +484,9 @@ def smooth_with_neighbours(tri, sides, normals):
     neighbour lists come from the same `cKDTree` calls, whose traversal order fixes the order of the sum."""
     from scipy.spatial import cKDTree
     n = len(tri.side)
+    smoothed = {}
     for side in sides:
+        smoothed[side] = 0
         centers = np.where((tri.side == side)[:, None], tri.center, np.array(PARKED, dtype=np.float64)[None, :])
         tree = cKDTree(centers)
         mine = np.flatnonzero(tri.side == side)
@@ -492,15 +497,17 @@ def smooth_with_neighbours(tri, sides, normals):
                 if b == t or b >= n:
                     continue
                 if abs(included_angle_between(normals[b], normals[t])) > np.pi / 18:
-                    weighted = [[tri.area[k] * c for c in normals[k]] for k in balls[row] if k != t]
-                    if weighted:
-                        avg = np.average(weighted, 0)
+                    ball = np.array([k for k in balls[row] if k != t], dtype=np.int64)
+                    if ball.size:
+                        avg = np.average(tri.area[ball][:, None] * normals[ball], 0)
                         mag2 = sum(c * c for c in avg)
                         if abs(mag2 - 1.0) > 0.00001:
                             mag = np.sqrt(mag2)
                             avg = tuple(c / mag for c in avg)
                         normals[t] = avg
+                        smoothed[side] += 1
                     break
+    return smoothed
 
 
 # ------------------------------------------------------------------------------------------ start points
@@ -617,9 +624,7 @@ def load_part(urdf_path, max_points=None, part_no=None, base_position=BASE_POSIT
     axes, non_principal = principal_axes(world)
     front_normal = [1 if k == non_principal else 0 for k in range(3)]
     tri = Triangles(world, fv, front_normal)
-    tri.b, tri.c = tri.a + 0.0, tri.a + 0.0
     wa = np.asarray(world, dtype=np.float64)
-    tri.b[:], tri.c[:] = wa[fv[:, 1]], wa[fv[:, 2]]
     uv = np.asarray(vt, dtype=np.float64)[ft]                                    # [T, 3, 2]
     side = FRONT
     # profile order of the sides (Part.preprocess :626-635): first appearance in the face list, `other` dropped
@@ -662,7 +667,7 @@ def load_part(urdf_path, max_points=None, part_no=None, base_position=BASE_POSIT
     # anchors (set_start_points :740-747, before any normal correction) and ranges
     from scipy.spatial import cKDTree
     corners, ranges = corner_points_and_ranges(world, axes)
-    normals = [list(nrm) for nrm in tri.normal]
+    normals = tri.normal.copy()                     # [T, 3], corrected in place below
     vertex_tree = cKDTree(masked[side])
     anchors = []
     for point in corners:
@@ -681,8 +686,8 @@ def load_part(urdf_path, max_points=None, part_no=None, base_position=BASE_POSIT
     lo, hi = silhouette.lo, silhouette.hi
 
     # normal correction (:650-698)
-    correct_with_hull(tri, world, silhouette.data, side, front_normal, axes, ranges, lo, hi, normals)
-    smooth_with_neighbours(tri, sides, normals)
+    hull_corrected = correct_with_hull(tri, world, silhouette.data, side, front_normal, axes, ranges, lo, hi, normals)
+    smoothed = smooth_with_neighbours(tri, sides, normals)
 
     starts = start_point_modes(tri, side, anchors, normals, axes, ranges, lo, hi)
 
@@ -705,7 +710,10 @@ def load_part(urdf_path, max_points=None, part_no=None, base_position=BASE_POSIT
         'part_name': name, 'part_no': part_no, 'urdf': os.path.basename(urdf_path), 'width': width, 'height': height,
         'axes': [int(a) for a in axes], 'non_principal_axis': int(non_principal), 'front_normal': front_normal,
         'base_position': base, 'max_points': max_points, 'density': float(density), 'grid_granularity': GRID_GRANULARITY,
-        'silhouette_scans': silhouette.scans, 'source': 'paintrl_b200.loader.load_part',
+        'source': 'paintrl_b200.loader.load_part',
+        'loader_stats': {'silhouette_scans': silhouette.scans, 'sparse_grid_rows': silhouette.sparse_rows,
+                         'hull_corrected_normals': int(hull_corrected), 'smoothed_normals': int(smoothed[side]),
+                         'triangles': int(len(fv)), 'front_triangles': int((tri.side == side).sum())},
     }
     if texture_size is not None:
         # a texel count scales with the texel density (see PartPack.retextured)
@@ -721,7 +729,7 @@ def load_part(urdf_path, max_points=None, part_no=None, base_position=BASE_POSIT
         tri_id=front.astype(np.int32),
         tri_a=tri.a[front], tri_v0=tri.v0[front], tri_v1=tri.v1[front], tri_b=tri.b[front], tri_c=tri.c[front],
         tri_uv=uv[front], tri_d00=tri.d00[front], tri_d01=tri.d01[front], tri_d11=tri.d11[front],
-        tri_inv_denom=tri.inv_denom[front], tri_n=np.array([list(normals[t]) for t in front], dtype=np.float64),
+        tri_inv_denom=tri.inv_denom[front], tri_n=normals[front],
         grid_lo=lo, grid_hi=hi,
         start_fixed=starts['fixed'], start_anchor=starts['anchor'], start_edge=starts['edge'], start_all=starts['all'],
     )

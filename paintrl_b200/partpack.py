@@ -63,10 +63,14 @@ class PartPack(object):
         return cls(meta, arrays)
 
     @classmethod
-    def for_part(cls, part_no, width=240, height=240, device=0):
-        """Pack of `Part_Dict[part_no]` (robot_gym_env.py:106-117) at a texture size.  Sizes without a
-        stored pack are derived from the part's 240x240 pack by rasterising its front triangles on
-        GPU `device` (`retextured`)."""
+    def for_part(cls, part_no, width=240, height=240, device=0, urdf_root=None):
+        """Pack of `Part_Dict[part_no]` (robot_gym_env.py:106-117) at a texture size.
+
+        Stored packs (`data/partpacks/`: the parts with a usable max-points entry) are read; sizes without a stored
+        pack are derived from the part's 240x240 pack by rasterising its front triangles on GPU `device`
+        (`retextured`).  A part without a stored pack is built from its URDF by `loader.load_part` -- found under
+        `urdf_root`/urdf/painting like the reference finds it (robot_gym_env.py:273; `urdf_root` is PaintGymEnv's
+        first argument, or the environment variable PAINTRL_URDF_ROOT)."""
         if part_no not in PART_DICT:
             raise KeyError(part_no)
         name = os.path.splitext(PART_DICT[part_no][0])[0]
@@ -74,10 +78,19 @@ class PartPack(object):
         if os.path.isfile(path):
             return cls.load(path)
         base = os.path.join(PACK_DIR, '%s_240x240.npz' % name)
-        if not os.path.isfile(base):
+        if os.path.isfile(base):
+            return cls.load(base).retextured(width, height, device=device)
+        urdf_root = urdf_root or os.environ.get('PAINTRL_URDF_ROOT')
+        urdf = os.path.join(urdf_root, 'urdf', 'painting', PART_DICT[part_no][0]) if urdf_root else None
+        if urdf is None or not os.path.isfile(urdf):
             raise FileNotFoundError(
-                'no part pack for Part_NO=%d (%s) at %dx%d: %s' % (part_no, name, width, height, path))
-        return cls.load(base).retextured(width, height, device=device)
+                'no stored part pack for Part_NO=%d (%s) and no URDF to build one from (%s): pass urdf_root= / set '
+                'PAINTRL_URDF_ROOT to the directory that holds urdf/painting/%s' % (part_no, name, urdf, PART_DICT[part_no][0]))
+        from . import loader
+        pack = loader.load_part(urdf, device=device)
+        if (pack.width, pack.height) != (width, height):
+            pack = pack.retextured(width, height, device=device)
+        return pack
 
     def rasterize(self, width, height, device=0):
         """Front texels at a texture size: `(ij [N,2] int32, pos [N,3] float64)` sorted by (i, j), from
@@ -85,7 +98,7 @@ class PartPack(object):
         bullet_paint_wrapper.py:604-618, 191-212) -- computed by `paintrl_rasterize_texels` on the GPU."""
         for key in ('tri_b', 'tri_c', 'tri_uv'):
             if key not in self.arrays:
-                raise ValueError('this part pack carries no %s: re-mint it (oracle/make_golden.py packs)' % key)
+                raise ValueError('this part pack carries no %s: rebuild it with paintrl_b200.loader.load_part' % key)
         lib = _capi.lib()
         tri = [np.ascontiguousarray(self.arrays[k], dtype=np.float64) for k in ('tri_a', 'tri_b', 'tri_c', 'tri_uv')]
         n_tris = tri[0].shape[0]

@@ -40,3 +40,28 @@ def permuted_pack(pack, frame):
     meta['non_principal_axis'] = 3 - sum(new_axes)
     meta['source'] = 'synthetic frame %s of %s' % (frame, meta.get('part_name'))
     return PartPack(meta, arrays)
+
+
+# ------------------------------------------------------------------------------------------ digests
+DIGEST_SKIP = ('grid_cells_4', 'grid_cells_10')      # reference-side cross-check tables, not produced by the loader
+_PER_TEXEL = ('front_ij', 'front_pos', 'texel_off', 'status_init_rgb', 'status_init_hsi')
+
+
+def pack_digest(pack):
+    """sha256 of every table of a pack, with the front texels brought into (i, j) order first (the reference keeps
+    them in `set` iteration order, the loader sorted), plus the scalars of the meta block that the step consumes."""
+    import hashlib
+    ij = np.asarray(pack.arrays['front_ij'], dtype=np.int64)
+    order = np.lexsort((ij[:, 1], ij[:, 0]))
+    out = {}
+    for key in sorted(pack.arrays):
+        if key in DIGEST_SKIP:
+            continue
+        a = np.asarray(pack.arrays[key])
+        if key in _PER_TEXEL:
+            a = a[order]
+        a = np.ascontiguousarray(a, dtype=np.int64 if a.dtype.kind in 'iu' else np.float64)
+        out[key] = '%s:%s' % ('x'.join(str(d) for d in a.shape), hashlib.sha256(a.tobytes()).hexdigest()[:24])
+    for key in ('width', 'height', 'axes', 'non_principal_axis', 'front_normal', 'density'):
+        out['meta.' + key] = repr(pack.meta[key])
+    return out

@@ -37,11 +37,11 @@ CASES = {
 }
 
 
-def _run_case(extra, kw, num_envs, steps, device, auto_reset=True, texture=None, status_every=7):
+def _run_case(extra, kw, num_envs, steps, device, auto_reset=True, texture=None, status_every=7, pack=None):
     from oracle.oracle import OracleBatch, action_directions, retextured_pack
     from paintrl_b200.batched_env import BatchedPaintEnv
     cfg = EnvConfig(extra, auto_reset=auto_reset, **kw)
-    pack = PartPack.for_part(cfg.part_no)
+    pack = pack if pack is not None else PartPack.for_part(cfg.part_no)
     if texture is None:
         env = BatchedPaintEnv(num_envs, cfg, device=device, pack=pack)
         ora = OracleBatch(pack, cfg, num_envs)
