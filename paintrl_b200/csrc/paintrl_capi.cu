@@ -37,18 +37,37 @@ int fail(int code, const std::string &msg) {
             return fail(PAINTRL_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
     } while (0)
 
+// Device allocations of one engine.  Read-only tables (`upload`) are carved out of a few large slabs so that the step
+// kernels can prefetch all of them into L2 with one strided loop (`static_ranges`); per-environment state (`alloc`)
+// gets its own allocations.
 struct DeviceArena {
+    static constexpr size_t kSlabBytes = size_t(24) << 20;
+    struct Slab { char *base; size_t cap, used; };
     std::vector<void *> ptrs;
+    std::vector<Slab> slabs;
     ~DeviceArena() {
         for (void *p : ptrs) cudaFree(p);
+    }
+    cudaError_t suballoc(void **out, size_t bytes) {
+        bytes = (std::max<size_t>(bytes, 16) + 255) & ~size_t(255);
+        if (slabs.empty() || slabs.back().used + bytes > slabs.back().cap) {
+            const size_t cap = std::max(bytes, kSlabBytes);
+            void *p = nullptr;
+            cudaError_t e = cudaMalloc(&p, cap);
+            if (e != cudaSuccess) return e;
+            ptrs.push_back(p);
+            slabs.push_back(Slab{static_cast<char *>(p), cap, 0});
+        }
+        Slab &s = slabs.back();
+        *out = s.base + s.used;
+        s.used += bytes;
+        return cudaSuccess;
     }
     template <typename T>
     cudaError_t upload(const std::vector<T> &host, const T **out) {
         void *p = nullptr;
-        size_t bytes = std::max<size_t>(host.size() * sizeof(T), 16);
-        cudaError_t e = cudaMalloc(&p, bytes);
+        cudaError_t e = suballoc(&p, host.size() * sizeof(T));
         if (e != cudaSuccess) return e;
-        ptrs.push_back(p);
         if (!host.empty()) {
             e = cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
             if (e != cudaSuccess) return e;
@@ -60,6 +79,11 @@ struct DeviceArena {
         cudaError_t e = cudaMalloc(out, std::max<size_t>(bytes, 16));
         if (e == cudaSuccess) ptrs.push_back(*out);
         return e;
+    }
+    size_t static_bytes() const {
+        size_t n = 0;
+        for (const Slab &s : slabs) n += s.used;
+        return n;
     }
 };
 
@@ -1144,6 +1168,19 @@ int paintrl_create(const PaintrlPartPack *pack, const PaintrlConfig *cfg, int32_
         if (err == cudaSuccess) err = cudaEventCreateWithFlags(&e->ev_done[k], cudaEventDisableTiming);
     }
     if (err != cudaSuccess) { delete e; return fail(PAINTRL_E_CUDA, std::string("creating the copy streams: ") + cudaGetErrorString(err)); }
+    {
+        // L2 prefetch ranges of the static tables (PAINTRL_L2_PREFETCH=0 switches the pass off; tables beyond 48 MB --
+        // multi-megapixel textures -- are left to demand loads)
+        const char *pf = getenv("PAINTRL_L2_PREFETCH");
+        e->pk.pf_n = 0;
+        if (!(pf && atoi(pf) == 0) && e->arena.static_bytes() <= (size_t(48) << 20) && e->arena.slabs.size() <= 4) {
+            for (const DeviceArena::Slab &s : e->arena.slabs) {
+                e->pk.pf_base[e->pk.pf_n] = s.base;
+                e->pk.pf_lines[e->pk.pf_n] = (unsigned)((s.used + 127) / 128);
+                e->pk.pf_n++;
+            }
+        }
+    }
     {
         ColdArgs ca;
         ca.pk = e->pk; ca.cfg = e->cfg; ca.ea = env_arrays(e);

@@ -1690,6 +1690,7 @@ step_fused_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO 
     __shared__ WarpScratch<STAGED> scratch[1];
     const int env = blockIdx.x;
     if (env >= num_envs) return;
+    l2_prefetch_tables(pk, blockIdx.x * 32 + threadIdx.x, gridDim.x * 32);
     paint_body<COLOR, STAGED, AX12, true, DISCRETE>(pk, cfg, ea, env, io, scratch[0], cold);
 }
 
