@@ -206,6 +206,30 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
             struct { double a, b, c, rlo, rhi; int n_planes, n_verts; } mc = {0.0, 0.0, 0.0, 1.0, -1.0, 0, 0};
             pidx.clear();
             vcs.clear();
+            unsigned long long fallback_link = 0;   // (sector offset | counts << 32) of the cell's fallback blob, 0: none
+            bool too_long = false;
+            // appends the blob of the current (mc, pidx, vcs) and returns its entry word: offset | n_planes << 32 | n_verts << 48
+            auto emit_blob = [&]() -> unsigned long long {
+                if (mc.n_planes > 0xffff || mc.n_verts > 0xffff || blob.size() / 4 > 0xfffffff0u) { too_long = true; return 0ull; }
+                const unsigned long long word = (unsigned long long)(blob.size() / 4) | ((unsigned long long)mc.n_planes << 32) |
+                                                ((unsigned long long)mc.n_verts << 48);
+                double hdr[8] = {mc.a, mc.b, mc.c, mc.rlo, mc.rhi, 0.0, 0.0, 0.0};
+                std::memcpy(&hdr[5], &fallback_link, 8);
+                fallback_link = 0;
+                blob.insert(blob.end(), hdr, hdr + 8);
+                for (int p : pidx) {
+                    const double pl[4] = {pack->plane_n[3 * p], pack->plane_n[3 * p + 1], pack->plane_n[3 * p + 2], pack->plane_off[p]};
+                    blob.insert(blob.end(), pl, pl + 4);
+                }
+                for (const VertCand &vc : vcs) {
+                    double v[4] = {vc.x, vc.y, vc.z, 0.0};
+                    const unsigned long long meta = (unsigned long long)vc.id | ((unsigned long long)vc.rec << 32);
+                    std::memcpy(&v[3], &meta, 8);
+                    blob.insert(blob.end(), v, v + 4);
+                }
+                plane_refs += pidx.size();
+                return word;
+            };
             const double lo0 = o0 + cx * cs, hi0 = o0 + (cx + 1) * cs, lo1 = o1 + cy * cs, hi1 = o1 + (cy + 1) * cs;
             const double mid0 = 0.5 * (lo0 + hi0), mid1 = 0.5 * (lo1 + hi1);
             // sample the hull's tool-side surface over the footprint
@@ -262,61 +286,115 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
                 // enter well below the tool-side surface: its slab reaches kPadBelowEdge down (measured: entry
                 // points up to 14 mm below the fitted plane; such cells sent 1 % of the environments through
                 // the verify pass on every sub-step and were the tail of the move phase).
-                const double below = hits < K * K ? kPadBelowEdge : kPadBelow;
-                const double rlo = rmin - (side > 0 ? below : kPadAbove), rhi = rmax + (side > 0 ? kPadAbove : below);
-                mc.a = fa - fb * mid0 - fc * mid1;
-                mc.b = fb;
-                mc.c = fc;
-                mc.rlo = rlo;
-                mc.rhi = rhi;
-                double corner[8][3];
-                double zmin = INFINITY, zmax = -INFINITY;
-                for (int c = 0; c < 8; ++c) {
-                    corner[c][a0] = (c & 1) ? hi0 + kFootSlack : lo0 - kFootSlack;
-                    corner[c][a1] = (c & 2) ? hi1 + kFootSlack : lo1 - kFootSlack;
-                    corner[c][np] = mc.a + mc.b * corner[c][a0] + mc.c * corner[c][a1] + ((c & 4) ? rhi : rlo);
-                    zmin = std::min(zmin, corner[c][np]); zmax = std::max(zmax, corner[c][np]);
-                }
-                zmin -= 1e-9; zmax += 1e-9;
-                for (int p = 0; p < pack->n_planes; ++p) {
-                    const double *n = pack->plane_n + 3 * p;
-                    double worst = -INFINITY;
-                    for (int c = 0; c < 8; ++c)
-                        worst = std::max(worst, n[0] * corner[c][0] + n[1] * corner[c][1] + n[2] * corner[c][2]);
-                    if (worst > pack->plane_off[p] - kMargin) pidx.push_back(p);
-                }
-                mc.n_planes = (int)pidx.size();
-                // candidates for the nearest front vertex of any point of the region (its bounding box)
-                double blo[3], bhi[3];
-                blo[a0] = lo0 - kFootSlack; bhi[a0] = hi0 + kFootSlack;
-                blo[a1] = lo1 - kFootSlack; bhi[a1] = hi1 + kFootSlack;
-                blo[np] = zmin; bhi[np] = zmax;
-                double best_far = INFINITY;
-                for (int v : front) {
-                    const double *p = pack->vertices + 3 * v;
-                    double far2 = 0;
-                    for (int k = 0; k < 3; ++k) {
-                        double f = std::max(std::fabs(p[k] - blo[k]), std::fabs(p[k] - bhi[k]));
-                        far2 += f * f;
+                // Two tiers for such cells: the PRIMARY region is the thin slab of an ordinary cell (short lists: almost
+                // every ray enters through the tool-side surface), the deep slab is a FALLBACK blob linked from the
+                // primary's header, tried when the entry point lies in this cell but not in the thin slab.  With the deep
+                // slab alone these cells carried 80 planes and up to 258 vertex candidates (mean 16 / 14 elsewhere) and
+                // their environments were the tail of the move phase.
+                const bool edge_cell = hits < K * K;
+                auto build_lists = [&](double below) {
+                    pidx.clear();
+                    vcs.clear();
+                    const double rlo = rmin - (side > 0 ? below : kPadAbove), rhi = rmax + (side > 0 ? kPadAbove : below);
+                    mc.a = fa - fb * mid0 - fc * mid1;
+                    mc.b = fb;
+                    mc.c = fc;
+                    mc.rlo = rlo;
+                    mc.rhi = rhi;
+                    double corner[8][3];
+                    double zmin = INFINITY, zmax = -INFINITY;
+                    for (int c = 0; c < 8; ++c) {
+                        corner[c][a0] = (c & 1) ? hi0 + kFootSlack : lo0 - kFootSlack;
+                        corner[c][a1] = (c & 2) ? hi1 + kFootSlack : lo1 - kFootSlack;
+                        corner[c][np] = mc.a + mc.b * corner[c][a0] + mc.c * corner[c][a1] + ((c & 4) ? rhi : rlo);
+                        zmin = std::min(zmin, corner[c][np]); zmax = std::max(zmax, corner[c][np]);
                     }
-                    best_far = std::min(best_far, std::sqrt(far2));
-                }
-                for (int v : front) {
-                    const double *p = pack->vertices + 3 * v;
-                    double near2 = 0;
-                    for (int k = 0; k < 3; ++k) {
-                        double g = std::max(0.0, std::max(blo[k] - p[k], p[k] - bhi[k]));
-                        near2 += g * g;
+                    zmin -= 1e-9; zmax += 1e-9;
+                    for (int p = 0; p < pack->n_planes; ++p) {
+                        const double *n = pack->plane_n + 3 * p;
+                        double worst = -INFINITY;
+                        for (int c = 0; c < 8; ++c)
+                            worst = std::max(worst, n[0] * corner[c][0] + n[1] * corner[c][1] + n[2] * corner[c][2]);
+                        if (worst > pack->plane_off[p] - kMargin) pidx.push_back(p);
                     }
-                    if (std::sqrt(near2) <= best_far + kVertSlack) {
-                        VertCand vc;
-                        vc.x = p[0]; vc.y = p[1]; vc.z = p[2];
-                        vc.id = (unsigned)v;
-                        vc.rec = vrec[v];
-                        vcs.push_back(vc);
+                    mc.n_planes = (int)pidx.size();
+                    // candidates for the nearest front vertex of any point of the region (its bounding box)
+                    double blo[3], bhi[3];
+                    blo[a0] = lo0 - kFootSlack; bhi[a0] = hi0 + kFootSlack;
+                    blo[a1] = lo1 - kFootSlack; bhi[a1] = hi1 + kFootSlack;
+                    blo[np] = zmin; bhi[np] = zmax;
+                    double best_far = INFINITY;
+                    for (int v : front) {
+                        const double *p = pack->vertices + 3 * v;
+                        double far2 = 0;
+                        for (int k = 0; k < 3; ++k) {
+                            double f = std::max(std::fabs(p[k] - blo[k]), std::fabs(p[k] - bhi[k]));
+                            far2 += f * f;
+                        }
+                        best_far = std::min(best_far, std::sqrt(far2));
                     }
+                    for (int v : front) {
+                        const double *p = pack->vertices + 3 * v;
+                        double near2 = 0;
+                        for (int k = 0; k < 3; ++k) {
+                            double g = std::max(0.0, std::max(blo[k] - p[k], p[k] - bhi[k]));
+                            near2 += g * g;
+                        }
+                        if (std::sqrt(near2) <= best_far + kVertSlack) {
+                            VertCand vc;
+                            vc.x = p[0]; vc.y = p[1]; vc.z = p[2];
+                            vc.id = (unsigned)v;
+                            vc.rec = vrec[v];
+                            vcs.push_back(vc);
+                        }
+                    }
+                    // Pruning by domination: vertex v cannot be nearest to any point q of the box if another candidate u is
+                    // strictly closer everywhere in it: |q-u|^2 < |q-v|^2  <=>  2 q.(v-u) < |v|^2 - |u|^2, linear in q, so
+                    // the box corner that maximises the left side decides (slack 1e-9: far above FP64 round-off of the
+                    // device's squared distances, so a dropped vertex is never nearest and never tied).  The box criterion
+                    // alone keeps everything in a ring as wide as the box around the nearest vertex -- hundreds of vertices
+                    // over a flat face whose own vertices are far away.
+                    if (vcs.size() > 8) {
+                        const size_t n = vcs.size();
+                        std::vector<double> c0(n);          // distance from the box centre: likely dominators first
+                        const double ctr[3] = {0.5 * (blo[0] + bhi[0]), 0.5 * (blo[1] + bhi[1]), 0.5 * (blo[2] + bhi[2])};
+                        std::vector<int> order(n);
+                        for (size_t i = 0; i < n; ++i) {
+                            const double dx = vcs[i].x - ctr[0], dy = vcs[i].y - ctr[1], dz = vcs[i].z - ctr[2];
+                            c0[i] = dx * dx + dy * dy + dz * dz;
+                            order[i] = (int)i;
+                        }
+                        std::sort(order.begin(), order.end(), [&](int x, int y) { return c0[x] < c0[y]; });
+                        std::vector<char> keep(n, 1);
+                        const size_t n_dom = std::min<size_t>(n, 24);
+                        for (size_t i = 0; i < n; ++i) {
+                            const VertCand &v = vcs[i];
+                            const double v2 = v.x * v.x + v.y * v.y + v.z * v.z;
+                            for (size_t j = 0; j < n_dom; ++j) {
+                                const int ui = order[j];
+                                if ((size_t)ui == i) continue;
+                                const VertCand &u = vcs[ui];
+                                const double d[3] = {2.0 * (v.x - u.x), 2.0 * (v.y - u.y), 2.0 * (v.z - u.z)};
+                                double lhs = 0.0;
+                                for (int k = 0; k < 3; ++k) lhs += std::max(d[k] * blo[k], d[k] * bhi[k]);
+                                const double rhs = v2 - (u.x * u.x + u.y * u.y + u.z * u.z);
+                                if (lhs < rhs - 1e-9) { keep[i] = 0; break; }
+                            }
+                        }
+                        // a dominator is never dominated itself by something it dominates: the nearest vertex of the box
+                        // centre always survives, so the list cannot come out empty
+                        size_t w = 0;
+                        for (size_t i = 0; i < n; ++i)
+                            if (keep[i]) vcs[w++] = vcs[i];
+                        vcs.resize(w);
+                    }
+                    mc.n_verts = (int)vcs.size();
+};
+                if (edge_cell) {
+                    build_lists(kPadBelowEdge);
+                    fallback_link = emit_blob();
                 }
-                mc.n_verts = (int)vcs.size();
+                build_lists(kPadBelow);
                 planes_total += mc.n_planes;
                 verts_total += mc.n_verts;
                 ++inside_cells;
@@ -346,24 +424,12 @@ int build_move_cells(PaintrlEngine *e, const PaintrlPartPack *pack, const std::v
                 mc.n_planes = (int)tmp.size();
             }
             // ---- the cell's blob: region, copies of its planes, its vertex candidates
-            if (mc.n_planes > 0xffff || mc.n_verts > 0xffff || blob.size() / 4 > 0xfffffff0u)
-                return fail(PAINTRL_E_INVALID, "move cell list too long");
+            if (too_long) return fail(PAINTRL_E_INVALID, "move cell list too long");
+            const unsigned long long primary = emit_blob();
+            if (too_long) return fail(PAINTRL_E_INVALID, "move cell list too long");
             uint2 &en = entries[(size_t)cy * nx + cx];
-            en.x = (unsigned)(blob.size() / 4);
-            en.y = (unsigned)mc.n_planes | ((unsigned)mc.n_verts << 16);
-            const double hdr[8] = {mc.a, mc.b, mc.c, mc.rlo, mc.rhi, 0.0, 0.0, 0.0};
-            blob.insert(blob.end(), hdr, hdr + 8);
-            for (int p : pidx) {
-                const double pl[4] = {pack->plane_n[3 * p], pack->plane_n[3 * p + 1], pack->plane_n[3 * p + 2], pack->plane_off[p]};
-                blob.insert(blob.end(), pl, pl + 4);
-            }
-            for (const VertCand &vc : vcs) {
-                double v[4] = {vc.x, vc.y, vc.z, 0.0};
-                const unsigned long long meta = (unsigned long long)vc.id | ((unsigned long long)vc.rec << 32);
-                std::memcpy(&v[3], &meta, 8);
-                blob.insert(blob.end(), v, v + 4);
-            }
-            plane_refs += pidx.size();
+            en.x = (unsigned)(primary & 0xffffffffu);
+            en.y = (unsigned)(primary >> 32);
         }
     }
     blob.resize(blob.size() + 4 * 64, 0.0);   // lanes may read one round of sectors past a short list

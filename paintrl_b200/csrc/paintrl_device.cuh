@@ -557,7 +557,7 @@ __device__ __forceinline__ void g_dbg_log_ray(const Vec3 &frm, double d0, double
 // candidates; `vc0` / `vc1` hold this lane's first candidate), else ref.blob == nullptr.
 // (pf0, pf1): expected displacement of the next ray along the principal axes -- its cell's blob is
 // prefetched into L1 while this ray is being tested (do_prefetch).
-constexpr int kRayAttempts = 3;
+constexpr int kRayAttempts = 5;   // two tiers per silhouette cell: a ray may need (cell A, its fallback, cell B, its fallback)
 
 // Region test of a move cell: does the point h (principal coordinates h0, h1) lie in the cell
 // (cx, cy) and within the slab around its fitted surface plane?
@@ -589,21 +589,34 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Ax &ax, const 
 #else
 #define PAINTRL_WHY(v)
 #endif
+    int tried_cx = -1, tried_cy = -1;
+    unsigned long long link = 0ull;    // fallback blob of the cell just tried (offset | counts << 32), 0: none
 #pragma unroll 1
     for (int attempt = 0; attempt < kRayAttempts; ++attempt) {
         const double g0 = comp(h, ax.a0), g1 = comp(h, ax.a1);
         int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
         int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
-        if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) { PAINTRL_WHY(1); break; }
+        if (link == 0ull && (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny)) { PAINTRL_WHY(1); break; }
 #if defined(PAINTRL_TRACE) || defined(PAINTRL_PROFILE)
         counts += 1 << 24;   // cell attempts of the step (diagnostic builds only)
 #endif
-        const uint2 entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+        uint2 entry;
+        if (link != 0ull) {
+            // the cell just tried is a silhouette cell whose thin primary slab did not hold the entry point: its second
+            // blob (deep slab, build_move_cells) comes next, whichever cell the provisional entry point fell into
+            cx = tried_cx; cy = tried_cy;
+            entry = make_uint2((unsigned)link, (unsigned)(link >> 32));
+        } else {
+            if (cx == tried_cx && cy == tried_cy) break;     // the same cell again: same list, same result
+            entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+        }
+        tried_cx = cx; tried_cy = cy;
         const int n_planes = (int)(entry.y & 0xffffu), n_verts = (int)(entry.y >> 16);
         if (n_planes <= 0) { PAINTRL_WHY(2); break; }
         const double2 *blob = pk.mc_blob + (size_t)entry.x * 2;
         // one round of independent loads: region, this lane's plane(s) (in slab_pass), first vertex candidate
-        const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);   // (a, b) (c, rlo) (rhi, -)
+        const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);   // (a, b) (c, rlo) (rhi, link)
+        link = (unsigned long long)__double_as_longlong(hpv.y);
         if (grp.gl < n_verts) {
             vc0 = __ldg(blob + 2 * (2 + n_planes + grp.gl));
             vc1 = __ldg(blob + 2 * (2 + n_planes + grp.gl) + 1);
@@ -624,7 +637,7 @@ __device__ __forceinline__ bool ray_test(const DevPack &pk, const Ax &ax, const 
         PAINTRL_PROF(7, grp.gl == 0);
         if (r.outside || r.t_in > r.t_out || r.t_in > 1.0 || r.t_out < 0.0) return false;   // (1)
         candidate = false;
-        if (!(r.t_in > -INFINITY)) { PAINTRL_WHY(3); break; }
+        if (!(r.t_in > -INFINITY)) { if (link != 0ull) continue; PAINTRL_WHY(3); break; }
         candidate = true;
         sub = blob + 4; n_sub = n_planes;
         h.x = frm.x + d0 * r.t_in; h.y = frm.y + d1 * r.t_in; h.z = frm.z + d2 * r.t_in;

@@ -797,20 +797,31 @@ __device__ __forceinline__ bool beam_ray(const DevPack &pk, int a0, int a1, Vec3
     Vec3 h = {frm.x + d0 * 0.5, frm.y + d1 * 0.5, frm.z + d2 * 0.5};
     double t_in, t_out;
     bool outside;
+    int tried_cx = -1, tried_cy = -1;
+    unsigned long long link = 0ull;
 #pragma unroll 1
     for (int attempt = 0; attempt < kRayAttempts; ++attempt) {
         const double g0 = comp(h, a0), g1 = comp(h, a1);
-        const int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
-        const int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
-        if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) break;
-        const uint2 entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+        int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
+        int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
+        if (link == 0ull && (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny)) break;
+        uint2 entry;
+        if (link != 0ull) {                              // a silhouette cell's deeper second blob follows its thin primary
+            cx = tried_cx; cy = tried_cy;
+            entry = make_uint2((unsigned)link, (unsigned)(link >> 32));
+        } else {
+            if (cx == tried_cx && cy == tried_cy) break;
+            entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+        }
+        tried_cx = cx; tried_cy = cy;
         const int n_planes = (int)(entry.y & 0xffffu);
         if (n_planes <= 0) break;
         const double2 *blob = pk.mc_blob + (size_t)entry.x * 2;
         const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);
+        link = (unsigned long long)__double_as_longlong(hpv.y);
         slab_serial(blob + 4, n_planes, frm, d0, d1, d2, t_in, t_out, outside);
         if (outside || t_in > t_out || t_in > 1.0 || t_out < 0.0) return false;          // a miss proven by the subset
-        if (!(t_in > -INFINITY)) break;
+        if (!(t_in > -INFINITY)) { if (link != 0ull) continue; break; }
         h.x = frm.x + d0 * t_in; h.y = frm.y + d1 * t_in; h.z = frm.z + d2 * t_in;
         if (in_cell_region(pk, h, comp(h, a0), comp(h, a1), comp(h, npax), cx, cy, abv, clv, hpv)) {
             if (!(0.0 <= t_in)) return false;
@@ -1191,7 +1202,9 @@ __device__ unsigned long long g_fast_reasons[8];   // why rays left the fast pat
 template <int G>
 __device__ __forceinline__ int ray_fast(const DevPack &pk, const Ax &ax, const Vec3 &frm, const Vec3 &to, const Grp &grp, Vec3 &hit,
                                         CellRef &ref, double2 &vc0, double2 &vc1, double pf0, double pf1, bool do_prefetch,
-                                        const unsigned *miss_cache_ptr) {
+                                        const unsigned *miss_cache_ptr, int &path_counts, int &path_sizes) {
+    // path_counts (read by the trace build only): bits 0..7 off-part sub-steps, 8..15 misses proven by the cached plane
+    // pair, 16..23 verify passes, 24..30 cell attempts
     const double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
     const int npax = 3 - ax.a0 - ax.a1;
     Vec3 h = {frm.x + d0 * kHookDistance, frm.y + d1 * kHookDistance, frm.z + d2 * kHookDistance};
@@ -1201,18 +1214,35 @@ __device__ __forceinline__ int ray_fast(const DevPack &pk, const Ax &ax, const V
     int why = 4;
     const double2 *sub = nullptr;      // the plane list of the last cell tried
     int n_sub = 0;
+    int tried_cx = -1, tried_cy = -1;
+    unsigned long long link = 0ull;    // fallback blob of the cell just tried (offset | counts << 32), 0: none
 #pragma unroll 1
     for (int attempt = 0; attempt < kRayAttempts; ++attempt) {
+        path_counts += 1 << 24;
         const double g0 = comp(h, ax.a0), g1 = comp(h, ax.a1);
-        const int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
-        const int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
-        if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) { why = 1; break; }
-        const uint2 entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+        int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
+        int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
+        if (link == 0ull && (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny)) { why = 1; break; }
+        uint2 entry;
+        if (link != 0ull) {
+            // the cell just tried is a silhouette cell whose thin primary slab did not hold the entry point: its second
+            // blob (deep slab, build_move_cells) comes next, whichever cell the provisional entry point fell into
+            cx = tried_cx; cy = tried_cy;
+            entry = make_uint2((unsigned)link, (unsigned)(link >> 32));
+        } else {
+            if (cx == tried_cx && cy == tried_cy) break;     // the same cell again: same list, same result
+            entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+        }
+        tried_cx = cx; tried_cy = cy;
         const int n_planes = (int)(entry.y & 0xffffu), n_verts = (int)(entry.y >> 16);
         if (n_planes <= 0) { why = 2; break; }
+#ifdef PAINTRL_TRACE
+        path_sizes = max(path_sizes & 0xff, min(n_planes, 255)) | (max(path_sizes >> 8, min(n_verts, 255)) << 8);
+#endif
         const double2 *blob = pk.mc_blob + (size_t)entry.x * 2;
         sub = blob + 4; n_sub = n_planes;
         const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);
+        link = (unsigned long long)__double_as_longlong(hpv.y);
         if (grp.gl < n_verts) {
             vc0 = __ldg(blob + 2 * (2 + n_planes + grp.gl));
             vc1 = __ldg(blob + 2 * (2 + n_planes + grp.gl) + 1);
@@ -1231,7 +1261,7 @@ __device__ __forceinline__ int ray_fast(const DevPack &pk, const Ax &ax, const V
         r = slab_pass<G>(blob + 4, n_planes, frm, d0, d1, d2, grp);
         if (r.outside || r.t_in > r.t_out || r.t_in > 1.0 || r.t_out < 0.0) return 0;   // (1)
         candidate = false;
-        if (!(r.t_in > -INFINITY)) { why = 3; break; }
+        if (!(r.t_in > -INFINITY)) { if (link != 0ull) continue; why = 3; break; }
         candidate = true;
         h.x = frm.x + d0 * r.t_in; h.y = frm.y + d1 * r.t_in; h.z = frm.z + d2 * r.t_in;
         if (in_cell_region(pk, h, comp(h, ax.a0), comp(h, ax.a1), comp(h, npax), cx, cy, abv, clv, hpv)) {   // (2a)
@@ -1243,8 +1273,10 @@ __device__ __forceinline__ int ray_fast(const DevPack &pk, const Ax &ax, const V
         }
     }
     // (1) again with the pair of planes that decided this environment's last full scan, as ray_test does
+    path_counts += 1 << 8;
     if (pair_proves_miss(pk, *miss_cache_ptr, r, candidate, frm, d0, d1, d2)) return 0;
     if (candidate) {
+        path_counts += 1 << 16;
         // (2b) the entry point of the last list lies in the region of none of the cells tried (a ray grazing a sharp
         // feature of the hull): one division-free pass over all hull planes decides whether that list was enough.
         // Out-of-line, rolled: a handful of rays in a million come here, but a step is as slow as its slowest environment.
@@ -1314,6 +1346,7 @@ __device__ __forceinline__ bool move_fast_body(const DevPack &pk, const DevConfi
     }
     const double delta1 = (u1 * kStepSize) / kPaintPerAction, delta2 = (u2 * kStepSize) / kPaintPerAction;
     const int counter_before = term_counter;
+    int path_counts = 0, path_sizes = 0;   // trace build: largest plane / vertex list met
     double quat[4];
     MoveOut *mv = FUSED ? smv : &ea.moves[env];
     double *centers = &mv->centers[0][0];
@@ -1329,7 +1362,7 @@ __device__ __forceinline__ bool move_fast_body(const DevPack &pk, const DevConfi
         double2 vc0 = make_double2(0.0, 0.0), vc1 = vc0;
         const double *rec = nullptr;
         const int code = ray_fast<G>(pk, ax, p, end, grp, hit, ref, vc0, vc1, delta1, delta2_scaled, s + 1 < kPaintPerAction,
-                                     &ea.moves[env].miss_cache);
+                                     &ea.moves[env].miss_cache, path_counts, path_sizes);
         if (code == 2) {
             // not decidable on the fast path: nothing of this step has been published (the shot centres written so
             // far are rewritten by the generic pass); the environment's paint warp takes the move over
@@ -1352,6 +1385,7 @@ __device__ __forceinline__ bool move_fast_body(const DevPack &pk, const DevConfi
             cur_n.x = -nx; cur_n.y = -ny; cur_n.z = -nz;
             flags |= kFlagLastOnPart;
         } else {
+            path_counts += 1;
             quat_from_normal(cur_n, quat);                              // robot.py:313: the orientation of the kept normal
             pos = transform_point(cur_p, quat, delta2, delta1, 0.0);    // robot.py:317 (sic)
             center = transform_point(pos, quat, 0.0, 0.0, 0.1);         // robot.py:277-278
@@ -1365,6 +1399,10 @@ __device__ __forceinline__ bool move_fast_body(const DevPack &pk, const DevConfi
         if (grp.gl == 0) { centers[3 * s] = center.x; centers[3 * s + 1] = center.y; centers[3 * s + 2] = center.z; }
         cur_p = pos;
     }
+#ifdef PAINTRL_TRACE
+    if (grp.gl == 0 && env < 65536) g_trace[env][6] |= ((unsigned long long)(unsigned)path_counts << 16) | ((unsigned long long)(unsigned)path_sizes << 48);
+#endif
+    (void)path_sizes;
     if (grp.gl == 0) {
         reinterpret_cast<double2 *>(gst)[0] = make_double2(cur_p.x, cur_p.y);
         reinterpret_cast<double2 *>(gst)[1] = make_double2(cur_p.z, quat[0]);
