@@ -491,10 +491,20 @@ def measure(key, args, rank, local_rank, world_size, device, steps, warmup, e2e=
         counters, counters_sha = captured_counters(key)
         sha = kernel_source_sha()
         sm_hz = (clocks.get('sm_mhz') or 1965.0) * 1e6
-        roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+        per_step_launches = (s1['kernel_launches'] - s0['kernel_launches']) / float(max(1, steps))
+        if cfg.paint_method == 'normal':
+            kernel_desc = 'paintrl::move_kernel + paintrl::paint_normal_kernel (beam-fan paint method: two launches per step)'
+        elif per_step_launches < 1.5:
+            kernel_desc = ('paintrl::step_fused_kernel (one launch per step: a warp runs the move and the paint phase of its environment; '
+                           'batches below 16384 environments per GPU)')
+        else:
+            kernel_desc = ('paintrl::move_fast_kernel + paintrl::paint_kernel (two launches per step; the paint grid is a programmatic '
+                           'dependent launch whose warps acquire per-environment flags)')
+        roof = {'bound': 'hbm', 'model_bound': 'hbm (SURVEY 8d algorithmic-bytes model: achieved / peak / frac are on that model)',
+                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                 'traffic': None, 'traffic_unit': 'bytes per step (ncu capture, profiles/kernel_counters.json)',
                 'peak_source': peak_src,
-                'kernel': 'paintrl::move_kernel + paintrl::paint_kernel (one step = two launches; the paint grid is a programmatic dependent launch whose warps acquire per-environment flags)',
+                'kernel': kernel_desc,
                 'kernel_ms': kernel_ms, 'algorithmic_bytes_per_env_step': b_alg,
                 'footprint_union_texels_mean': u_mean, 'p_reset': p_reset,
                 'ray_full_scans_per_env_step': (s1['ray_full_scans'] - s0['ray_full_scans']) / max(1, steps_done),
@@ -513,11 +523,14 @@ def measure(key, args, rank, local_rank, world_size, device, steps, warmup, e2e=
             roof['issue_frac'] = insts / (N_SMS * 4 * sm_hz * kernel_ms * 1e-3)
             # what the step is bound by, read off the two measured fractions: neither reaches its roof when
             # both are low -- the remainder is dependent latency (FP64 chains, table lookups) per environment
+            roof['serialized_kernel_us'] = {k: v['us'] for k, v in counters.get('kernels', {}).items()}
             if roof['dram_frac_measured'] >= 0.6:
                 roof['bound_measured'] = 'hbm'
             elif roof['issue_frac'] >= 0.6:
                 roof['bound_measured'] = 'instruction issue'
+                roof['bound'] = 'issue'
             else:
+                roof['bound'] = 'latency'
                 roof['bound_measured'] = ('latency (dependent FP64 / lookup chains per environment; issue slots %.0f %% busy, '
                                           'DRAM %.1f %% of peak -- NOT hbm-bound; `frac` is the algorithmic-bytes model of SURVEY 8d)'
                                           % (100 * roof['issue_frac'], 100 * roof['dram_frac_measured']))
