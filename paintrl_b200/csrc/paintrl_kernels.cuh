@@ -789,8 +789,9 @@ __device__ __forceinline__ void slab_serial(const double2 *planes, int n, const 
     }
 }
 
-// shim S1 rayTestBatch for one beam, by one lane
-__device__ __forceinline__ bool beam_ray(const DevPack &pk, int a0, int a1, Vec3 frm, Vec3 to, Vec3 &hit) {
+// shim S1 rayTestBatch for one beam, by one lane, as far as the move cells' plane lists decide it: 0 miss, 1 hit, 2
+// undecided (the caller scans all hull planes with the whole warp: one lane doing that alone held up the other 31)
+__device__ __forceinline__ int beam_ray(const DevPack &pk, int a0, int a1, Vec3 frm, Vec3 to, Vec3 &hit) {
     const double d0 = to.x - frm.x, d1 = to.y - frm.y, d2 = to.z - frm.z;
     const int npax = 3 - a0 - a1;
     // the TCP hovers kHookDistance above the surface and the fan's plane lies 0.2 ahead: expect the entry half way
@@ -820,19 +821,16 @@ __device__ __forceinline__ bool beam_ray(const DevPack &pk, int a0, int a1, Vec3
         const double2 abv = __ldg(blob), clv = __ldg(blob + 1), hpv = __ldg(blob + 2);
         link = (unsigned long long)__double_as_longlong(hpv.y);
         slab_serial(blob + 4, n_planes, frm, d0, d1, d2, t_in, t_out, outside);
-        if (outside || t_in > t_out || t_in > 1.0 || t_out < 0.0) return false;          // a miss proven by the subset
+        if (outside || t_in > t_out || t_in > 1.0 || t_out < 0.0) return 0;              // a miss proven by the subset
         if (!(t_in > -INFINITY)) { if (link != 0ull) continue; break; }
         h.x = frm.x + d0 * t_in; h.y = frm.y + d1 * t_in; h.z = frm.z + d2 * t_in;
         if (in_cell_region(pk, h, comp(h, a0), comp(h, a1), comp(h, npax), cx, cy, abv, clv, hpv)) {
-            if (!(0.0 <= t_in)) return false;
+            if (!(0.0 <= t_in)) return 0;
             hit = h;
-            return true;
+            return 1;
         }
     }
-    slab_serial(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, frm, d0, d1, d2, t_in, t_out, outside);
-    if (outside || !(t_in <= t_out && 0.0 <= t_in && t_in <= 1.0)) return false;
-    hit.x = frm.x + d0 * t_in; hit.y = frm.y + d1 * t_in; hit.z = frm.z + d2 * t_in;
-    return true;
+    return 2;
 }
 
 // cKDTree.query(point, k = 1) over the front texel positions, by one lane: returns the slot
@@ -844,9 +842,14 @@ __device__ __forceinline__ int nearest_texel(const DevPack &pk, int a0, int a1, 
     const double cw = 1.0 / pk.cx_inv;
     double best = INFINITY;
     int arg = -1;
+    // Block search that grows to what the best distance so far demands: every texel outside the block lies beyond the
+    // block's border in the principal plane, so the block's winner is the global one as soon as its (3-D) distance is
+    // below the border distance.  Hits lie on the hull, texels on the mesh: over the part's concave regions the nearest
+    // texel is centimetres away and a fixed schedule of block sizes fell through to a scan of every texel.
+    int R = 1, D = 1;
 #pragma unroll 1
-    for (int R = 1; R <= 9; R += 4) {                 // half-widths 1, 5, 9 cells; then everything
-        const int ra = max(r0 - 1, 0), rb = min(r0 + 1, pk.n_rows - 1);
+    for (int round = 0; round < 6; ++round) {
+        const int ra = max(r0 - D, 0), rb = min(r0 + D, pk.n_rows - 1);
         const int ca = max(c0 - R, 0), cb = min(c0 + R, pk.ncx - 1);
         best = INFINITY; arg = -1;
         for (int r = ra; r <= rb; ++r) {
@@ -860,14 +863,19 @@ __device__ __forceinline__ int nearest_texel(const DevPack &pk, int a0, int a1, 
                 if (d < best) { best = d; arg = j; }
             }
         }
-        // every texel outside the block lies beyond the block's border in the principal plane
-        double m = INFINITY;
-        if (ca > 0) m = fmin(m, q0 - (pk.cx_o0 + ca * cw));
-        if (cb < pk.ncx - 1) m = fmin(m, (pk.cx_o0 + (cb + 1) * cw) - q0);
-        if (ra > 0) m = fmin(m, q1 - (pk.row_o1 + ra * pk.row_h));
-        if (rb < pk.n_rows - 1) m = fmin(m, (pk.row_o1 + (rb + 1) * pk.row_h) - q1);
-        m -= 1e-9;
+        double m0 = INFINITY, m1 = INFINITY;
+        if (ca > 0) m0 = fmin(m0, q0 - (pk.cx_o0 + ca * cw));
+        if (cb < pk.ncx - 1) m0 = fmin(m0, (pk.cx_o0 + (cb + 1) * cw) - q0);
+        if (ra > 0) m1 = fmin(m1, q1 - (pk.row_o1 + ra * pk.row_h));
+        if (rb < pk.n_rows - 1) m1 = fmin(m1, (pk.row_o1 + (rb + 1) * pk.row_h) - q1);
+        const double m = fmin(m0, m1) - 1e-9;
         if (arg >= 0 && (m == INFINITY || (m > 0.0 && best < m * m))) return __ldg(&pk.nn_rep_slot[arg]);
+        if (m == INFINITY) break;                      // the block is the whole table and holds no texel
+        if (arg < 0) { R = 2 * R + 1; D += 1; continue; }
+        // the block that certainly holds the winner: border distance above sqrt(best) on every side
+        const double rho = sqrt(best) + 2e-9;
+        if (!(m0 - 1e-9 > rho)) R = max(R + 1, (int)(rho * pk.cx_inv) + 2);
+        if (!(m1 - 1e-9 > rho)) D = max(D + 1, (int)(rho * pk.row_inv) + 2);
     }
     best = INFINITY; arg = -1;
     for (int r = 0; r < pk.n_rows; ++r) {
@@ -902,12 +910,34 @@ __device__ __forceinline__ void stamp_normal(const DevPack &pk, const DevConfig 
         const Vec3 pose = {ns.pos[s][0], ns.pos[s][1], ns.pos[s][2]};
         const Vec3 center = {ws.mv.centers[s][0], ws.mv.centers[s][1], ws.mv.centers[s][2]};
         int hits = 0;
-        for (int b = lane; b < cfg.n_beams; b += 32) {
-            const Vec3 dst = transform_point(pose, ns.quat[s], __ldg(&cfg.beam_plain[3 * b]), __ldg(&cfg.beam_plain[3 * b + 1]),
-                                             __ldg(&cfg.beam_plain[3 * b + 2]));
-            Vec3 hit;
+        for (int b0 = 0; b0 < cfg.n_beams; b0 += 32) {
+            const int b = b0 + lane;
+            const bool live = b < cfg.n_beams;
+            Vec3 dst = pose, hit = pose;
+            int code = 0;
+            if (live) {
+                dst = transform_point(pose, ns.quat[s], __ldg(&cfg.beam_plain[3 * b]), __ldg(&cfg.beam_plain[3 * b + 1]),
+                                      __ldg(&cfg.beam_plain[3 * b + 2]));
+                code = beam_ray(pk, ax.a0, ax.a1, pose, dst, hit);
+            }
+            // beams no plane list decided: the serial slab test over all hull planes, the whole warp on one beam at a time
+            unsigned undecided = __ballot_sync(kFull, code == 2);
+            while (undecided) {
+                const int src = __ffs(undecided) - 1;
+                undecided &= undecided - 1;
+                const double d0 = __shfl_sync(kFull, dst.x, src) - pose.x, d1 = __shfl_sync(kFull, dst.y, src) - pose.y,
+                             d2 = __shfl_sync(kFull, dst.z, src) - pose.z;
+                unsigned args;
+                const SlabResult r = slab_pass_all<32>(reinterpret_cast<const double2 *>(pk.planes), pk.n_planes, pose, d0, d1, d2,
+                                                       make_grp<32>(lane), &args);
+                if (lane == src) {
+                    code = (r.outside || !(r.t_in <= r.t_out && 0.0 <= r.t_in && r.t_in <= 1.0)) ? 0 : 1;
+                    hit.x = pose.x + d0 * r.t_in; hit.y = pose.y + d1 * r.t_in; hit.z = pose.z + d2 * r.t_in;
+                }
+            }
+            if (!live) continue;
             int slot = -1;
-            if (beam_ray(pk, ax.a0, ax.a1, pose, dst, hit)) slot = nearest_texel(pk, ax.a0, ax.a1, hit);
+            if (code == 1) slot = nearest_texel(pk, ax.a0, ax.a1, hit);
             ns.beam_slot[b] = slot >= 0 ? (uint16_t)slot : (uint16_t)0xFFFF;
             if (slot >= 0) {
                 hits++;
@@ -1711,7 +1741,7 @@ paint_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io, c
 
 // Paint kernel of the normal paint method (staged plane, generic axes; one warp per block).
 template <int COLOR>
-__global__ void __launch_bounds__(32, 8)
+__global__ void __launch_bounds__(32, 14)   // 15 KB of shared memory per warp: 14 warps per SM
 paint_normal_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io, const ColdArgs *cold) {
     __shared__ WarpScratch<true> scratch[1];
     __shared__ NormalScratch nscratch[1];
