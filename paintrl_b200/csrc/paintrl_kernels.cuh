@@ -1433,6 +1433,7 @@ __device__ __forceinline__ bool move_fast_body(const DevPack &pk, const DevConfi
     if (grp.gl == 0 && env < 65536) g_trace[env][6] |= ((unsigned long long)(unsigned)path_counts << 16) | ((unsigned long long)(unsigned)path_sizes << 48);
 #endif
     (void)path_sizes;
+    if (FUSED) __syncwarp();     // every lane read the record from the warp's shared scratch at the top; lane 0 rewrites it
     if (grp.gl == 0) {
         reinterpret_cast<double2 *>(gst)[0] = make_double2(cur_p.x, cur_p.y);
         reinterpret_cast<double2 *>(gst)[1] = make_double2(cur_p.z, quat[0]);
