@@ -259,6 +259,17 @@ int paintrl_rasterize_texels(const double *tri_a, const double *tri_b, const dou
                              int32_t device, int32_t capacity, int32_t *texel_ij_out,
                              double *texel_pos_out, int32_t *n_texels_out);
 
+/* Load-time silhouette scans (Part._get_exact_boundary, bullet_paint_wrapper.py:906-920, called by _set_grid_dict
+ * :922-963 for the left and the right end of every row of the 100-row grid): from `points[k]` march along
+ * `proof_axis` in 1 mm steps (towards smaller values where is_min[k]) and test, at every step, a ray along
+ * `non_principal_axis` (end points 1, 2, 3 ... beyond the point on either side, as the reference accumulates them)
+ * against the collision hull  plane_n . x <= plane_off  with shim S1's slab arithmetic; boundary_out[k] is the coordinate
+ * of the first step whose ray misses, found_out[k] = 0 when none of the `steps_range` steps does (the reference then
+ * returns None).  One warp per scan on the GPU.  All pointers are HOST pointers; synchronous. */
+int paintrl_silhouette_march(const double *plane_n, const double *plane_off, int32_t n_planes, const double *points,
+                             const int8_t *is_min, int32_t n_scans, int32_t proof_axis, int32_t non_principal_axis,
+                             int32_t steps_range, int32_t device, double *boundary_out, int8_t *found_out);
+
 /*
  * The grid-world ParamTestEnv (PaintRLEnv/param_test_env.py:96-246; driven by param_test_*.py), batched:
  * one handle = num_envs independent size x size worlds on one GPU.  Same conventions as above.

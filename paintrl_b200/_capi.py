@@ -109,6 +109,7 @@ SIGNATURES = {
     'paintrl_job_status': (ctypes.c_int, [_VP, _VP, _VP]),
     'paintrl_stats': (ctypes.c_int, [_VP, ctypes.POINTER(PaintrlStats)]),
     'paintrl_rasterize_texels': (ctypes.c_int, [_VP, _VP, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP, _VP, _VP]),
+    'paintrl_silhouette_march': (ctypes.c_int, [_VP, _VP, _I32, _VP, _VP, _I32, _I32, _I32, _I32, _I32, _VP, _VP]),
     'paintrl_param_create': (ctypes.c_int, [ctypes.POINTER(PaintrlParamConfig), _I32, _I32, ctypes.POINTER(_VP)]),
     'paintrl_param_destroy': (None, [_VP]),
     'paintrl_param_obs_dim': (_I32, [_VP]),

@@ -945,6 +945,37 @@ int paintrl_rasterize_texels(const double *tri_a, const double *tri_b, const dou
     return PAINTRL_OK;
 }
 
+/* Part._get_exact_boundary scans on the GPU (see paintrl_raster.cuh and paintrl.h). */
+int paintrl_silhouette_march(const double *plane_n, const double *plane_off, int32_t n_planes, const double *points,
+                             const int8_t *is_min, int32_t n_scans, int32_t proof_axis, int32_t non_principal_axis,
+                             int32_t steps_range, int32_t device, double *boundary_out, int8_t *found_out) {
+    if (!plane_n || !plane_off || !points || !is_min || !boundary_out || !found_out) return fail(PAINTRL_E_INVALID, "null argument");
+    if (n_planes <= 0 || n_scans < 0 || steps_range < 0 || proof_axis < 0 || proof_axis > 2 || non_principal_axis < 0 ||
+        non_principal_axis > 2 || proof_axis == non_principal_axis)
+        return fail(PAINTRL_E_INVALID, "bad plane / scan count or axes");
+    if (n_scans == 0) return PAINTRL_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    std::vector<double4> planes((size_t)n_planes);
+    for (int q = 0; q < n_planes; ++q) planes[q] = make_double4(plane_n[3 * q], plane_n[3 * q + 1], plane_n[3 * q + 2], plane_off[q]);
+    DeviceArena arena;
+    double4 *d_planes = nullptr;
+    double *d_points = nullptr, *d_bound = nullptr;
+    signed char *d_min = nullptr, *d_found = nullptr;
+    if (arena.alloc((void **)&d_planes, sizeof(double4) * n_planes) != cudaSuccess || arena.alloc((void **)&d_points, sizeof(double) * 3 * n_scans) != cudaSuccess ||
+        arena.alloc((void **)&d_bound, sizeof(double) * n_scans) != cudaSuccess || arena.alloc((void **)&d_min, n_scans) != cudaSuccess ||
+        arena.alloc((void **)&d_found, n_scans) != cudaSuccess)
+        return fail(PAINTRL_E_CUDA, "device allocation failed (silhouette scans)");
+    CUDA_TRY(cudaMemcpy(d_planes, planes.data(), sizeof(double4) * n_planes, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_points, points, sizeof(double) * 3 * n_scans, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_min, is_min, n_scans, cudaMemcpyHostToDevice));
+    silhouette_march_kernel<<<(n_scans + 3) / 4, 128>>>(d_planes, n_planes, d_points, d_min, n_scans, proof_axis, non_principal_axis,
+                                                        steps_range, d_bound, d_found);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpy(boundary_out, d_bound, sizeof(double) * n_scans, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(found_out, d_found, n_scans, cudaMemcpyDeviceToHost));
+    return PAINTRL_OK;
+}
+
 /* ---- the rollout policy (paint_ppo.py:179-183), see paintrl_policy.cuh ---- */
 struct PaintrlPolicyEngine {
     int device = 0;
@@ -1350,7 +1381,7 @@ int paintrl_step(PaintrlHandle h, const void *actions_dev, double *obs_dev, doub
         const EnvArrays fea = env_arrays(h);
         const ColdArgs *cold = (const ColdArgs *)h->cold_args;
         cudaStream_t fs = as_stream(stream);
-#define PAINTRL_FUSED_K(C, ST, AX, DI) step_fused_kernel<C, ST, AX, DI><<<h->num_envs, 32, 0, fs>>>(h->pk, h->cfg, fea, h->num_envs, io, cold)
+#define PAINTRL_FUSED_K(C, ST, AX, DI) step_fused_kernel<C, ST, AX, DI><<<(h->num_envs + PAINTRL_FUSED_WPB - 1) / PAINTRL_FUSED_WPB, 32 * PAINTRL_FUSED_WPB, 0, fs>>>(h->pk, h->cfg, fea, h->num_envs, io, cold)
 #define PAINTRL_FUSED_AD(C, ST)                                                        \
     do {                                                                               \
         if (ax12f && disc) PAINTRL_FUSED_K(C, ST, true, true);                         \

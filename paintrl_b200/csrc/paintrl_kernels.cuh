@@ -1753,14 +1753,18 @@ paint_normal_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepI
 
 // The whole step of one environment in one warp (batches that cannot fill the GPU twice over: the two-kernel step
 // pays the move grid's drain before the paint grid's warps get their slots; here a warp goes straight on).
+#ifndef PAINTRL_FUSED_WPB
+#define PAINTRL_FUSED_WPB 1      // warps (= environments) per CTA of the one-kernel step
+#endif
 template <int COLOR, bool STAGED, bool AX12, bool DISCRETE>
-__global__ void __launch_bounds__(32, STAGED ? PAINTRL_PAINT_OCC : 16)
+__global__ void __launch_bounds__(32 * PAINTRL_FUSED_WPB, (STAGED ? PAINTRL_PAINT_OCC : 16) / PAINTRL_FUSED_WPB)
 step_fused_kernel(DevPack pk, DevConfig cfg, EnvArrays ea, int num_envs, StepIO io, const ColdArgs *cold) {
-    __shared__ WarpScratch<STAGED> scratch[1];
-    const int env = blockIdx.x;
+    __shared__ WarpScratch<STAGED> scratch[PAINTRL_FUSED_WPB];
+    const int warp = threadIdx.x >> 5;
+    const int env = blockIdx.x * PAINTRL_FUSED_WPB + warp;
     if (env >= num_envs) return;
-    l2_prefetch_tables(pk, blockIdx.x * 32 + threadIdx.x, gridDim.x * 32);
-    paint_body<COLOR, STAGED, AX12, true, DISCRETE>(pk, cfg, ea, env, io, scratch[0], cold);
+    l2_prefetch_tables(pk, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    paint_body<COLOR, STAGED, AX12, true, DISCRETE>(pk, cfg, ea, env, io, scratch[warp], cold);
 }
 
 // PaintGymEnv.reset / Robot.reset(pose) for the listed environments, with their first observation.

@@ -115,4 +115,52 @@ raster_position_kernel(const double *tri_a, const double *tri_b, const double *t
     for (int q = 0; q < 3; ++q) out[q] = (bu * __ldg(a + q) + bv * __ldg(b + q)) + bw * __ldg(c + q);
 }
 
+// ---- silhouette scans (Part._get_exact_boundary, bullet_paint_wrapper.py:906-920) ------------------------------------
+// A scan marches from `point` along the first principal axis (`proof`) in 1 mm steps, outwards (is_min: towards smaller
+// values), and at every step tests a ray along the non-principal axis `npa` against the collision hull; it reports the
+// coordinate of the first step whose ray misses.  The reference moves the ray's end points 1 further out at every step
+// (start -= 1, end += 1, cumulatively rounded) -- kept.  One warp per scan, 32 consecutive steps per round (lane = step),
+// every lane scanning all hull planes for its own ray with shim S1's slab arithmetic (products and sums rounded one by
+// one: the translation unit is compiled with -fmad=false), the first missing lane found by ballot.
+__global__ void __launch_bounds__(128)
+silhouette_march_kernel(const double4 *planes, int n_planes, const double *points, const signed char *is_min, int n_scans, int proof,
+                        int npa, int steps_range, double *boundary_out, signed char *found_out) {
+    const int scan = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (scan >= n_scans) return;
+    const double p[3] = {points[3 * scan], points[3 * scan + 1], points[3 * scan + 2]};
+    const double step = is_min[scan] ? -1e-3 : 1e-3;
+    double s_base = p[npa], e_base = p[npa];             // the ray's end points after the steps of the previous rounds
+    for (int i0 = 0; i0 < steps_range; i0 += 32) {
+        const int i = i0 + lane;
+        double s = s_base, e = e_base;
+        for (int k = 0; k <= lane; ++k) { s -= 1.0; e += 1.0; }
+        for (int k = 0; k < 32; ++k) { s_base -= 1.0; e_base += 1.0; }
+        const double bound = p[proof] + (double)i * step;
+        double frm[3] = {p[0], p[1], p[2]}, to[3] = {p[0], p[1], p[2]};
+        frm[proof] = bound; to[proof] = bound;
+        frm[npa] = s; to[npa] = e;
+        const double d0 = to[0] - frm[0], d1 = to[1] - frm[1], d2 = to[2] - frm[2];
+        double t_in = -INFINITY, t_out = INFINITY;
+        bool parallel_out = false;
+        for (int q = 0; q < n_planes; ++q) {
+            const double2 pa = __ldg(reinterpret_cast<const double2 *>(planes + q)), pb = __ldg(reinterpret_cast<const double2 *>(planes + q) + 1);
+            const double4 pl = make_double4(pa.x, pa.y, pb.x, pb.y);
+            const double den = (pl.x * d0 + pl.y * d1) + pl.z * d2;
+            const double num = pl.w - ((pl.x * frm[0] + pl.y * frm[1]) + pl.z * frm[2]);
+            if (den == 0.0) { parallel_out |= num < 0.0; continue; }
+            const double t = num / den;
+            if (den < 0.0) t_in = fmax(t_in, t); else t_out = fmin(t_out, t);
+        }
+        const bool hit = !parallel_out && t_in <= t_out && 0.0 <= t_in && t_in <= 1.0;
+        const unsigned miss = __ballot_sync(0xffffffffu, i < steps_range && !hit);
+        if (miss) {
+            const int src = __ffs(miss) - 1;
+            const double b = __shfl_sync(0xffffffffu, bound, src);
+            if (lane == 0) { boundary_out[scan] = b; found_out[scan] = 1; }
+            return;
+        }
+    }
+    if (lane == 0) { boundary_out[scan] = 0.0; found_out[scan] = 0; }
+}
+
 }  // namespace paintrl

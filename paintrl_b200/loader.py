@@ -270,53 +270,86 @@ def point_along(point, length, normal):
 
 
 # ------------------------------------------------------------------------------------------ silhouette table
+def march_host(planes_n, planes_off, points, is_min, proof, npa, steps_range, chunk=64):
+    """`Part._get_exact_boundary` (bullet_paint_wrapper.py:906-920) for a batch of scans, NumPy: (boundary [n], found [n]).
+    Same arithmetic as `paintrl_silhouette_march` (csrc/paintrl_raster.cuh), which the loader uses on the GPU."""
+    n = len(points)
+    boundary, found = np.zeros(n), np.zeros(n, dtype=bool)
+    for k in range(n):
+        base = np.array(points[k], dtype=np.float64)
+        step = -1e-3 if is_min[k] else 1e-3
+        s_np, e_np = float(base[npa]), float(base[npa])
+        i = 0
+        while i < steps_range and not found[k]:
+            m = min(chunk, steps_range - i)
+            frm = np.tile(base, (m, 1))
+            to = np.tile(base, (m, 1))
+            bounds = np.empty(m)
+            for r in range(m):
+                bounds[r] = base[proof] + (i + r) * step
+                s_np -= 1
+                e_np += 1
+                frm[r, npa], to[r, npa] = s_np, e_np
+            frm[:, proof] = bounds
+            to[:, proof] = bounds
+            miss = ~rays_hit(planes_n, planes_off, frm, to)
+            if miss.any():
+                boundary[k], found[k] = bounds[int(np.argmax(miss))], True
+            i += m
+    return boundary, found
+
+
+def march_gpu(planes_n, planes_off, points, is_min, proof, npa, steps_range, device=0):
+    """The same scans by `paintrl_silhouette_march`: one warp per scan on the GPU."""
+    import ctypes
+    from . import _capi
+    lib = _capi.lib()
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    mins = np.ascontiguousarray(is_min, dtype=np.int8)
+    pn, po = np.ascontiguousarray(planes_n, dtype=np.float64), np.ascontiguousarray(planes_off, dtype=np.float64)
+    boundary, found = np.zeros(len(pts)), np.zeros(len(pts), dtype=np.int8)
+    _capi.check(lib.paintrl_silhouette_march(pn.ctypes.data, po.ctypes.data, len(po), pts.ctypes.data, mins.ctypes.data, len(pts),
+                                             int(proof), int(npa), int(steps_range), int(device), boundary.ctypes.data, found.ctypes.data))
+    return boundary, found.astype(bool)
+
+
 class Silhouette(object):
     """`Part._set_grid_dict` + `_get_exact_boundary` (bullet_paint_wrapper.py:906-963) for one side: per row of the
     100-row grid along the second principal axis, the extent of the collision hull along the first one, found by
     marching a ray in 1 mm steps outwards from the row's extreme vertices until it misses.
 
     The reference mutates rows of `cKDTree.data` in the sparse-row branch (:944-947; shim S3 makes that a writable
-    copy), which later comparisons of the sorted walk and `ConvHull.separate_by_side` then see: `data` is that copy."""
+    copy), which later comparisons of the sorted walk and `ConvHull.separate_by_side` then see: `data` is that copy.
 
-    CHUNK = 64
+    The walk itself is host work (it is a sequential scan of a sorted list); its scans are queued and marched in
+    batches by `march` (the GPU kernel, or `march_host`) -- a batch ends where the sparse-row branch needs the
+    previous row's result."""
 
-    def __init__(self, masked_vertices, axes, non_principal, ranges, planes_n, planes_off):
+    def __init__(self, masked_vertices, axes, non_principal, ranges, planes_n, planes_off, march=None):
         self.data = np.array(masked_vertices, dtype=np.float64, copy=True)
         self.ax1, self.ax2 = axes
         self.npa = non_principal
         self.ranges = ranges
         self.n, self.off = planes_n, planes_off
-        self.lo = [0] * GRID_GRANULARITY
-        self.hi = [0] * GRID_GRANULARITY
+        self.march = march or march_host
         self.scans = 0
+        self.batches = 0
         self.sparse_rows = 0
         self._run()
 
-    def _boundary(self, point, is_min):
-        proof = self.ax1
-        step = -1e-3 if is_min else 1e-3
-        steps_range = int((self.ranges[0][1] - self.ranges[0][0]) / abs(step))
-        self.scans += 1
-        base = np.array(point, dtype=np.float64)
-        s_np, e_np = float(base[self.npa]), float(base[self.npa])
-        i = 0
-        while i < steps_range:
-            k = min(self.CHUNK, steps_range - i)
-            frm = np.tile(base, (k, 1))
-            to = np.tile(base, (k, 1))
-            bounds = np.empty(k)
-            for r in range(k):
-                bounds[r] = base[proof] + (i + r) * step
-                s_np -= 1
-                e_np += 1
-                frm[r, self.npa], to[r, self.npa] = s_np, e_np
-            frm[:, proof] = bounds
-            to[:, proof] = bounds
-            miss = ~rays_hit(self.n, self.off, frm, to)
-            if miss.any():
-                return np.float64(bounds[int(np.argmax(miss))])
-            i += k
-        return None
+    def _flush(self, known, queue):
+        if not queue:
+            return
+        steps_range = int((self.ranges[0][1] - self.ranges[0][0]) / abs(1e-3))
+        boundary, found = self.march(self.n, self.off, np.array([q[2] for q in queue]), [q[1] for q in queue], self.ax1, self.npa,
+                                     steps_range)
+        self.batches += 1
+        for (row, is_min, _), b, ok in zip(queue, boundary, found):
+            if not ok:
+                raise ValueError('silhouette scan of grid row %d never left the part (bullet_paint_wrapper.py:906-920)' % row)
+            lo, hi = known[row]
+            known[row] = (np.float64(b), hi) if is_min else (lo, np.float64(b))
+        del queue[:]
 
     def _run(self):
         data, ax1, ax2 = self.data, self.ax1, self.ax2
@@ -326,7 +359,7 @@ class Silhouette(object):
         step_size = (r11 - r10) / GRID_GRANULARITY
         left = right = int(order[0])
         traverse = 0
-        known = {}
+        known, queue = {}, []
         for i in range(GRID_GRANULARITY):
             cur = traverse
             step_max = r10 + (i + 1) * step_size
@@ -338,7 +371,11 @@ class Silhouette(object):
             if index - cur <= 1:
                 self.sparse_rows += 1
                 new2 = step_max + 0.5 * step_size
-                new1 = data[order[index], ax1] if (i - 1) not in known else (known[i - 1][0] + known[i - 1][1]) / 2
+                if (i - 1) not in known:
+                    new1 = data[order[index], ax1]
+                else:
+                    self._flush(known, queue)           # the previous row's extent is an input here
+                    new1 = (known[i - 1][0] + known[i - 1][1]) / 2
                 for row in (left, right):
                     data[row, ax2] = new2
                 for row in (left, right):
@@ -347,14 +384,14 @@ class Silhouette(object):
                 target = order[cur:index]
                 by1 = target[np.argsort(data[target, ax1], kind='stable')]
                 left, right = int(by1[0]), int(by1[-1])
-            known[i] = (self._boundary(data[left], True), self._boundary(data[right], False))
-            if known[i][0] is None or known[i][1] is None:
-                raise ValueError('silhouette scan of grid row %d never left the part (bullet_paint_wrapper.py:906-920)' % i)
+            known[i] = (None, None)
+            queue.append((i, True, data[left].copy()))
+            queue.append((i, False, data[right].copy()))
+            self.scans += 2
             traverse = index + 1
-        for i in range(GRID_GRANULARITY):
-            self.lo[i], self.hi[i] = known[i]
-        self.lo = np.array(self.lo, dtype=np.float64)
-        self.hi = np.array(self.hi, dtype=np.float64)
+        self._flush(known, queue)
+        self.lo = np.array([known[i][0] for i in range(GRID_GRANULARITY)], dtype=np.float64)
+        self.hi = np.array([known[i][1] for i in range(GRID_GRANULARITY)], dtype=np.float64)
 
 
 def grid_index(value, ranges):
@@ -600,7 +637,8 @@ def load_part(urdf_path, max_points=None, part_no=None, base_position=BASE_POSIT
 
     `max_points`: `Part_Dict`'s second column (robot_gym_env.py:106-117); looked up from the URDF's file name when
     omitted.  `texture_size=(W, H)` replaces the texture by a blank one of that size (BASELINE config C4).
-    `rasterizer(tri_a, tri_b, tri_c, tri_uv, width, height) -> (ij, pos)` replaces the GPU rasteriser (tests)."""
+    `rasterizer(tri_a, tri_b, tri_c, tri_uv, width, height) -> (ij, pos)` replaces the GPU rasteriser and switches the
+    silhouette scans to their NumPy form as well (machines without a GPU: the CPU tests)."""
     urdf_path = os.path.abspath(urdf_path)
     name = os.path.splitext(os.path.basename(urdf_path))[0]
     if max_points is None or part_no is None:
@@ -637,9 +675,8 @@ def load_part(urdf_path, max_points=None, part_no=None, base_position=BASE_POSIT
         raise ValueError('%s has no triangle facing the front normal %s' % (name, front_normal))
 
     # texels (Part.preprocess :622-648, BarycentricInterpolator.get_uv_pixels :191-212)
+    gpu_stages = rasterizer is None       # the product path: rasteriser and silhouette scans on the GPU
     if rasterizer is None:
-        def rasterizer(a, b, c, tuv, w, h):
-            raise RuntimeError('unreachable')
         texels = {s: rasterize_side(tri, uv, np.flatnonzero(tri.side == s), width, height, device) for s in sides}
     else:
         texels = {}
@@ -682,7 +719,8 @@ def load_part(urdf_path, max_points=None, part_no=None, base_position=BASE_POSIT
         raise ValueError('%s has no collision mesh' % urdf_path)
     planes_n, planes_off = hull_half_spaces(to_world(read_obj(collision)[0], base))
     length_width_ratio = (ranges[0][1] - ranges[0][0]) / (ranges[1][1] - ranges[1][0])
-    silhouette = Silhouette(masked[side], axes, non_principal, ranges, planes_n, planes_off)
+    march = (lambda *a: march_gpu(*a, device=device)) if gpu_stages else march_host
+    silhouette = Silhouette(masked[side], axes, non_principal, ranges, planes_n, planes_off, march=march)
     lo, hi = silhouette.lo, silhouette.hi
 
     # normal correction (:650-698)
@@ -711,7 +749,8 @@ def load_part(urdf_path, max_points=None, part_no=None, base_position=BASE_POSIT
         'axes': [int(a) for a in axes], 'non_principal_axis': int(non_principal), 'front_normal': front_normal,
         'base_position': base, 'max_points': max_points, 'density': float(density), 'grid_granularity': GRID_GRANULARITY,
         'source': 'paintrl_b200.loader.load_part',
-        'loader_stats': {'silhouette_scans': silhouette.scans, 'sparse_grid_rows': silhouette.sparse_rows,
+        'loader_stats': {'silhouette_scans': silhouette.scans, 'silhouette_batches': silhouette.batches, 'sparse_grid_rows': silhouette.sparse_rows,
+                         'gpu_stages': bool(gpu_stages),
                          'hull_corrected_normals': int(hull_corrected), 'smoothed_normals': int(smoothed[side]),
                          'triangles': int(len(fv)), 'front_triangles': int((tri.side == side).sum())},
     }

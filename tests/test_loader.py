@@ -133,6 +133,26 @@ def test_unpacked_reference_parts_match_the_reference_digests(part_no):
 def test_gpu_rasteriser_path_matches_the_reference_pack(cuda_device):
     made = loader.load_part(BULGE_URDF, max_points=5200, part_no=100)
     assert_same_tables(made, PartPack.load(BULGE_GOLDEN))
+    stats = made.meta['loader_stats']
+    assert stats['gpu_stages'] and stats['silhouette_scans'] == 200 and stats['silhouette_batches'] > 1
+
+
+@pytest.mark.gpu
+def test_gpu_silhouette_march_matches_the_host_march(cuda_device):
+    """`paintrl_silhouette_march` against `march_host` on the synthetic part's hull: scans from random points inside and
+    outside the part, both directions, including scans that never leave (found = 0) because the range is cut short."""
+    v = loader.read_obj(loader.collision_mesh_file(BULGE_URDF))[0]
+    n, off = loader.hull_half_spaces(loader.to_world(v, list(loader.BASE_POSITION)))
+    rng = np.random.default_rng(5)
+    lo, hi = np.array([-0.45, -0.7, 0.2]), np.array([-0.25, 0.3, 1.3])
+    pts = rng.uniform(lo, hi, size=(300, 3))
+    is_min = rng.integers(0, 2, size=300).astype(bool)
+    for steps_range in (800, 37):
+        want_b, want_f = loader.march_host(n, off, pts, is_min, 1, 0, steps_range)
+        got_b, got_f = loader.march_gpu(n, off, pts, is_min, 1, 0, steps_range)
+        assert np.array_equal(want_f, got_f)
+        assert np.array_equal(want_b[want_f], got_b[got_f])
+        assert want_f.any() and (steps_range == 800 or not want_f.all())
 
 
 @pytest.mark.gpu
