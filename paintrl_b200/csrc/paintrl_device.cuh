@@ -569,6 +569,15 @@ __device__ __forceinline__ bool in_cell_region(const DevPack &pk, const Vec3 &h,
     return hx == cx && hy == cy && resid >= clv.y && resid <= hpv.x;
 }
 
+// The same test against the cell's index cy * mc_nx + cx.
+__device__ __forceinline__ bool in_cell_region_idx(const DevPack &pk, double h0, double h1, double depth, int cell, const double2 &abv,
+                                                   const double2 &clv, const double2 &hpv) {
+    const int hx = (int)floor((h0 - pk.mc_o0) * pk.mc_inv);
+    const int hy = (int)floor((h1 - pk.mc_o1) * pk.mc_inv);
+    const double resid = depth - (abv.x + abv.y * h0 + clv.x * h1);
+    return hx >= 0 && hx < pk.mc_nx && hy * pk.mc_nx + hx == cell && resid >= clv.y && resid <= hpv.x;
+}
+
 template <int G>
 __device__ __forceinline__ bool ray_test(const DevPack &pk, const Ax &ax, const Vec3 &frm, const Vec3 &to, const Grp &grp, Vec3 &hit,
                                          CellRef &ref, double2 &vc0, double2 &vc1, int &counts, unsigned &miss_cache, double pf0,

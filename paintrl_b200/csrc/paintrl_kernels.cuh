@@ -1244,26 +1244,27 @@ __device__ __forceinline__ int ray_fast(const DevPack &pk, const Ax &ax, const V
     int why = 4;
     const double2 *sub = nullptr;      // the plane list of the last cell tried
     int n_sub = 0;
-    int tried_cx = -1, tried_cy = -1;
+    int tried = -1;                    // index of the cell just tried (one register instead of two coordinates)
     unsigned long long link = 0ull;    // fallback blob of the cell just tried (offset | counts << 32), 0: none
 #pragma unroll 1
     for (int attempt = 0; attempt < kRayAttempts; ++attempt) {
         path_counts += 1 << 24;
         const double g0 = comp(h, ax.a0), g1 = comp(h, ax.a1);
-        int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
-        int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
-        if (link == 0ull && (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny)) { why = 1; break; }
+        int cell = tried;
         uint2 entry;
         if (link != 0ull) {
             // the cell just tried is a silhouette cell whose thin primary slab did not hold the entry point: its second
             // blob (deep slab, build_move_cells) comes next, whichever cell the provisional entry point fell into
-            cx = tried_cx; cy = tried_cy;
             entry = make_uint2((unsigned)link, (unsigned)(link >> 32));
         } else {
-            if (cx == tried_cx && cy == tried_cy) break;     // the same cell again: same list, same result
-            entry = __ldg(&pk.mc_entry[cy * pk.mc_nx + cx]);
+            const int cx = (int)floor((g0 - pk.mc_o0) * pk.mc_inv);
+            const int cy = (int)floor((g1 - pk.mc_o1) * pk.mc_inv);
+            if (cx < 0 || cy < 0 || cx >= pk.mc_nx || cy >= pk.mc_ny) { why = 1; break; }
+            cell = cy * pk.mc_nx + cx;
+            if (cell == tried) break;                        // the same cell again: same list, same result
+            entry = __ldg(&pk.mc_entry[cell]);
         }
-        tried_cx = cx; tried_cy = cy;
+        tried = cell;
         const int n_planes = (int)(entry.y & 0xffffu), n_verts = (int)(entry.y >> 16);
         if (n_planes <= 0) { why = 2; break; }
 #ifdef PAINTRL_TRACE
@@ -1280,7 +1281,7 @@ __device__ __forceinline__ int ray_fast(const DevPack &pk, const Ax &ax, const V
         if (do_prefetch && attempt == 0) {
             const int px = (int)floor((g0 + pf0 - pk.mc_o0) * pk.mc_inv);
             const int py = (int)floor((g1 + pf1 - pk.mc_o1) * pk.mc_inv);
-            if (px >= 0 && py >= 0 && px < pk.mc_nx && py < pk.mc_ny && (px != cx || py != cy)) {
+            if (px >= 0 && py >= 0 && px < pk.mc_nx && py < pk.mc_ny && py * pk.mc_nx + px != cell) {
                 const uint2 pe = __ldg(&pk.mc_entry[py * pk.mc_nx + px]);
                 const int sectors = 2 + (int)(pe.y & 0xffffu) + (int)(pe.y >> 16);
                 const char *pb = reinterpret_cast<const char *>(pk.mc_blob + (size_t)pe.x * 2);
@@ -1294,7 +1295,7 @@ __device__ __forceinline__ int ray_fast(const DevPack &pk, const Ax &ax, const V
         if (!(r.t_in > -INFINITY)) { if (link != 0ull) continue; why = 3; break; }
         candidate = true;
         h.x = frm.x + d0 * r.t_in; h.y = frm.y + d1 * r.t_in; h.z = frm.z + d2 * r.t_in;
-        if (in_cell_region(pk, h, comp(h, ax.a0), comp(h, ax.a1), comp(h, npax), cx, cy, abv, clv, hpv)) {   // (2a)
+        if (in_cell_region_idx(pk, comp(h, ax.a0), comp(h, ax.a1), comp(h, npax), cell, abv, clv, hpv)) {   // (2a)
             if (!(0.0 <= r.t_in)) return 0;        // with (1) passed this is the serial scan's hit test
             if (n_verts <= 0) { PAINTRL_FAST_REASON(5); return 2; }
             ref.blob = blob; ref.n_planes = n_planes; ref.n_verts = n_verts;
