@@ -650,6 +650,48 @@ int build_tables(PaintrlEngine *e, const PaintrlPartPack *pack, const PaintrlCon
             rep[j] = t >= 0 ? pack_to_slot[r] : j;
         }
         CUDA_TRY(e->arena.upload(rep, &pk.nn_rep_slot));
+        // Nearest-texel grid of the normal paint method (Part.paint's cKDTree.query, bullet_paint_wrapper.py:565): square
+        // cells of two texel pitches over the principal plane, the texels of a cell stored together as (x, y, z, slot) --
+        // a query scans a 3 x 3 block of about 36 texels instead of whole stretches of the 37 mm rows of the step's layout.
+        pk.nn_nx = pk.nn_ny = 0;
+        if (cfg->paint_method == 1 && n > 0) {
+            double lo0 = INFINITY, hi0 = -INFINITY, lo1 = INFINITY, hi1 = -INFINITY;
+            for (int t = 0; t < n; ++t) {
+                const double *p = pack->texel_pos + 3 * t;
+                lo0 = std::min(lo0, p[a0]); hi0 = std::max(hi0, p[a0]);
+                lo1 = std::min(lo1, p[a1]); hi1 = std::max(hi1, p[a1]);
+            }
+            const double area = std::max((hi0 - lo0) * (hi1 - lo1), 1e-12);
+            const double g = std::max(2.0 * std::sqrt(area / n), 1e-6);
+            const int nx = std::max(1, std::min(4096, (int)std::floor((hi0 - lo0) / g) + 1));
+            const int ny = std::max(1, std::min(4096, (int)std::floor((hi1 - lo1) / g) + 1));
+            const double inv = 1.0 / g;
+            auto cell_of = [&](const double *p) {
+                const int cx = std::min(std::max((int)std::floor((p[a0] - lo0) * inv), 0), nx - 1);
+                const int cy = std::min(std::max((int)std::floor((p[a1] - lo1) * inv), 0), ny - 1);
+                return cy * nx + cx;
+            };
+            std::vector<int> start((size_t)nx * ny + 1, 0);
+            for (int t = 0; t < n; ++t) start[cell_of(pack->texel_pos + 3 * t) + 1]++;
+            for (size_t c = 0; c < (size_t)nx * ny; ++c) start[c + 1] += start[c];
+            std::vector<int> fill(start.begin(), start.end() - 1);
+            std::vector<double> pos4((size_t)n * 4, 0.0);
+            for (int j = 0; j < pk.n_slots; ++j) {          // in slot order: ties inside a cell go to the lower slot, as before
+                const int t = slot_to_pack[j];
+                if (t < 0) continue;
+                const double *p = pack->texel_pos + 3 * t;
+                const size_t at = (size_t)fill[cell_of(p)]++;
+                pos4[4 * at] = p[0]; pos4[4 * at + 1] = p[1]; pos4[4 * at + 2] = p[2];
+                const long long slot = j;
+                std::memcpy(&pos4[4 * at + 3], &slot, 8);
+            }
+            pk.nn_nx = nx; pk.nn_ny = ny;
+            pk.nn_o0 = lo0; pk.nn_o1 = lo1; pk.nn_inv = inv; pk.nn_cell = g;
+            CUDA_TRY(e->arena.upload(start, &pk.nn_start));
+            const double *dev = nullptr;
+            CUDA_TRY(e->arena.upload(pos4, &dev));
+            pk.nn_pos = reinterpret_cast<const double2 *>(dev);
+        }
     }
 
     // ---- grid-observation cells (bullet_paint_wrapper.py:1072-1112)

@@ -192,6 +192,11 @@ struct DevPack {
     const int *slot_to_pack;      // [n_slots] part-pack texel index, -1 for pad slots
     const int *pack_to_slot;      // [n_texels]
     const int *nn_rep_slot;       // [n_slots] normal paint: the slot cKDTree.query reports among texels at this slot's exact position
+    // normal paint: nearest-texel grid over the principal plane (square cells of two texel pitches)
+    int nn_nx, nn_ny;
+    double nn_o0, nn_o1, nn_inv, nn_cell;
+    const int *nn_start;          // [nn_nx * nn_ny + 1]
+    const double2 *nn_pos;        // per texel, grouped by cell: (x, y) (z, slot as int64 bits)
     // grid observation (bullet_paint_wrapper.py:1072-1112)
     int n_gcells, n_gcells_pad;
     const int *gtotal;            // [obs_grad^2]

@@ -833,61 +833,55 @@ __device__ __forceinline__ int beam_ray(const DevPack &pk, int a0, int a1, Vec3 
     return 2;
 }
 
-// cKDTree.query(point, k = 1) over the front texel positions, by one lane: returns the slot
+// cKDTree.query(point, k = 1) over the front texel positions, by one lane: returns the slot.
+// Block search over the nearest-texel grid that grows to what the best distance so far demands: every texel outside
+// the block lies beyond the block's border in the principal plane, so the block's winner is the global one as soon as
+// its (3-D) distance is below the border distance.  Hits lie on the hull, texels on the mesh: over the part's concave
+// regions the nearest texel is centimetres away, and the block grows once to the radius the first winner sets.
 __device__ __forceinline__ int nearest_texel(const DevPack &pk, int a0, int a1, Vec3 p) {
-    const double *kx = pk.tx, *ky = pk.ty, *kz = pk.tz;
     const double q0 = comp(p, a0), q1 = comp(p, a1);
-    const int r0 = min(max((int)floor((q1 - pk.row_o1) * pk.row_inv), 0), pk.n_rows - 1);
-    const int c0 = min(max((int)floor((q0 - pk.cx_o0) * pk.cx_inv), 0), pk.ncx - 1);
-    const double cw = 1.0 / pk.cx_inv;
-    double best = INFINITY;
-    int arg = -1;
-    // Block search that grows to what the best distance so far demands: every texel outside the block lies beyond the
-    // block's border in the principal plane, so the block's winner is the global one as soon as its (3-D) distance is
-    // below the border distance.  Hits lie on the hull, texels on the mesh: over the part's concave regions the nearest
-    // texel is centimetres away and a fixed schedule of block sizes fell through to a scan of every texel.
-    int R = 1, D = 1;
+    const int c0 = min(max((int)floor((q0 - pk.nn_o0) * pk.nn_inv), 0), pk.nn_nx - 1);
+    const int c1 = min(max((int)floor((q1 - pk.nn_o1) * pk.nn_inv), 0), pk.nn_ny - 1);
+    int R = 1;
 #pragma unroll 1
-    for (int round = 0; round < 6; ++round) {
-        const int ra = max(r0 - D, 0), rb = min(r0 + D, pk.n_rows - 1);
-        const int ca = max(c0 - R, 0), cb = min(c0 + R, pk.ncx - 1);
-        best = INFINITY; arg = -1;
-        for (int r = ra; r <= rb; ++r) {
-            const int *cs = pk.cell_start + (size_t)r * (pk.ncx + 1);
-            const int i0 = __ldg(cs + ca), i1 = __ldg(cs + cb + 1);
-            const int base = __ldg(&pk.row_word0[r]) * 32;
+    for (int round = 0; round < 12; ++round) {
+        const int xa = max(c0 - R, 0), xb = min(c0 + R, pk.nn_nx - 1);
+        const int ya = max(c1 - R, 0), yb = min(c1 + R, pk.nn_ny - 1);
+        double best = INFINITY;
+        long long arg = -1;
+        for (int y = ya; y <= yb; ++y) {
+            const int i0 = __ldg(&pk.nn_start[y * pk.nn_nx + xa]), i1 = __ldg(&pk.nn_start[y * pk.nn_nx + xb + 1]);
             for (int i = i0; i < i1; ++i) {
-                const int j = base + i;
-                const double dx = __ldg(&kx[j]) - p.x, dy = __ldg(&ky[j]) - p.y, dz = __ldg(&kz[j]) - p.z;
+                const double2 xy = __ldg(pk.nn_pos + 2 * i), zs = __ldg(pk.nn_pos + 2 * i + 1);
+                const double dx = xy.x - p.x, dy = xy.y - p.y, dz = zs.x - p.z;
                 const double d = dx * dx + dy * dy + dz * dz;
-                if (d < best) { best = d; arg = j; }
+                const long long slot = __double_as_longlong(zs.y);
+                if (d < best || (d == best && slot < arg)) { best = d; arg = slot; }
             }
         }
-        double m0 = INFINITY, m1 = INFINITY;
-        if (ca > 0) m0 = fmin(m0, q0 - (pk.cx_o0 + ca * cw));
-        if (cb < pk.ncx - 1) m0 = fmin(m0, (pk.cx_o0 + (cb + 1) * cw) - q0);
-        if (ra > 0) m1 = fmin(m1, q1 - (pk.row_o1 + ra * pk.row_h));
-        if (rb < pk.n_rows - 1) m1 = fmin(m1, (pk.row_o1 + (rb + 1) * pk.row_h) - q1);
-        const double m = fmin(m0, m1) - 1e-9;
-        if (arg >= 0 && (m == INFINITY || (m > 0.0 && best < m * m))) return __ldg(&pk.nn_rep_slot[arg]);
-        if (m == INFINITY) break;                      // the block is the whole table and holds no texel
-        if (arg < 0) { R = 2 * R + 1; D += 1; continue; }
-        // the block that certainly holds the winner: border distance above sqrt(best) on every side
-        const double rho = sqrt(best) + 2e-9;
-        if (!(m0 - 1e-9 > rho)) R = max(R + 1, (int)(rho * pk.cx_inv) + 2);
-        if (!(m1 - 1e-9 > rho)) D = max(D + 1, (int)(rho * pk.row_inv) + 2);
+        double m = INFINITY;
+        if (xa > 0) m = fmin(m, q0 - (pk.nn_o0 + xa * pk.nn_cell));
+        if (xb < pk.nn_nx - 1) m = fmin(m, (pk.nn_o0 + (xb + 1) * pk.nn_cell) - q0);
+        if (ya > 0) m = fmin(m, q1 - (pk.nn_o1 + ya * pk.nn_cell));
+        if (yb < pk.nn_ny - 1) m = fmin(m, (pk.nn_o1 + (yb + 1) * pk.nn_cell) - q1);
+        if (arg >= 0 && m == INFINITY) return __ldg(&pk.nn_rep_slot[(int)arg]);      // the block is the whole grid
+        m -= 1e-9;
+        if (arg >= 0 && m > 0.0 && best < m * m) return __ldg(&pk.nn_rep_slot[(int)arg]);
+        if (m == INFINITY) return -1;                                                 // no texel at all
+        R = arg < 0 ? 2 * R + 1 : max(R + 1, (int)((sqrt(best) + 2e-9) * pk.nn_inv) + 2);
     }
-    best = INFINITY; arg = -1;
-    for (int r = 0; r < pk.n_rows; ++r) {
-        const int base = __ldg(&pk.row_word0[r]) * 32, cnt = __ldg(&pk.row_count[r]);
-        for (int i = 0; i < cnt; ++i) {
-            const int j = base + i;
-            const double dx = __ldg(&kx[j]) - p.x, dy = __ldg(&ky[j]) - p.y, dz = __ldg(&kz[j]) - p.z;
-            const double d = dx * dx + dy * dy + dz * dz;
-            if (d < best) { best = d; arg = j; }
-        }
+    // (not reached with a sane grid: 12 rounds of a radius that at least doubles cover 4096 cells) scan everything
+    double best = INFINITY;
+    long long arg = -1;
+    const int total = __ldg(&pk.nn_start[pk.nn_nx * pk.nn_ny]);
+    for (int i = 0; i < total; ++i) {
+        const double2 xy = __ldg(pk.nn_pos + 2 * i), zs = __ldg(pk.nn_pos + 2 * i + 1);
+        const double dx = xy.x - p.x, dy = xy.y - p.y, dz = zs.x - p.z;
+        const double d = dx * dx + dy * dy + dz * dz;
+        const long long slot = __double_as_longlong(zs.y);
+        if (d < best || (d == best && slot < arg)) { best = d; arg = slot; }
     }
-    return arg >= 0 ? __ldg(&pk.nn_rep_slot[arg]) : -1;
+    return arg >= 0 ? __ldg(&pk.nn_rep_slot[(int)arg]) : -1;
 }
 
 // Returns (warp-uniform) like stamp(): newly painted texels (RGB) / thickness units removed (HSI), |union of valid
