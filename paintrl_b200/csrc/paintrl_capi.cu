@@ -1060,7 +1060,10 @@ int paintrl_policy_create(const PaintrlPolicyConfig *cfg, int32_t device, Paintr
               e->arena.upload(w3, &pp.w3) == cudaSuccess && e->arena.upload(b3, &pp.b3) == cudaSuccess &&
               e->arena.alloc((void **)&pp.counters, sizeof(unsigned) * (size_t)cfg->capacity) == cudaSuccess;
     if (ok) ok = cudaMemset(pp.counters, 0, sizeof(unsigned) * (size_t)cfg->capacity) == cudaSuccess;
-    if (ok) ok = cudaFuncSetAttribute(policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmemBytes) == cudaSuccess;
+    if (ok) ok = cudaFuncSetAttribute(policy_act_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmemBytes) == cudaSuccess &&
+                 cudaFuncSetAttribute(policy_act_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmemBytes) == cudaSuccess &&
+                 cudaFuncSetAttribute(policy_act_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmemBytes) == cudaSuccess &&
+                 cudaFuncSetAttribute(policy_act_kernel<32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPolSmemBytes) == cudaSuccess;
     if (!ok) { delete e; cudaGetLastError(); return fail(PAINTRL_E_CUDA, "setting up the policy engine failed (allocation / shared memory opt-in)"); }
     *out = e;
     return PAINTRL_OK;
@@ -1084,7 +1087,12 @@ int paintrl_policy_act(PaintrlPolicyHandle h, const double *obs_dev, int32_t bat
     io.act_discrete = h->pp.discrete ? reinterpret_cast<long long *>(actions_dev) : nullptr;
     io.act_continuous = h->pp.discrete ? nullptr : reinterpret_cast<double *>(actions_dev);
     io.logp = logp_dev; io.value = value_dev; io.logits = logits_dev; io.sample = sample ? 1 : 0;
-    policy_act_kernel<<<(batch + kPolRows - 1) / kPolRows, kPolThreads, kPolSmemBytes, as_stream(stream)>>>(h->pp, io);
+    const dim3 pgrid((batch + kPolRows - 1) / kPolRows);
+    const bool small_obs = h->pp.obs_dim <= 8, small_out = h->pp.n_out + 1 <= 8;
+    if (small_obs && small_out) policy_act_kernel<8, 8><<<pgrid, kPolThreads, kPolSmemBytes, as_stream(stream)>>>(h->pp, io);
+    else if (small_obs) policy_act_kernel<8, 16><<<pgrid, kPolThreads, kPolSmemBytes, as_stream(stream)>>>(h->pp, io);
+    else if (small_out) policy_act_kernel<32, 8><<<pgrid, kPolThreads, kPolSmemBytes, as_stream(stream)>>>(h->pp, io);
+    else policy_act_kernel<32, 16><<<pgrid, kPolThreads, kPolSmemBytes, as_stream(stream)>>>(h->pp, io);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(PAINTRL_E_CUDA, std::string("policy_act_kernel: ") + cudaGetErrorString(err));
     h->launches++;

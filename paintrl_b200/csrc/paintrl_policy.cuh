@@ -79,6 +79,10 @@ __device__ __forceinline__ float pol_tanh(float x) {
 }
 
 // dynamic shared memory: A (64 KB) | B (64 KB) | w1 | b1 | b2 | w3 | b3 | barriers
+// MO / MX: compile-time caps of the observation and output loops (register arrays, fully unrolled): 8 / 8 for the
+// reference's spaces (6-18 observations are 8 or 32; 4 logits + value), 32 / 16 in general.  The shared-memory layout
+// does not depend on them.
+template <int MO, int MX>
 __global__ void __launch_bounds__(kPolThreads, 1) policy_act_kernel(PolicyParams pp, PolicyIO io) {
     extern __shared__ __align__(1024) unsigned char pol_smem[];
     __nv_bfloat16 *sA = reinterpret_cast<__nv_bfloat16 *>(pol_smem);
@@ -120,9 +124,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_act_kernel(PolicyParams
     for (int i = tid; i < kPolH2; i += kPolThreads) sb2[i] = __ldg(&pp.b2[i]);
     for (int i = tid; i < kPolH2 * nout1; i += kPolThreads) sw3[i] = __ldg(&pp.w3[i]);
     if (tid < nout1) sb3[tid] = __ldg(&pp.b3[tid]);
-    float x[kPolMaxObs];
+    float x[MO];
 #pragma unroll
-    for (int i = 0; i < kPolMaxObs; ++i) x[i] = (i < pp.obs_dim && env < io.batch) ? (float)io.obs[(size_t)env * pp.obs_dim + i] : 0.f;
+    for (int i = 0; i < MO; ++i) x[i] = (i < pp.obs_dim && env < io.batch) ? (float)io.obs[(size_t)env * pp.obs_dim + i] : 0.f;
     __syncthreads();
 
     // ---- layer 1: h1 = tanh(x W1 + b1) -> BF16, canonical layout; this thread's quarter of the row's features
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_act_kernel(PolicyParams
 #pragma unroll
             for (int c = 0; c < 8; ++c) h[c] = sb1[kj * 8 + c];
 #pragma unroll
-            for (int i = 0; i < kPolMaxObs; ++i) {
+            for (int i = 0; i < MO; ++i) {
                 if (i < pp.obs_dim) {
                     const float xi = x[i];
                     const float *wr = sw1 + i * kPolH1 + kj * 8;
@@ -186,9 +190,9 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_act_kernel(PolicyParams
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: this thread's quarter of its row of D (TMEM lane = row), + b2, tanh, head
-    float out[kPolMaxOut];
+    float out[MX];
 #pragma unroll
-    for (int o = 0; o < kPolMaxOut; ++o) out[o] = (o < nout1 && part == 0) ? sb3[o] : 0.f;
+    for (int o = 0; o < MX; ++o) out[o] = (o < nout1 && part == 0) ? sb3[o] : 0.f;
     const unsigned lane_base = tmem + ((unsigned)((warp & 3) * 32) << 16);
 #pragma unroll 1
     for (int c0 = part * (kPolH2 / kPolSplit); c0 < (part + 1) * (kPolH2 / kPolSplit); c0 += 16) {
@@ -204,14 +208,14 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_act_kernel(PolicyParams
             const float h2 = pol_tanh(__uint_as_float(r[c]) + sb2[c0 + c]);
             const float *wr = sw3 + (c0 + c) * nout1;
 #pragma unroll
-            for (int o = 0; o < kPolMaxOut; ++o)
+            for (int o = 0; o < MX; ++o)
                 if (o < nout1) out[o] = fmaf(h2, wr[o], out[o]);
         }
     }
     // partial heads of the row's other three threads -> the row's first thread
     if (part > 0) {
 #pragma unroll
-        for (int o = 0; o < kPolMaxOut; ++o) spart[((part - 1) * kPolRows + row) * kPolMaxOut + o] = out[o];
+        for (int o = 0; o < MX; ++o) spart[((part - 1) * kPolRows + row) * kPolMaxOut + o] = out[o];
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -220,16 +224,16 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_act_kernel(PolicyParams
 #pragma unroll
     for (int q = 0; q < kPolSplit - 1; ++q)
 #pragma unroll
-        for (int o = 0; o < kPolMaxOut; ++o) out[o] += spart[(q * kPolRows + row) * kPolMaxOut + o];
+        for (int o = 0; o < MX; ++o) out[o] += spart[(q * kPolRows + row) * kPolMaxOut + o];
 
     // ---- outputs
     float v = 0.f;                              // out[n_out], selected without dynamic register indexing
 #pragma unroll
-    for (int o = 0; o < kPolMaxOut; ++o) if (o == pp.n_out) v = out[o];
+    for (int o = 0; o < MX; ++o) if (o == pp.n_out) v = out[o];
     io.value[env] = v;
     if (io.logits) {
 #pragma unroll
-        for (int o = 0; o < kPolMaxOut; ++o) if (o < nout1) io.logits[(size_t)env * nout1 + o] = out[o];
+        for (int o = 0; o < MX; ++o) if (o < nout1) io.logits[(size_t)env * nout1 + o] = out[o];
     }
     if (!io.sample) return;
     const unsigned ctr = pp.counters[env];
@@ -238,15 +242,15 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_act_kernel(PolicyParams
         // log-softmax + Gumbel-max
         float mx = -INFINITY;
 #pragma unroll
-        for (int o = 0; o < kPolMaxOut; ++o) if (o < pp.n_out) mx = fmaxf(mx, out[o]);
+        for (int o = 0; o < MX; ++o) if (o < pp.n_out) mx = fmaxf(mx, out[o]);
         float se = 0.f;
 #pragma unroll
-        for (int o = 0; o < kPolMaxOut; ++o) if (o < pp.n_out) se += __expf(out[o] - mx);
+        for (int o = 0; o < MX; ++o) if (o < pp.n_out) se += __expf(out[o] - mx);
         const float lse = mx + __logf(se);
         float best = -INFINITY, best_l = 0.f;
         int arg = 0;
 #pragma unroll
-        for (int o = 0; o < kPolMaxOut; ++o) {
+        for (int o = 0; o < MX; ++o) {
             if (o < pp.n_out) {
                 const float u = pol_uniform(pp.seed, (unsigned)env, ctr, (unsigned)o);
                 const float g = out[o] - __logf(-__logf(u));
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kPolThreads, 1) policy_act_kernel(PolicyParams
     } else {
         float lp = 0.f;
 #pragma unroll
-        for (int o = 0; o < kPolMaxOut; ++o) {
+        for (int o = 0; o < MX; ++o) {
             if (o < pp.n_out) {
                 const float u1 = pol_uniform(pp.seed, (unsigned)env, ctr, (unsigned)(2 * o));
                 const float u2 = pol_uniform(pp.seed, (unsigned)env, ctr, (unsigned)(2 * o + 1));
