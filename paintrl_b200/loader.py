@@ -455,6 +455,11 @@ class Flat(object):
         out = np.full(n, -1, dtype=np.int64)
         if m == 0:
             return out
+        chunk = max(1, (1 << 22) // m)               # about 4 M (point, triangle) pairs at a time
+        if n > chunk:
+            for at in range(0, n, chunk):
+                out[at:at + chunk] = self.first_containing(points[at:at + chunk])
+            return out
         v2x = points[:, None, 0] - self.a[None, :, 0]
         v2y = points[:, None, 1] - self.a[None, :, 1]
         d20 = v2x * self.v0[None, :, 0] + v2y * self.v0[None, :, 1]

@@ -31,6 +31,7 @@ PART_DICT = {
 }
 
 START_POINT_MODES = ('fixed', 'anchor', 'edge', 'all')
+_LOADED = {}      # packs built by loader.load_part in this process: (urdf path, mtime) -> PartPack
 
 
 class PartPack(object):
@@ -87,7 +88,10 @@ class PartPack(object):
                 'no stored part pack for Part_NO=%d (%s) and no URDF to build one from (%s): pass urdf_root= / set '
                 'PAINTRL_URDF_ROOT to the directory that holds urdf/painting/%s' % (part_no, name, urdf, PART_DICT[part_no][0]))
         from . import loader
-        pack = loader.load_part(urdf, device=device)
+        key = (os.path.realpath(urdf), os.path.getmtime(urdf))
+        pack = _LOADED.get(key)
+        if pack is None:                      # one load per part and process (1-7 s)
+            pack = _LOADED[key] = loader.load_part(urdf, device=device)
         if (pack.width, pack.height) != (width, height):
             pack = pack.retextured(width, height, device=device)
         return pack
