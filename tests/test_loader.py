@@ -170,3 +170,41 @@ def test_loaded_pack_steps_like_the_oracle(case, cuda_device):
     }[case]
     episodes = _run_case(extra, kw, 48, 45, cuda_device, pack=pack)
     assert episodes > 0
+
+
+def test_load_part_error_paths(tmp_path):
+    # a URDF whose mesh has no MTL / texture: the reference's own message (bullet_paint_wrapper.py:1331)
+    (tmp_path / 'raw.obj').write_text('v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n')
+    urdf = tmp_path / 'raw.urdf'
+    urdf.write_text('<robot name="r"><link name="l"><visual><geometry><mesh filename="raw.obj"/></geometry></visual></link></robot>')
+    with pytest.raises(FileNotFoundError, match='processed by Blender'):
+        loader.load_part(str(urdf), max_points=1, part_no=0, rasterizer=oracle_rasterizer)
+    # a part that is not in Part_Dict needs its max-points value
+    with pytest.raises(ValueError, match='max_points'):
+        loader.load_part(BULGE_URDF, rasterizer=oracle_rasterizer)
+    # no stored pack and no URDF root: the error says what to pass
+    with pytest.raises(FileNotFoundError, match='urdf_root'):
+        PartPack.for_part(2, urdf_root=str(tmp_path))
+
+
+def test_silhouette_march_rejects_bad_arguments():
+    """Argument checks of `paintrl_silhouette_march` come before any CUDA call: testable without a GPU (-1 = PAINTRL_E_INVALID)."""
+    import ctypes
+    from paintrl_b200 import _capi
+    lib = _capi.lib()
+    n = np.array([[1.0, 0.0, 0.0]])
+    off = np.array([1.0])
+    pts = np.zeros((1, 3))
+    mins = np.zeros(1, dtype=np.int8)
+    out_b, out_f = np.zeros(1), np.zeros(1, dtype=np.int8)
+    args = [n.ctypes.data, off.ctypes.data, 1, pts.ctypes.data, mins.ctypes.data, 1, 1, 0, 10, 0, out_b.ctypes.data, out_f.ctypes.data]
+    bad_axes = list(args)
+    bad_axes[6], bad_axes[7] = 2, 2                       # proof axis == non-principal axis
+    assert lib.paintrl_silhouette_march(*bad_axes) == -1
+    null_out = list(args)
+    null_out[10] = None
+    assert lib.paintrl_silhouette_march(*null_out) == -1
+    no_planes = list(args)
+    no_planes[2] = 0
+    assert lib.paintrl_silhouette_march(*no_planes) == -1
+    assert b'plane' in lib.paintrl_last_error() or b'null' in lib.paintrl_last_error()
